@@ -1,0 +1,890 @@
+// K2/K3: per-agent destination force, force assembly, rider control and bicycle
+// dynamics for every model class -- one thread per agent, state in registers.
+//
+// Reference (src/cyclistsocialforce/):
+//   Vehicle.updateDestination        vehicle.py:545-594
+//   Vehicle.updateNavState           vehicle.py:354-457
+//   TwoDBicycle.calcDestinationForce vehicle.py:1416-1558   (FITPACK splprep/splev restated)
+//   Bicycle.calcDestinationForceField / calc_direct_approach_dest_force  :1150-1187, :2078-2108
+//   calc_forces (per-agent tail)     intersection.py:841-862,  utils.limitMagnitude utils.py:56-86
+//   Bicycle.control / move           vehicle.py:1218-1272
+//   TwoDBicycle.step                 vehicle.py:1386-1414
+//   InvPendulumBicycle.step*         vehicle.py:1738-1950, parameters.py:1832-1892
+//   BalancingRiderDynamics.step      dynamics.py:602-705,  from_pole_placement :1167-1227
+//   PlanarPointDynamics.step         dynamics.py:996-1079
+#include "csf_common.cuh"
+
+namespace {
+
+enum { MODE_FORCES = 0, MODE_ADVANCE = 1, MODE_STEP = 2 };
+
+// ----------------------------------------------------------------------------------------
+// per-agent register image
+// ----------------------------------------------------------------------------------------
+template <typename T> struct Agent {
+    double x, y;
+    T psi, v, delta, theta;
+    T vd_def;
+    int i;            // Vehicle.i
+    int ptr, qlen;    // destination pointer / queue length
+    int znav;         // bit0 go, bit1 decel, bit2 arrived
+    T z_v0, z_d0, z_d1;
+    const double* q;  // this agent's destination queue [q_cap][3]
+    int flags;        // status bits raised by this agent
+};
+
+template <typename T> __device__ __forceinline__ T dist_to(const Agent<T>& a, int idx) {
+    const T dx = (T)(a.q[idx * 3 + 0] - a.x), dy = (T)(a.q[idx * 3 + 1] - a.y);
+    return sqrt(dx * dx + dy * dy);
+}
+
+// Vehicle.updateDestination, vehicle.py:545-594
+template <typename T> __device__ void update_destination(Agent<T>& a, const CsfAgentParams& p) {
+    const T dnext = dist_to(a, a.ptr);
+    if (a.znav & 6) return;
+    if (dnext <= (T)p.d_arrived_inter) a.ptr = min(a.ptr + 1, a.qlen - 1);
+    if (a.ptr < a.qlen - 1) {
+        const T dnn = dist_to(a, a.ptr + 1);
+        if (dnn < dnext) a.ptr += 1;
+    }
+}
+
+// Vehicle.updateNavState, vehicle.py:354-457 -> v_d ; *ddest_out = distance to destination
+template <typename T> __device__ T update_nav_state(Agent<T>& a, const CsfAgentParams& p, bool stop, T* ddest_out) {
+    const T k = (T)1.5;
+    const bool z0 = a.znav & 1, z1 = a.znav & 2, z2 = a.znav & 4;
+    const T vhd = (T)p.v_max_harddecel;
+    T d0, d1;
+    if (z0) {
+        d0 = (T)0.5 * (vhd * vhd - a.v * a.v) / (T)p.a_desired[0];
+        d1 = (T)0.5 * -(vhd * vhd) / (T)p.a_max[0];
+    } else {
+        d0 = a.z_d0;
+        d1 = a.z_d1;
+    }
+    const T dd = dist_to(a, a.ptr);
+    const bool x0 = stop, x1 = dd <= k * (d0 + d1), x2 = dd <= (T)p.d_arrived_stop, x3 = a.v <= (T)p.v_max_stop;
+    const bool n0 = !x0 || (x0 && !x1 && ((z0 && !x2) || z1));
+    const bool n1 = x0 && ((z0 && ((!x2 && x1) || (x2 && !x3))) || (z1 && x1 && (!x2 || !x3)));
+    const bool n2 = x0 && (((z0 || z1) && x2 && x3) || z2);
+    a.znav = (n0 ? 1 : 0) | (n1 ? 2 : 0) | (n2 ? 4 : 0);
+    if (z0 && n1) {
+        a.z_v0 = a.v;
+        a.z_d0 = d0;
+        a.z_d1 = d1;
+    }
+    *ddest_out = dd;
+    T vd;
+    if (n0) vd = a.vd_def;
+    else if (n1) {
+        if (dd < k * a.z_d1) vd = vhd / a.z_d1 * dd * (T)1 / k;
+        else vd = (a.z_v0 - vhd) / a.z_d0 * (dd - a.z_d1) * (T)1 / k + vhd;
+    } else if (n2) vd = (T)0;
+    else {
+        vd = (T)0;
+        a.flags |= 2;  // reference raises "Invalid navigation state"
+    }
+    return vd;
+}
+
+// Bicycle.calcDestinationForceField (vehicle.py:1168-1187) == calc_direct_approach_dest_force (:2096-2108)
+template <typename T> __device__ void dest_force_direct(Agent<T>& a, const CsfAgentParams& p, T& fx, T& fy) {
+    update_destination(a, p);
+    const double* d = a.q + a.ptr * 3;
+    T dd;
+    const T vd = update_nav_state(a, p, d[2] != 0.0, &dd);
+    if (dd > (T)0) {
+        fx = -vd * (T)(a.x - d[0]) / dd;
+        fy = -vd * (T)(a.y - d[1]) / dd;
+    } else {
+        fx = (T)0;
+        fy = (T)0;
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// interpolating parametric cubic B-spline through m in {4,5,6} points
+// (scipy.interpolate.splprep(s=0)/splev == FITPACK parcur/fppara/splev/splder)
+// ----------------------------------------------------------------------------------------
+template <typename T> struct Spline {
+    int m;
+    T t4, t5;       // interior knots (u_2, u_3) where present
+    T cx[6], cy[6]; // B-spline coefficients
+};
+template <typename T> __device__ __forceinline__ T knot(const Spline<T>& s, int i) {
+    if (i <= 3) return (T)0;
+    if (i >= s.m) return (T)1;
+    return i == 4 ? s.t4 : s.t5;
+}
+template <typename T> __device__ __forceinline__ T pick6(const T* c, int idx) {
+    T r = c[0];
+#pragma unroll
+    for (int q = 1; q < 6; ++q) r = (idx == q) ? c[q] : r;
+    return r;
+}
+// Cox-de Boor on knot interval l: cubic N3[0..3] (B_{l-3..l}), quadratic N2[0..2], linear N1[0..1]
+template <typename T>
+__device__ void bspline_basis(const Spline<T>& s, T u, int l, T* N3, T* N2, T* N1) {
+    T left[4], right[4], N[4];
+#pragma unroll
+    for (int j = 1; j <= 3; ++j) {
+        left[j] = u - knot(s, l + 1 - j);
+        right[j] = knot(s, l + j) - u;
+    }
+    N[0] = (T)1;
+#pragma unroll
+    for (int j = 1; j <= 3; ++j) {
+        T saved = (T)0;
+#pragma unroll
+        for (int r = 0; r < j; ++r) {
+            const T temp = N[r] / (right[r + 1] + left[j - r]);
+            N[r] = saved + right[r + 1] * temp;
+            saved = left[j - r] * temp;
+        }
+        N[j] = saved;
+        if (j == 1) { N1[0] = N[0]; N1[1] = N[1]; }
+        if (j == 2) { N2[0] = N[0]; N2[1] = N[1]; N2[2] = N[2]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) N3[j] = N[j];
+}
+template <typename T> __device__ __forceinline__ int spline_interval(const Spline<T>& s, T u) {
+    int l = 3;  // FITPACK splev: advance while u >= t[l+1] and l != m-1
+    if (l != s.m - 1 && u >= knot(s, 4)) l = 4;
+    if (l == 4 && l != s.m - 1 && u >= knot(s, 5)) l = 5;
+    return l;
+}
+// Fit: px,py = control points (relative coordinates); returns false on duplicate points.
+template <typename T> __device__ bool spline_fit(Spline<T>& s, const T* px, const T* py, int m) {
+    s.m = m;
+    T u[6];
+    u[0] = (T)0;
+    bool ok = true;
+#pragma unroll
+    for (int k = 1; k < 6; ++k) {
+        if (k < m) {
+            const T dx = px[k] - px[k - 1], dy = py[k] - py[k - 1];
+            const T d = sqrt(dx * dx + dy * dy);
+            ok = ok && (d > (T)0);
+            u[k] = u[k - 1] + d;
+        } else u[k] = u[k - 1];
+    }
+    const T tot = pick6(u, m - 1);
+#pragma unroll
+    for (int k = 1; k < 6; ++k) u[k] = (k < m - 1) ? u[k] / tot : (T)1;
+    s.t4 = u[2];
+    s.t5 = u[3];
+    if (!ok) return false;
+    // collocation system, dense 6x6 (rows/cols >= m are identity)
+    T A[6][6], bx[6], by[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) A[i][j] = (i == j) ? (T)1 : (T)0;
+        bx[i] = (i < m) ? px[i] : (T)0;
+        by[i] = (i < m) ? py[i] : (T)0;
+    }
+#pragma unroll
+    for (int i = 1; i < 5; ++i) {
+        if (i <= m - 2) {
+            const int l = min(i + 2, m - 1);
+            T N3[4], N2[3], N1[2];
+            bspline_basis(s, u[i], l, N3, N2, N1);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                T v = (T)0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) v = (j == l - 3 + r) ? N3[r] : v;
+                A[i][j] = v;
+            }
+        }
+    }
+    // Gaussian elimination without pivoting (B-spline collocation matrices are totally positive)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const T inv = (T)1 / A[k][k];
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) {
+            const T f = A[i][k] * inv;
+#pragma unroll
+            for (int j = k + 1; j < 6; ++j) A[i][j] -= f * A[k][j];
+            bx[i] -= f * bx[k];
+            by[i] -= f * by[k];
+        }
+    }
+#pragma unroll
+    for (int k = 5; k >= 0; --k) {
+        T sx = bx[k], sy = by[k];
+#pragma unroll
+        for (int j = k + 1; j < 6; ++j) {
+            sx -= A[k][j] * s.cx[j];
+            sy -= A[k][j] * s.cy[j];
+        }
+        const T inv = (T)1 / A[k][k];
+        s.cx[k] = sx * inv;
+        s.cy[k] = sy * inv;
+    }
+    return true;
+}
+// S(u) and optionally S'(u), S''(u)
+template <typename T>
+__device__ void spline_eval(const Spline<T>& s, T u, bool der, T& x, T& y, T& dx, T& dy, T& ddx, T& ddy) {
+    const int l = spline_interval(s, u);
+    T N3[4], N2[3], N1[2];
+    bspline_basis(s, u, l, N3, N2, N1);
+    T cxl[4], cyl[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        cxl[r] = pick6(s.cx, l - 3 + r);
+        cyl[r] = pick6(s.cy, l - 3 + r);
+    }
+    x = y = (T)0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        x += N3[r] * cxl[r];
+        y += N3[r] * cyl[r];
+    }
+    if (!der) return;
+    T d1x[3], d1y[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const T w = (T)3 / (knot(s, l + 1 + r) - knot(s, l - 2 + r));
+        d1x[r] = w * (cxl[r + 1] - cxl[r]);
+        d1y[r] = w * (cyl[r + 1] - cyl[r]);
+    }
+    dx = N2[0] * d1x[0] + N2[1] * d1x[1] + N2[2] * d1x[2];
+    dy = N2[0] * d1y[0] + N2[1] * d1y[1] + N2[2] * d1y[2];
+    const T w0 = (T)2 / (knot(s, l + 1) - knot(s, l - 1)), w1 = (T)2 / (knot(s, l + 2) - knot(s, l));
+    ddx = N1[0] * (w0 * (d1x[1] - d1x[0])) + N1[1] * (w1 * (d1x[2] - d1x[1]));
+    ddy = N1[0] * (w0 * (d1y[1] - d1y[0])) + N1[1] * (w1 * (d1y[2] - d1y[1]));
+}
+
+// TwoDBicycle.calcDestinationForce, vehicle.py:1443-1558
+template <typename T>
+__device__ void dest_force_twod(Agent<T>& a, const CsfAgentParams& p, const CsfAgentState& st, int64_t k, T& fx,
+                                T& fy) {
+    update_destination(a, p);
+    const double* d = a.q + a.ptr * 3;
+    const bool stop = d[2] != 0.0;
+    T dd;
+    const T vd = update_nav_state(a, p, stop, &dd);
+    if (a.i == 0) {  // :1455-1458
+        T sn, cs;
+        sincosT(a.psi, &sn, &cs);
+        fx = vd * cs;
+        fy = vd * sn;
+        return;
+    }
+    if (a.znav & 4) {  // :1461-1462
+        fx = fy = (T)0;
+        return;
+    }
+    const bool last = a.ptr + 1 >= a.qlen;
+    // control points relative to the current position (index of the current position: 1 or 2)
+    T px[6], py[6];
+    int m, cur;
+    const T pvx = (T)(st.prev_x[k] - a.x), pvy = (T)(st.prev_y[k] - a.y);
+    if (!last) {  // [traj[i-1], traj[i], destqueue[ptr : ptr+4]]  :1468-1479
+        px[0] = pvx; py[0] = pvy;
+        px[1] = (T)0; py[1] = (T)0;
+        const int nd = min(4, a.qlen - a.ptr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int idx = min(a.ptr + j, a.qlen - 1);
+            px[2 + j] = (T)(a.q[idx * 3 + 0] - a.x);
+            py[2 + j] = (T)(a.q[idx * 3 + 1] - a.y);
+        }
+        m = 2 + nd;
+        cur = 1;
+    } else {  // [traj[max(0, i-100)], traj[i-1], traj[i], dest]  :1486-1492
+        const int back = min(a.i, p.hist_len);
+        const int hs = st.hist_step[k];
+        const int row = (hs - back) & (p.hist_cap - 1);
+        px[0] = (T)(st.hist_x[(size_t)row * st.n + k] - a.x);
+        py[0] = (T)(st.hist_y[(size_t)row * st.n + k] - a.y);
+        px[1] = pvx; py[1] = pvy;
+        px[2] = (T)0; py[2] = (T)0;
+        px[3] = (T)(d[0] - a.x); py[3] = (T)(d[1] - a.y);
+        px[4] = px[5] = py[4] = py[5] = (T)0;
+        m = 4;
+        cur = 2;
+    }
+    Spline<T> sp;
+    if (!spline_fit(sp, px, py, m)) {
+        a.flags |= 8;  // reference: FITPACK ValueError (duplicate points); here: direct approach
+        dest_force_direct(a, p, fx, fy);
+        return;
+    }
+    const T step = (T)1 / (T)19;
+    int i_s = 1;
+    T sx, sy, dx, dy, ddx, ddy;
+    if (last) {  // argmin over the 20 samples  :1516-1520
+        T best = (T)0;
+        for (int j = 0; j < 20; ++j) {
+            const T u = (j == 19) ? (T)1 : (T)j * step;
+            T x, y, t0, t1, t2, t3;
+            spline_eval(sp, u, false, x, y, t0, t1, t2, t3);
+            const T ex = x - px[cur], ey = y - py[cur];
+            const T d2 = ex * ex + ey * ey;
+            if (j == 0 || d2 < best) { best = d2; i_s = j; }
+        }
+    }
+    const int i_p = i_s + (stop ? 5 : 3);  // :1523-1526
+    if (i_p < 20) {
+        const T us = (i_s == 19) ? (T)1 : (T)i_s * step;
+        const T up = (i_p == 19) ? (T)1 : (T)i_p * step;
+        spline_eval(sp, us, true, sx, sy, dx, dy, ddx, ddy);
+        T qx, qy, t0, t1, t2, t3;
+        spline_eval(sp, up, false, qx, qy, t0, t1, t2, t3);
+        const T sp1 = sqrt(dx * dx + dy * dy);
+        const T R = sp1 * sp1 * sp1 / fabs(dx * ddy - dy * ddx);  // :1532-1537
+        const T thetacomf = (T)(10.0 * (CSF_TWO_PI / 360.0));
+        T v = fmax((T)2.5, sqrt(thetacomf * (T)p.g * R));
+        v = fmin(v, vd);
+        const T ex = qx - sx, ey = qy - sy;
+        const T temp = v / sqrt(ex * ex + ey * ey);
+        fx = temp * ex;
+        fy = temp * ey;
+    } else {
+        dest_force_direct(a, p, fx, fy);  // :1556
+    }
+}
+
+template <typename T, int MODEL>
+__device__ void destination_force(Agent<T>& a, const CsfAgentParams& p, const CsfAgentState& st, int64_t k, T& fx,
+                                  T& fy) {
+    if (MODEL == CSF_MODEL_TWOD || MODEL == CSF_MODEL_INVPENDULUM) dest_force_twod(a, p, st, k, fx, fy);
+    else if (MODEL == CSF_MODEL_BICYCLE) dest_force_direct(a, p, fx, fy);              // vehicle.py:1189-1194
+    else if (MODEL == CSF_MODEL_BALANCINGRIDER) {
+        update_destination(a, p);                                                      // vehicle.py:295-297
+        dest_force_direct(a, p, fx, fy);
+    } else {                                                                           // planarpoint
+        update_destination(a, p);                                                      // vehicle.py:295-297
+        dest_force_twod(a, p, st, k, fx, fy);                                          // vehicle.py:2025
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// Bicycle.control + move, vehicle.py:1218-1272
+// ----------------------------------------------------------------------------------------
+template <typename T> __device__ void control_move(Agent<T>& a, const CsfAgentParams& p, T Fx, T Fy) {
+    const T th = atan2(Fy, Fx);
+    T vF = sqrt(Fx * Fx + Fy * Fy);
+    const T dd = dist_to(a, a.ptr);
+    if (dd < (T)3 && (a.ptr + 1 >= a.qlen)) vF = (vF / (T)3) * dd;
+    const T target = angle_difference(a.psi, th);
+    const T ddelta = angle_difference(a.delta, target);
+    T acc = (T)p.k_p_v * (vF - a.v);
+    const T od = (T)p.k_p_delta * ddelta;
+    const T ts = (T)p.t_s;
+    acc = clampT(acc, (T)p.a_max[0], (T)p.a_max[1]);
+    T delta = limit_angle(a.delta + ts * od);
+    T v = a.v + ts * acc;
+    delta = clampT(delta, (T)-p.delta_max, (T)p.delta_max);
+    v = clampT(v, (T)p.v_max_riding[0], (T)p.v_max_riding[1]);
+    const T psi = limit_angle(a.psi + ts * v * tan(delta) / (T)p.l);
+    T sn, cs;
+    sincosT(psi, &sn, &cs);
+    a.y += (double)(ts * v * sn);
+    a.x += (double)(ts * v * cs);
+    a.psi = psi;
+    a.v = v;
+    a.delta = delta;
+}
+
+// ----------------------------------------------------------------------------------------
+// small dense double-precision linear algebra (per-agent, local arrays)
+// ----------------------------------------------------------------------------------------
+template <int N> __device__ void mat_mul(const double* A, const double* B, double* C) {
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < N; ++k) s = fma(A[i * N + k], B[k * N + j], s);
+            C[i * N + j] = s;
+        }
+}
+// E = exp(M) for the 6x6 augmented matrix [[A_c t, B_c t],[0,0]]: degree-13 Pade approximant with
+// scaling and squaring (Higham 2005, the algorithm behind scipy.linalg.expm that the reference
+// reaches through control.forced_response, vehicle.py:1835-1842).
+__device__ void expm6(const double* Min, double* E) {
+    constexpr int N = 6;
+    const double b[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800.,
+                          129060195264000.,   10559470521600.,    670442572800.,     33522128640.,
+                          1323241920.,        40840800.,          960960.,           16380.,
+                          182.,               1.};
+    double nrm = 0.0;
+    for (int j = 0; j < N; ++j) {
+        double c = 0.0;
+        for (int i = 0; i < N; ++i) c += fabs(Min[i * N + j]);
+        nrm = fmax(nrm, c);
+    }
+    int s = 0;
+    double sc = 1.0;
+    while (nrm * sc > 5.371920351148152 && s < 60) { sc *= 0.5; ++s; }
+    double A[N * N], A2[N * N], A4[N * N], A6[N * N], U[N * N], V[N * N], W[N * N];
+    for (int i = 0; i < N * N; ++i) A[i] = Min[i] * sc;
+    mat_mul<N>(A, A, A2);
+    mat_mul<N>(A2, A2, A4);
+    mat_mul<N>(A4, A2, A6);
+    for (int i = 0; i < N * N; ++i) W[i] = b[13] * A6[i] + b[11] * A4[i] + b[9] * A2[i];
+    mat_mul<N>(A6, W, V);  // V as scratch
+    for (int i = 0; i < N * N; ++i)
+        W[i] = V[i] + b[7] * A6[i] + b[5] * A4[i] + b[3] * A2[i] + ((i % (N + 1) == 0) ? b[1] : 0.0);
+    mat_mul<N>(A, W, U);
+    for (int i = 0; i < N * N; ++i) W[i] = b[12] * A6[i] + b[10] * A4[i] + b[8] * A2[i];
+    mat_mul<N>(A6, W, V);
+    for (int i = 0; i < N * N; ++i)
+        V[i] += b[6] * A6[i] + b[4] * A4[i] + b[2] * A2[i] + ((i % (N + 1) == 0) ? b[0] : 0.0);
+    // solve (V - U) R = (V + U): P := V - U, Q := V + U (in A2, A4), partial pivoting
+    double* P = A2;
+    double* Q = A4;
+    for (int i = 0; i < N * N; ++i) { P[i] = V[i] - U[i]; Q[i] = V[i] + U[i]; }
+    for (int k = 0; k < N; ++k) {
+        int piv = k;
+        double best = fabs(P[k * N + k]);
+        for (int i = k + 1; i < N; ++i)
+            if (fabs(P[i * N + k]) > best) { best = fabs(P[i * N + k]); piv = i; }
+        if (piv != k)
+            for (int j = 0; j < N; ++j) {
+                double t = P[k * N + j]; P[k * N + j] = P[piv * N + j]; P[piv * N + j] = t;
+                t = Q[k * N + j]; Q[k * N + j] = Q[piv * N + j]; Q[piv * N + j] = t;
+            }
+        const double inv = 1.0 / P[k * N + k];
+        for (int i = k + 1; i < N; ++i) {
+            const double f = P[i * N + k] * inv;
+            for (int j = k; j < N; ++j) P[i * N + j] -= f * P[k * N + j];
+            for (int j = 0; j < N; ++j) Q[i * N + j] -= f * Q[k * N + j];
+        }
+    }
+    for (int k = N - 1; k >= 0; --k) {
+        const double inv = 1.0 / P[k * N + k];
+        for (int j = 0; j < N; ++j) {
+            double t = Q[k * N + j];
+            for (int i = k + 1; i < N; ++i) t -= P[k * N + i] * E[i * N + j];
+            E[k * N + j] = t * inv;
+        }
+    }
+    for (int q = 0; q < s; ++q) {
+        mat_mul<N>(E, E, W);
+        for (int i = 0; i < N * N; ++i) E[i] = W[i];
+    }
+}
+// solve A x = b (5x5, partial pivoting), A destroyed
+__device__ void solve5(double* A, double* b, double* x) {
+    constexpr int N = 5;
+    for (int k = 0; k < N; ++k) {
+        int piv = k;
+        double best = fabs(A[k * N + k]);
+        for (int i = k + 1; i < N; ++i)
+            if (fabs(A[i * N + k]) > best) { best = fabs(A[i * N + k]); piv = i; }
+        if (piv != k) {
+            for (int j = 0; j < N; ++j) { double t = A[k * N + j]; A[k * N + j] = A[piv * N + j]; A[piv * N + j] = t; }
+            double t = b[k]; b[k] = b[piv]; b[piv] = t;
+        }
+        const double inv = 1.0 / A[k * N + k];
+        for (int i = k + 1; i < N; ++i) {
+            const double f = A[i * N + k] * inv;
+            for (int j = k; j < N; ++j) A[i * N + j] -= f * A[k * N + j];
+            b[i] -= f * b[k];
+        }
+    }
+    for (int k = N - 1; k >= 0; --k) {
+        double s = b[k];
+        for (int j = k + 1; j < N; ++j) s -= A[k * N + j] * x[j];
+        x[k] = s / A[k * N + k];
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// InvPendulumBicycle, vehicle.py:1738-1950 (dynamics in double in both builds)
+// ----------------------------------------------------------------------------------------
+__device__ void invpend_yaw_step(const CsfAgentParams& p, double v, double psi_d, double* x /*[5]*/) {
+    // open loop (:1738-1768) with time-varying K, K tau_2, tau_3 (parameters.py:1850-1855)
+    const double l = p.l;
+    const double K_tau_2 = (v * p.l_2) / (p.g * l), K = (v * v) / (p.g * l), tau_3 = l / v;
+    const double iv = 1.0 / v;
+    const double vd[4] = {1.0, iv, iv * iv, iv * iv * iv};
+    double kx[5], ku = 0.0;
+    for (int r = 0; r < 5; ++r) {
+        kx[r] = 0.0;
+        for (int c = 0; c < 4; ++c) kx[r] += p.kx_table[r][c] * vd[c];
+    }
+    for (int c = 0; c < 4; ++c) ku += p.ku_table[c] * vd[c];
+    const double bI = 1.0 / p.i_steer;
+    const double ts = p.t_s;
+    double Mx[36];
+    for (int i = 0; i < 36; ++i) Mx[i] = 0.0;
+    // A_c = A - B K_x ; B_c = K_u B  (rows scaled by t_s)
+    Mx[0 * 6 + 1] = ts;
+    for (int c = 0; c < 5; ++c) Mx[1 * 6 + c] = -bI * kx[c] * ts;
+    Mx[1 * 6 + 1] += (-p.c_steer * bI) * ts;
+    Mx[1 * 6 + 5] = ku * bI * ts;
+    Mx[2 * 6 + 3] = ts;
+    Mx[3 * 6 + 0] = -K / p.tau_1_squared * ts;
+    Mx[3 * 6 + 1] = -K_tau_2 / p.tau_1_squared * ts;
+    Mx[3 * 6 + 2] = 1.0 / p.tau_1_squared * ts;
+    Mx[4 * 6 + 0] = 1.0 / tau_3 * ts;
+    double E[36];
+    expm6(Mx, E);
+    double xn[5];
+    for (int r = 0; r < 5; ++r) {
+        double s = E[r * 6 + 5] * psi_d;
+        for (int c = 0; c < 5; ++c) s = fma(E[r * 6 + c], x[c], s);
+        xn[r] = s;
+    }
+    for (int r = 0; r < 5; ++r) x[r] = xn[r];
+}
+
+// ----------------------------------------------------------------------------------------
+// BalancingRiderBicycle gain design: Ackermann's formula == ct.place for a single input
+// (dynamics.py:602-615, :1205-1209).  K = e_n^T C^-1 phi(A)
+// ----------------------------------------------------------------------------------------
+__device__ void br_matrix(const CsfAgentParams& p, double v, double* A) {
+    for (int i = 0; i < 25; ++i) A[i] = p.br_A0[i] + v * p.br_A1[i] + v * v * p.br_A2[i];
+}
+__device__ void br_gains(const CsfAgentParams& p, double v, double* K) {
+    constexpr int N = 5;
+    double A[25], T1[25], T2[25], Phi[25];
+    br_matrix(p, v, A);
+    double f[5];
+    for (int i = 0; i < 5; ++i) f[i] = p.br_pole_icpt[i] + p.br_pole_coef[i] * v;
+    // phi(A) = (A - p0 I) (A^2 - 2 re1 A + |p1|^2 I) (A^2 - 2 re2 A + |p2|^2 I)
+    double A2[25];
+    mat_mul<N>(A, A, A2);
+    for (int i = 0; i < 25; ++i) Phi[i] = A[i] - ((i % 6 == 0) ? f[0] : 0.0);
+    for (int q = 0; q < 2; ++q) {
+        const double re = f[1 + 2 * q], im = f[2 + 2 * q];
+        for (int i = 0; i < 25; ++i) T1[i] = A2[i] - 2.0 * re * A[i] + ((i % 6 == 0) ? (re * re + im * im) : 0.0);
+        mat_mul<N>(Phi, T1, T2);
+        for (int i = 0; i < 25; ++i) Phi[i] = T2[i];
+    }
+    // controllability matrix columns b, Ab, ..., A^4 b
+    double C[25], col[5], nxt[5];
+    for (int i = 0; i < 5; ++i) col[i] = p.br_B[i];
+    for (int c = 0; c < 5; ++c) {
+        for (int i = 0; i < 5; ++i) C[i * 5 + c] = col[i];
+        for (int i = 0; i < 5; ++i) {
+            double s = 0.0;
+            for (int j = 0; j < 5; ++j) s = fma(A[i * 5 + j], col[j], s);
+            nxt[i] = s;
+        }
+        for (int i = 0; i < 5; ++i) col[i] = nxt[i];
+    }
+    // w^T = e_5^T C^-1  <=>  C^T w = e_5
+    double Ct[25], e[5] = {0, 0, 0, 0, 1}, w[5];
+    for (int i = 0; i < 5; ++i)
+        for (int j = 0; j < 5; ++j) Ct[i * 5 + j] = C[j * 5 + i];
+    solve5(Ct, e, w);
+    for (int j = 0; j < 5; ++j) {
+        double s = 0.0;
+        for (int i = 0; i < 5; ++i) s = fma(w[i], Phi[i * 5 + j], s);
+        K[j] = s;
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// the per-agent kernel
+// ----------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T ldT(const void* p, int64_t k) { return reinterpret_cast<const T*>(p)[k]; }
+template <typename T> __device__ __forceinline__ void stT(void* p, int64_t k, T v) { reinterpret_cast<T*>(p)[k] = v; }
+
+template <typename T, int MODEL, int MODE>
+__global__ void __launch_bounds__(128) agent_kernel(CsfAgentState st, CsfAgentParams p, int64_t n_total,
+                                                    const T* __restrict__ frep, const T* __restrict__ froad,
+                                                    T* __restrict__ force, T* __restrict__ fdest_out,
+                                                    void* __restrict__ next_xycs) {
+    const int64_t k = st.first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= st.first + st.count) return;
+    Agent<T> a;
+    a.x = st.x[k];
+    a.y = st.y[k];
+    a.psi = ldT<T>(st.psi, k);
+    a.v = ldT<T>(st.v, k);
+    a.delta = (MODEL != CSF_MODEL_PLANARPOINT) ? ldT<T>(st.delta, k) : (T)0;
+    a.theta = (MODEL == CSF_MODEL_INVPENDULUM || MODEL == CSF_MODEL_BALANCINGRIDER) ? ldT<T>(st.theta, k) : (T)0;
+    a.vd_def = ldT<T>(st.vd_default, k);
+    a.i = st.step_i[k];
+    a.ptr = st.dest_ptr[k];
+    a.qlen = st.dest_len[k];
+    a.znav = st.znav[k];
+    a.z_v0 = ldT<T>(st.znav_v0, k);
+    a.z_d0 = ldT<T>(st.znav_d0, k);
+    a.z_d1 = ldT<T>(st.znav_d1, k);
+    a.q = st.destq + (size_t)k * p.q_cap * 3;
+    a.flags = 0;
+
+    T Fx, Fy;
+    if (MODE != MODE_ADVANCE) {
+        // ---- K2: destination force + assembly (intersection.py:797-799, :841-862) ----
+        T fdx, fdy;
+        destination_force<T, MODEL>(a, p, st, k, fdx, fdy);
+        T frx = (T)0, fry = (T)0;
+        if (n_total > 1 && frep != nullptr) {
+            frx = frep[k * 2];
+            fry = frep[k * 2 + 1];
+            const T rin = sqrt(frx * frx + fry * fry), r = sqrt(fdx * fdx + fdy * fdy);
+            if (rin > r) {  // utils.limitMagnitude, utils.py:79-84
+                frx = frx * r / rin;
+                fry = fry * r / rin;
+            }
+        }
+        Fx = frx + fdx;
+        Fy = fry + fdy;
+        if (froad != nullptr) {
+            Fx += froad[k * 2];
+            Fy += froad[k * 2 + 1];
+        }
+        if (force != nullptr) { force[k * 2] = Fx; force[k * 2 + 1] = Fy; }
+        if (fdest_out != nullptr) { fdest_out[k * 2] = fdx; fdest_out[k * 2 + 1] = fdy; }
+        st.dest_ptr[k] = a.ptr;
+        st.znav[k] = a.znav;
+        stT<T>(st.znav_v0, k, a.z_v0);
+        stT<T>(st.znav_d0, k, a.z_d0);
+        stT<T>(st.znav_d1, k, a.z_d1);
+        if (!(isfinite((double)Fx) && isfinite((double)Fy))) a.flags |= 1;
+    } else {
+        Fx = force[k * 2];
+        Fy = force[k * 2 + 1];
+    }
+
+    if (MODE != MODE_FORCES) {
+        // ---- K3: rider control + dynamics ----
+        const double ox = a.x, oy = a.y;
+        bool wrap = true;
+        if (MODEL == CSF_MODEL_TWOD || MODEL == CSF_MODEL_BICYCLE) {
+            if (MODEL == CSF_MODEL_TWOD && (a.znav & 4)) {  // vehicle.py:1397-1398
+                a.v = (T)0;
+                a.delta = (T)0;
+            } else control_move(a, p, Fx, Fy);
+        } else if (MODEL == CSF_MODEL_INVPENDULUM) {
+            // updateRidingState, vehicle.py:1932-1950
+            int zr = st.ip_zrid[k];
+            const int run = st.ip_delta_run[k];
+            const bool cvwalk = a.v < (T)p.v_max_walk;
+            const bool cdelta = run >= min(a.i, p.hist_len) + 1;
+            const bool ride = !cvwalk && (((zr & 2) && cdelta) || (zr & 1));
+            zr = ride ? 1 : 2;
+            st.ip_zrid[k] = zr;
+            double xs[5];
+            for (int r = 0; r < 5; ++r) xs[r] = st.ip_x[(size_t)r * st.n + k];
+            if (a.znav & 4) {  // :1898-1899
+                a.v = (T)0; a.delta = (T)0; a.theta = (T)0;
+            } else if (ride) {
+                // step_pos (:1850-1881): P-controlled speed, Euler position with the OLD psi
+                const T vdF = sqrt(Fx * Fx + Fy * Fy);
+                const T acc = clampT((T)p.k_p_v * (vdF - a.v), (T)p.a_max[0], (T)p.a_max[1]);
+                const T v = clampT(a.v + (T)p.t_s * acc, (T)p.v_max_riding[0], (T)p.v_max_riding[1]);
+                T sn, cs;
+                sincosT(a.psi, &sn, &cs);
+                a.y += (double)((T)p.t_s * v * sn);
+                a.x += (double)((T)p.t_s * v * cs);
+                a.v = v;
+                // step_yaw (:1810-1848) with the updated speed
+                invpend_yaw_step(p, (double)a.v, (double)atan2(Fy, Fx), xs);
+                a.psi = (T)limit_angle(xs[4]);
+                a.delta = (T)limit_angle(xs[0]);
+                a.theta = (T)limit_angle(xs[2]);
+            } else {  // walking, :1905-1916
+                a.v = (T)p.v_max_walk;
+                a.theta = (T)0;
+                control_move(a, p, Fx, Fy);
+                xs[0] = (double)a.delta; xs[1] = 0.0; xs[2] = (double)a.theta; xs[3] = 0.0; xs[4] = (double)a.psi;
+            }
+            for (int r = 0; r < 5; ++r) st.ip_x[(size_t)r * st.n + k] = xs[r];
+            const bool ok = fabs(a.delta) < (T)p.delta_max_walk;
+            // the window restarts when Vehicle.i wraps to 0 (traj[4, 0:i+1])
+            const int inew = (a.i + 1) % p.traj_len;
+            st.ip_delta_run[k] = ok ? ((inew == 0) ? 1 : run + 1) : 0;
+            stT<T>(st.theta, k, a.theta);
+        } else if (MODEL == CSF_MODEL_PLANARPOINT) {
+            // PlanarPointDynamics.step, dynamics.py:1051-1079 (closed-form implicit midpoint)
+            wrap = false;
+            const double vold = st.dyn_v[k];
+            const double vdF = sqrt((double)Fx * Fx + (double)Fy * Fy);
+            const double acc = clampT(p.k_p_v * (vdF - vold), p.a_max[0], p.a_max[1]);
+            const double v = clampT(vold + p.t_s * acc, p.v_max_riding[0], p.v_max_riding[1]);
+            const double vbar = 0.5 * (v + vold);  // vehicle.s[3] == dynamics.v in the reference
+            const double psi_c = limit_angle(atan2((double)Fy, (double)Fx));  // dynamics.py:112-121
+            const double h = p.t_s, kp = p.k_psi;
+            const double ps = st.dyn_x[k];
+            const double pn = ((1.0 - h * kp / 2) * ps + h * kp * psi_c) / (1.0 + h * kp / 2);
+            double sn, cs;
+            sincos(0.5 * (ps + pn), &sn, &cs);
+            a.x += h * vbar * cs;
+            a.y += h * vbar * sn;
+            st.dyn_x[k] = pn;
+            st.dyn_v[k] = v;
+            a.psi = (T)limit_angle(pn);
+            a.v = (T)v;
+        } else if (MODEL == CSF_MODEL_BALANCINGRIDER) {
+            // BalancingRiderDynamics.step, dynamics.py:674-705 (closed-form implicit midpoint)
+            wrap = false;
+            const double vold = st.dyn_v[k];
+            const double vdF = sqrt((double)Fx * Fx + (double)Fy * Fy);
+            const double acc = clampT(p.k_p_v * (vdF - vold), p.a_max[0], p.a_max[1]);
+            const double v = clampT(vold + p.t_s * acc, p.v_max_riding[0], p.v_max_riding[1]);
+            const double vbar = 0.5 * (v + vold);  // vehicle.s[3] == dynamics.v in the reference
+            double g[5], xb[5];
+            for (int r = 0; r < 5; ++r) xb[r] = st.dyn_x[(size_t)r * st.n + k];
+            if (v != vold) {  // :680-681
+                br_gains(p, vbar, g);
+                for (int r = 0; r < 5; ++r) st.br_gains[(size_t)r * st.n + k] = g[r];
+            } else
+                for (int r = 0; r < 5; ++r) g[r] = st.br_gains[(size_t)r * st.n + k];
+            const double psi_F = limit_angle(atan2(-(double)Fy, (double)Fx));  // :661-671
+            const double psi_c = xb[4] + angle_difference(xb[4], psi_F);
+            double A[25], L[25], rhs[5], xn[5];
+            br_matrix(p, vbar, A);
+            const double h = p.t_s;
+            for (int i = 0; i < 5; ++i)
+                for (int j = 0; j < 5; ++j) A[i * 5 + j] -= p.br_B[i] * g[j];  // A_c
+            for (int i = 0; i < 5; ++i) {
+                double s = h * p.br_B[i] * g[4] * psi_c;
+                for (int j = 0; j < 5; ++j) {
+                    L[i * 5 + j] = ((i == j) ? 1.0 : 0.0) - 0.5 * h * A[i * 5 + j];
+                    s += (((i == j) ? 1.0 : 0.0) + 0.5 * h * A[i * 5 + j]) * xb[j];
+                }
+                rhs[i] = s;
+            }
+            solve5(L, rhs, xn);
+            double sn, cs;
+            sincos(0.5 * (xb[4] + xn[4]), &sn, &cs);
+            // bike frame (N): p_x = x, p_y = -y   (dynamics.py:347-356, :389-397)
+            a.x += h * vbar * cs;
+            a.y -= h * vbar * sn;
+            for (int r = 0; r < 5; ++r) st.dyn_x[(size_t)r * st.n + k] = xn[r];
+            st.dyn_v[k] = v;
+            a.psi = (T)(-limit_angle(xn[4]));
+            a.v = (T)v;
+            a.delta = (T)(-limit_angle(xn[1]));
+            a.theta = (T)limit_angle(xn[0]);
+            stT<T>(st.theta, k, a.theta);
+            stT<T>(st.deltadot, k, (T)(-xn[3]));
+            stT<T>(st.thetadot, k, (T)xn[2]);
+        }
+        // ---- bookkeeping: Vehicle.i, traj ring (vehicle.py:1407-1410, :320-321) ----
+        a.i = a.i + 1;
+        if (wrap) a.i %= p.traj_len;
+        st.step_i[k] = a.i;
+        st.x[k] = a.x;
+        st.y[k] = a.y;
+        stT<T>(st.psi, k, a.psi);
+        stT<T>(st.v, k, a.v);
+        if (MODEL != CSF_MODEL_PLANARPOINT) stT<T>(st.delta, k, a.delta);
+        if (MODEL != CSF_MODEL_BALANCINGRIDER && MODEL != CSF_MODEL_BICYCLE) {
+            st.prev_x[k] = ox;
+            st.prev_y[k] = oy;
+            const int hs = st.hist_step[k] + 1;
+            st.hist_step[k] = hs;
+            const int row = hs & (p.hist_cap - 1);
+            st.hist_x[(size_t)row * st.n + k] = a.x;
+            st.hist_y[(size_t)row * st.n + k] = a.y;
+        }
+        if (!(isfinite(a.x) && isfinite(a.y) && isfinite((double)a.psi) && isfinite((double)a.v))) a.flags |= 1;
+        if (next_xycs != nullptr) {
+            int ovf = 0;
+            store_xycs<T>(next_xycs, st.payload_offset + k, a.x, a.y, a.psi, 1.0 / p.q_scale, &ovf);
+            if (ovf) a.flags |= 4;
+        }
+    }
+    if (a.flags && st.status != nullptr) atomicOr(st.status, a.flags);
+}
+
+template <typename T>
+__global__ void pack_state_kernel(CsfAgentState st, double inv_q, void* xycs) {
+    const int64_t k = st.first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= st.first + st.count) return;
+    int ovf = 0;
+    store_xycs<T>(xycs, st.payload_offset + k, st.x[k], st.y[k], ldT<T>(st.psi, k), inv_q, &ovf);
+    if (ovf && st.status != nullptr) atomicOr(st.status, 4);
+}
+template <typename T>
+__global__ void pack_xypsi_kernel(const double* x, const double* y, const double* psi, int64_t n, double inv_q,
+                                  void* xycs) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int ovf = 0;
+    store_xycs<T>(xycs, k, x[k], y[k], (T)psi[k], inv_q, &ovf);
+}
+
+template <typename T, int MODE>
+int launch_agent(int model, const CsfAgentState* st, const CsfAgentParams* p, int64_t n_total, const T* frep,
+                 const T* froad, T* force, T* fdest, void* next_xycs, cudaStream_t stream) {
+    if (st->count <= 0) return 0;
+    const unsigned grid = (unsigned)((st->count + 127) / 128);
+#define CSF_LAUNCH(MODEL)                                                                                      \
+    agent_kernel<T, MODEL, MODE><<<grid, 128, 0, stream>>>(*st, *p, n_total, frep, froad, force, fdest, next_xycs)
+    switch (model) {
+        case CSF_MODEL_TWOD: CSF_LAUNCH(CSF_MODEL_TWOD); break;
+        case CSF_MODEL_INVPENDULUM: CSF_LAUNCH(CSF_MODEL_INVPENDULUM); break;
+        case CSF_MODEL_BALANCINGRIDER: CSF_LAUNCH(CSF_MODEL_BALANCINGRIDER); break;
+        case CSF_MODEL_PLANARPOINT: CSF_LAUNCH(CSF_MODEL_PLANARPOINT); break;
+        case CSF_MODEL_BICYCLE: CSF_LAUNCH(CSF_MODEL_BICYCLE); break;
+        default:
+            csf_set_error("csf_agent_*: unknown model id", cudaErrorInvalidValue);
+            return -(int)cudaErrorInvalidValue;
+    }
+#undef CSF_LAUNCH
+    CSF_CHECK_LAUNCH("agent_kernel");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int csf_agent_forces_f32(int model, const CsfAgentState* st, const CsfAgentParams* p, int64_t n_total,
+                         const float* frep, const float* froad, float* force, float* fdest, csf_stream_t s) {
+    return launch_agent<float, MODE_FORCES>(model, st, p, n_total, frep, froad, force, fdest, nullptr, (cudaStream_t)s);
+}
+int csf_agent_forces_f64(int model, const CsfAgentState* st, const CsfAgentParams* p, int64_t n_total,
+                         const double* frep, const double* froad, double* force, double* fdest, csf_stream_t s) {
+    return launch_agent<double, MODE_FORCES>(model, st, p, n_total, frep, froad, force, fdest, nullptr, (cudaStream_t)s);
+}
+int csf_agent_advance_f32(int model, const CsfAgentState* st, const CsfAgentParams* p, const float* force,
+                          void* next_xycs, csf_stream_t s) {
+    return launch_agent<float, MODE_ADVANCE>(model, st, p, 0, nullptr, nullptr, const_cast<float*>(force), nullptr,
+                                             next_xycs, (cudaStream_t)s);
+}
+int csf_agent_advance_f64(int model, const CsfAgentState* st, const CsfAgentParams* p, const double* force,
+                          void* next_xycs, csf_stream_t s) {
+    return launch_agent<double, MODE_ADVANCE>(model, st, p, 0, nullptr, nullptr, const_cast<double*>(force), nullptr,
+                                              next_xycs, (cudaStream_t)s);
+}
+int csf_agent_step_f32(int model, const CsfAgentState* st, const CsfAgentParams* p, int64_t n_total,
+                       const float* frep, const float* froad, float* force, void* next_xycs, csf_stream_t s) {
+    return launch_agent<float, MODE_STEP>(model, st, p, n_total, frep, froad, force, nullptr, next_xycs, (cudaStream_t)s);
+}
+int csf_agent_step_f64(int model, const CsfAgentState* st, const CsfAgentParams* p, int64_t n_total,
+                       const double* frep, const double* froad, double* force, void* next_xycs, csf_stream_t s) {
+    return launch_agent<double, MODE_STEP>(model, st, p, n_total, frep, froad, force, nullptr, next_xycs, (cudaStream_t)s);
+}
+int csf_pack_xycs_f32(const CsfAgentState* st, const CsfAgentParams* p, void* xycs, csf_stream_t s) {
+    if (st->count <= 0) return 0;
+    pack_state_kernel<float><<<(unsigned)((st->count + 127) / 128), 128, 0, (cudaStream_t)s>>>(*st, 1.0 / p->q_scale, xycs);
+    CSF_CHECK_LAUNCH("pack_state_kernel");
+    return 0;
+}
+int csf_pack_xycs_f64(const CsfAgentState* st, const CsfAgentParams* p, void* xycs, csf_stream_t s) {
+    if (st->count <= 0) return 0;
+    pack_state_kernel<double><<<(unsigned)((st->count + 127) / 128), 128, 0, (cudaStream_t)s>>>(*st, 1.0, xycs);
+    CSF_CHECK_LAUNCH("pack_state_kernel");
+    return 0;
+}
+int csf_pack_xypsi_f32(const double* x, const double* y, const double* psi, int64_t n, double q_scale, void* xycs,
+                       csf_stream_t s) {
+    if (n <= 0) return 0;
+    pack_xypsi_kernel<float><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)s>>>(x, y, psi, n, 1.0 / q_scale, xycs);
+    CSF_CHECK_LAUNCH("pack_xypsi_kernel");
+    return 0;
+}
+int csf_pack_xypsi_f64(const double* x, const double* y, const double* psi, int64_t n, double q_scale, void* xycs,
+                       csf_stream_t s) {
+    (void)q_scale;
+    if (n <= 0) return 0;
+    pack_xypsi_kernel<double><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)s>>>(x, y, psi, n, 1.0, xycs);
+    CSF_CHECK_LAUNCH("pack_xypsi_kernel");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,489 @@
+// K1: all-pairs repulsive force (tiled N-body), road-edge force, FFMA peak probe.
+//
+// Replaces, per step, reference intersection.py:690-745 (FOV / priority mask),
+// :788-823 (pair loop), :841-843 (sum over sources) and
+// vehicle.py:1560-1648 (TwoDBicycle.calcRepulsiveForce).
+//
+// Formulation (trig-free; u = (target - source)/rho):
+//   c = u . h_i            s = u x h_i (signed)          h = (cos psi, sin psi)
+//   visible  <=>  -(u . h_j) >= cos(hfov/2)              [and (h_j x -u) <= 0 under p2r]
+//   s2 = sin^2(psi_i - psi_j);  A,B,e linear in s2
+//   sigma = A - B |sin(phi/2)|;  sigma' = -B |cos(phi/2)| sign(s)/2;  q^2 = 1-(e c)^2
+//   P = f0 exp(-rho q / sigma)
+//   F = P * unit( R(phi1) (q^2 sigma,  sign(s) [q^2 B sqrt((1+c)/2)/2 + e^2 |s| c sigma]) )
+// (the common positive factor P/(sigma^2 q) of (F_rho, F_phi) is dropped before
+// normalising, vehicle.py:1631-1646).  sigma is pre-divided by q_scale*log2(e) so
+// that the exponent is a bare ex2 of rho in payload units.
+//
+// Mapping: one thread owns TPT targets in registers; a dedicated producer warp
+// streams source tiles (16 B/source) into a multi-stage shared-memory ring with
+// 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx); 4 consumer warps
+// read each source once per warp as a broadcast LDS.128.  Work items are
+// (target block x source chunk); per-chunk partial sums are written to a
+// workspace and reduced in a fixed order (deterministic, no atomics).
+#include "csf_common.cuh"
+
+namespace {
+
+constexpr int kConsumerWarps = 4;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kThreads = kConsumerThreads + 32;  // + producer warp
+constexpr int kStages = 4;
+constexpr int kMaxChunks = 64;
+
+template <typename T> struct PairConst {
+    T sg0, sg1, sg2, sg3;  // sigma_0..3 / (q_scale * log2 e)
+    T e0, e1;
+    T ncosH;               // -cos(hfov/2); +2 if hfov/2 >= pi (always visible)
+    T tiny;                // guard added to rho^2 (coincident pair -> zero contribution)
+};
+
+template <typename T> struct Tgt;
+template <> struct Tgt<float> { int32_t xq, yq; float c, s; };
+template <> struct Tgt<double> { double x, y, c, s; };
+
+__device__ __forceinline__ void delta(const Xycs<float>& sr, const Tgt<float>& tg, float& dx, float& dy) {
+    dx = (float)(tg.xq - sr.xq);  // exact integer difference, then one rounding
+    dy = (float)(tg.yq - sr.yq);
+}
+__device__ __forceinline__ void delta(const Xycs<double>& sr, const Tgt<double>& tg, double& dx, double& dy) {
+    dx = tg.x - sr.x;
+    dy = tg.y - sr.y;
+}
+__device__ __forceinline__ float mulsign(float v, float s) {  // v * sign(s), s != 0
+    return __int_as_float(__float_as_int(v) ^ (__float_as_int(s) & 0x80000000));
+}
+__device__ __forceinline__ double mulsign(double v, double s) {
+    return __longlong_as_double(__double_as_longlong(v) ^ (__double_as_longlong(s) & 0x8000000000000000ll));
+}
+
+template <typename T, bool P2R>
+__device__ __forceinline__ void pair_eval(const Xycs<T>& sr, const Tgt<T>& tg, const PairConst<T>& k, T& ax, T& ay) {
+    T dx, dy;
+    delta(sr, tg, dx, dy);
+    const T r2 = fma(dy, dy, fma(dx, dx, k.tiny));
+    const T rinv = M<T>::rsqrt(r2);
+    const T ux = dx * rinv, uy = dy * rinv;
+    const T c = fma(uy, sr.s, ux * sr.c);
+    const T s = fma(-ux, sr.s, uy * sr.c);
+    const T t = fma(uy, tg.s, ux * tg.c);
+    bool vis = t <= k.ncosH;
+    if (P2R) vis = vis && (fma(tg.s, ux, -(tg.c * uy)) <= (T)0);
+    const T sr_ = fma(sr.s, tg.c, -(sr.c * tg.s));
+    const T s2 = sr_ * sr_;
+    const T A = fma(k.sg1, s2, k.sg0);
+    const T B = fma(k.sg3, s2, k.sg2);
+    const T e = fma(-k.e1, s2, k.e0);
+    // half angles |sin(phi/2)|, |cos(phi/2)| without the 1 -/+ c cancellation:
+    //   big = sqrt((1+|c|)/2),  small = |s| / (2 big);   (h1, h2) = c >= 0 ? (small, big) : (big, small)
+    const T hm = fma((T)0.5, fabs(c), (T)0.5);
+    const T rm = M<T>::rsqrt(hm);
+    const T hbig = hm * rm;
+    const T hsmall = fabs(s) * ((T)0.5 * rm);
+    const bool fwd = c >= (T)0;
+    const T h1 = fwd ? hsmall : hbig;
+    const T h2 = fwd ? hbig : hsmall;
+    const T sg = fma(-B, h1, A);
+    const T ec = e * c;
+    const T q2 = fma(-ec, ec, (T)1);
+    const T w = (e * fabs(s)) * ec;
+    const T mv = fma(w, sg, (T)0.5 * (q2 * (B * h2)));
+    const T grho = q2 * sg;
+    const T gphi = (s == (T)0) ? (T)0 : mulsign(mv, s);
+    const T ry = M<T>::rsqrt(grho * sg);
+    const T qs = q2 * ry;
+    const T rho = r2 * rinv;
+    const T P = M<T>::ex2(-(rho * qs));
+    const T rn = M<T>::rsqrt(fma(gphi, gphi, grho * grho));
+    const T sc = vis ? P * rn : (T)0;
+    const T a = sc * grho, b = sc * gphi;
+    ax = fma(a, ux, ax);
+    ax = fma(-b, uy, ax);
+    ay = fma(a, uy, ay);
+    ay = fma(b, ux, ay);
+}
+
+// ---- mbarrier / TMA bulk-copy primitives (sm_90+/sm_100a) --------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- the pair kernel -----------------------------------------------------------------
+// grid: persistent, item = blockIdx.x + k*gridDim.x over n_tblocks * n_chunks items;
+// item -> target block tb = item % n_tblocks, source chunk ch = item / n_tblocks.
+template <typename T, int TPT, int TILE, bool P2R>
+__global__ void __launch_bounds__(kThreads) pair_kernel(const Xycs<T>* __restrict__ src, int64_t n_src,
+                                                        const Xycs<T>* __restrict__ tgt, int64_t n_tgt,
+                                                        PairConst<T> k, T* __restrict__ partial, int chunk_tiles,
+                                                        int n_chunks, int n_tblocks) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Xycs<T>* tiles = reinterpret_cast<Xycs<T>*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * TILE * sizeof(Xycs<T>));
+    uint64_t* empty = full + kStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t n_items = (int64_t)n_tblocks * n_chunks;
+    const int64_t chunk_len = (int64_t)chunk_tiles * TILE;
+
+    if (warp == kConsumerWarps) {
+        // ===== producer warp: one lane streams tiles for every item of this CTA =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int64_t ch = item / n_tblocks;
+                const int64_t s_begin = ch * chunk_len;
+                const int64_t s_end = min(n_src, s_begin + chunk_len);
+                for (int64_t s0 = s_begin; s0 < s_end; s0 += TILE, ++it) {
+                    const int stage = it % kStages;
+                    const uint32_t phase = (it / kStages) & 1;
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    const uint32_t cnt = (uint32_t)min((int64_t)TILE, s_end - s0);
+                    const uint32_t bytes = cnt * (uint32_t)sizeof(Xycs<T>);
+                    mbar_expect_tx(&full[stage], bytes);
+                    tma_bulk_g2s(tiles + (size_t)stage * TILE, src + s0, bytes, &full[stage]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumer warps =====
+    uint32_t it = 0;
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int64_t tb = item % n_tblocks, ch = item / n_tblocks;
+        const int64_t s_begin = ch * chunk_len;
+        const int64_t s_end = min(n_src, s_begin + chunk_len);
+        Tgt<T> tg[TPT];
+        T ax[TPT], ay[TPT];
+        int64_t tidx[TPT];
+#pragma unroll
+        for (int j = 0; j < TPT; ++j) {
+            tidx[j] = tb * (int64_t)(kConsumerThreads * TPT) + j * kConsumerThreads + threadIdx.x;
+            const Xycs<T> e = tgt[min(tidx[j], n_tgt - 1)];
+            tg[j] = *reinterpret_cast<const Tgt<T>*>(&e);
+            ax[j] = (T)0;
+            ay[j] = (T)0;
+        }
+        for (int64_t s0 = s_begin; s0 < s_end; s0 += TILE, ++it) {
+            const int stage = it % kStages;
+            const uint32_t phase = (it / kStages) & 1;
+            const int cnt = (int)min((int64_t)TILE, s_end - s0);
+            mbar_wait(&full[stage], phase);
+            const Xycs<T>* tile = tiles + (size_t)stage * TILE;
+#pragma unroll 4
+            for (int s = 0; s < cnt; ++s) {
+                const Xycs<T> sr = tile[s];  // same address across the warp: broadcast
+#pragma unroll
+                for (int j = 0; j < TPT; ++j) pair_eval<T, P2R>(sr, tg[j], k, ax[j], ay[j]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+        }
+#pragma unroll
+        for (int j = 0; j < TPT; ++j) {
+            if (tidx[j] < n_tgt) {
+                T* o = partial + ((size_t)ch * n_tgt + tidx[j]) * 2;
+                o[0] = ax[j];
+                o[1] = ay[j];
+            }
+        }
+    }
+}
+
+// frep[j] = (accumulate ? frep[j] : 0) + f0 * sum_ch partial[ch][j]   (fixed order)
+template <typename T>
+__global__ void reduce_partials_kernel(const T* __restrict__ partial, int n_chunks, int64_t n_tgt, T f0,
+                                       T* __restrict__ frep, int accumulate) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n_tgt*2 scalars
+    if (i >= n_tgt * 2) return;
+    T acc = (T)0;
+    for (int c = 0; c < n_chunks; ++c) acc += partial[(size_t)c * n_tgt * 2 + i];
+    acc *= f0;
+    frep[i] = accumulate ? frep[i] + acc : acc;
+}
+
+// ---- batched independent scenarios: block-diagonal interaction, `group` agents each ----
+template <typename T, bool P2R>
+__global__ void pair_grouped_kernel(const Xycs<T>* __restrict__ xycs, int64_t n, int group, PairConst<T> k, T f0,
+                                    T* __restrict__ frep) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int64_t g0 = (j / group) * group;
+    const int64_t g1 = min(n, g0 + group);
+    const Xycs<T> e = xycs[j];
+    const Tgt<T> tg = *reinterpret_cast<const Tgt<T>*>(&e);
+    T ax = (T)0, ay = (T)0;
+    for (int64_t i = g0; i < g1; ++i) {
+        const Xycs<T> sr = xycs[i];
+        pair_eval<T, P2R>(sr, tg, k, ax, ay);
+    }
+    frep[j * 2] = f0 * ax;
+    frep[j * 2 + 1] = f0 * ay;
+}
+
+// ---- road-edge force -----------------------------------------------------------------
+// intersection.py:226-242: F = sum_k -F_0 r^-sigma (v_k - p)/r ; one thread per agent,
+// vertices staged through shared memory in tiles.
+template <typename T>
+__global__ void road_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
+                            const double* __restrict__ verts, int64_t m, double F_0, double sigma,
+                            T* __restrict__ out, int accumulate) {
+    __shared__ double sv[256][2];
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const double px = j < n ? x[j] : 0.0, py = j < n ? y[j] : 0.0;
+    T fx = (T)0, fy = (T)0;
+    for (int64_t v0 = 0; v0 < m; v0 += 256) {
+        const int cnt = (int)min((int64_t)256, m - v0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < cnt * 2; t += blockDim.x) (&sv[0][0])[t] = verts[v0 * 2 + t];
+        __syncthreads();
+        for (int t = 0; t < cnt; ++t) {
+            const T dx = (T)(sv[t][0] - px), dy = (T)(sv[t][1] - py);
+            const T r2 = dx * dx + dy * dy;
+            // -F_0 * r^(-sigma) / r = -F_0 * r2^(-(sigma+1)/2)
+            const T f = (T)(-F_0) * (T)pow((double)r2, -0.5 * (sigma + 1.0));
+            fx = fma(f, dx, fx);
+            fy = fma(f, dy, fy);
+        }
+    }
+    if (j < n) {
+        out[j * 2] = accumulate ? out[j * 2] + fx : fx;
+        out[j * 2 + 1] = accumulate ? out[j * 2 + 1] + fy : fy;
+    }
+}
+
+// ---- FP32 FFMA peak probe ---------------------------------------------------------------
+__global__ void __launch_bounds__(256) ffma_peak_kernel(int64_t iters, float* sink) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
+          a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f, c = 1e-3f;
+    for (int64_t i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    const float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678f) sink[0] = r;
+}
+
+template <typename T> PairConst<T> make_const(const CsfFieldParams* fp, bool is_f32) {
+    const double kappa = is_f32 ? fp->q_scale * 1.4426950408889634 : 1.4426950408889634;
+    PairConst<T> k;
+    k.sg0 = (T)(fp->sigma_0 / kappa);
+    k.sg1 = (T)(fp->sigma_1 / kappa);
+    k.sg2 = (T)(fp->sigma_2 / kappa);
+    k.sg3 = (T)(fp->sigma_3 / kappa);
+    k.e0 = (T)fp->e_0;
+    k.e1 = (T)fp->e_1;
+    k.ncosH = (fp->hfov * 0.5 >= CSF_PI) ? (T)2 : (T)(-cos(fp->hfov * 0.5));
+    k.tiny = (T)(is_f32 ? 1e-6 : 1e-200);
+    return k;
+}
+
+int g_sm_count = 0;
+int g_pair_ctas_per_sm[2] = {0, 0};
+
+struct PairPlan {
+    int n_tblocks, n_chunks, chunk_tiles, grid;
+};
+
+template <typename T, int TPT, int TILE> size_t pair_smem_bytes() {
+    return (size_t)kStages * TILE * sizeof(Xycs<T>) + 2 * kStages * sizeof(uint64_t);
+}
+
+template <int TPT, int TILE> PairPlan make_plan(int64_t n_src, int64_t n_tgt, int ctas_per_sm) {
+    PairPlan p;
+    const int64_t tb = (n_tgt + kConsumerThreads * TPT - 1) / (kConsumerThreads * TPT);
+    const int64_t src_tiles = (n_src + TILE - 1) / TILE;
+    const int64_t slots = (int64_t)csf_sm_count() * ctas_per_sm;
+    int64_t want = (32 * slots + tb - 1) / tb;  // chunks so that items >= 32 x slots
+    int64_t chunks = want < 1 ? 1 : want;
+    if (chunks > kMaxChunks) chunks = kMaxChunks;
+    if (chunks > src_tiles) chunks = src_tiles;
+    const int64_t ct = (src_tiles + chunks - 1) / chunks;
+    chunks = (src_tiles + ct - 1) / ct;
+    p.n_tblocks = (int)tb;
+    p.n_chunks = (int)chunks;
+    p.chunk_tiles = (int)ct;
+    const int64_t items = tb * chunks;
+    p.grid = (int)(items < slots ? items : slots);
+    return p;
+}
+
+template <typename T> struct PairCfg;
+template <> struct PairCfg<float> { static constexpr int TPT = 2, TILE = 512, idx = 0; };
+template <> struct PairCfg<double> { static constexpr int TPT = 1, TILE = 256, idx = 1; };
+
+template <typename T, bool P2R> int pair_occupancy() {
+    using C = PairCfg<T>;
+    auto kern = pair_kernel<T, C::TPT, C::TILE, P2R>;
+    const size_t smem = pair_smem_bytes<T, C::TPT, C::TILE>();
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
+    return nb < 1 ? 1 : nb;
+}
+
+template <typename T> int pair_ctas() {
+    using C = PairCfg<T>;
+    if (g_pair_ctas_per_sm[C::idx] == 0) {
+        int a = pair_occupancy<T, false>(), b = pair_occupancy<T, true>();
+        g_pair_ctas_per_sm[C::idx] = a < b ? a : b;
+    }
+    return g_pair_ctas_per_sm[C::idx];
+}
+
+template <typename T>
+int pair_forces(const void* src_xycs, int64_t n_src, const void* tgt_xycs, int64_t n_tgt, const CsfFieldParams* fp,
+                T* frep, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    using C = PairCfg<T>;
+    if (n_tgt <= 0) return 0;
+    if (n_src <= 0 || fp->f_0 == 0.0) {  // vehicle.py:1592-1593
+        if (!accumulate) cudaMemsetAsync(frep, 0, sizeof(T) * 2 * n_tgt, stream);
+        return 0;
+    }
+    if (fp->field_kind != 0) {
+        csf_set_error("csf_pair_forces: field_kind != 0 not supported yet", cudaErrorNotSupported);
+        return -(int)cudaErrorNotSupported;
+    }
+    const PairPlan pl = make_plan<C::TPT, C::TILE>(n_src, n_tgt, pair_ctas<T>());
+    const size_t need = (size_t)pl.n_chunks * n_tgt * 2 * sizeof(T);
+    if (workspace_bytes < need || workspace == nullptr) {
+        csf_set_error("csf_pair_forces: workspace too small", cudaErrorInvalidValue);
+        return -(int)cudaErrorInvalidValue;
+    }
+    const PairConst<T> k = make_const<T>(fp, sizeof(T) == 4);
+    const size_t smem = pair_smem_bytes<T, C::TPT, C::TILE>();
+    T* partial = reinterpret_cast<T*>(workspace);
+    if (fp->p2r)
+        pair_kernel<T, C::TPT, C::TILE, true><<<pl.grid, kThreads, smem, stream>>>(
+            (const Xycs<T>*)src_xycs, n_src, (const Xycs<T>*)tgt_xycs, n_tgt, k, partial, pl.chunk_tiles, pl.n_chunks,
+            pl.n_tblocks);
+    else
+        pair_kernel<T, C::TPT, C::TILE, false><<<pl.grid, kThreads, smem, stream>>>(
+            (const Xycs<T>*)src_xycs, n_src, (const Xycs<T>*)tgt_xycs, n_tgt, k, partial, pl.chunk_tiles, pl.n_chunks,
+            pl.n_tblocks);
+    CSF_CHECK_LAUNCH("pair_kernel");
+    const int64_t n2 = n_tgt * 2;
+    reduce_partials_kernel<T><<<(unsigned)((n2 + 255) / 256), 256, 0, stream>>>(partial, pl.n_chunks, n_tgt,
+                                                                                (T)fp->f_0, frep, accumulate);
+    CSF_CHECK_LAUNCH("reduce_partials_kernel");
+    return 0;
+}
+
+template <typename T>
+int pair_grouped(const void* xycs, int64_t n, int group, const CsfFieldParams* fp, T* frep, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    if (group < 1) group = 1;
+    const PairConst<T> k = make_const<T>(fp, sizeof(T) == 4);
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    if (fp->p2r)
+        pair_grouped_kernel<T, true><<<grid, 128, 0, stream>>>((const Xycs<T>*)xycs, n, group, k, (T)fp->f_0, frep);
+    else
+        pair_grouped_kernel<T, false><<<grid, 128, 0, stream>>>((const Xycs<T>*)xycs, n, group, k, (T)fp->f_0, frep);
+    CSF_CHECK_LAUNCH("pair_grouped_kernel");
+    return 0;
+}
+
+template <typename T>
+int road_forces(const double* x, const double* y, int64_t n, const double* verts, int64_t m, double F_0,
+                double sigma, T* out, int accumulate, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    road_kernel<T><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(x, y, n, verts, m, F_0, sigma, out, accumulate);
+    CSF_CHECK_LAUNCH("road_kernel");
+    return 0;
+}
+
+}  // namespace
+
+// ---- error bookkeeping ---------------------------------------------------------------------
+static char g_err[256] = "";
+void csf_set_error(const char* where, cudaError_t e) { snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e)); }
+
+extern "C" {
+
+int csf_version(void) { return CSF_ABI_VERSION; }
+const char* csf_last_error_string(void) { return g_err; }
+int csf_sm_count(void) {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+size_t csf_pair_workspace_bytes(int64_t n_src, int64_t n_tgt, int elem_bytes) {
+    if (n_src <= 0 || n_tgt <= 0) return 0;
+    const int chunks = elem_bytes == 4
+                           ? make_plan<PairCfg<float>::TPT, PairCfg<float>::TILE>(n_src, n_tgt, pair_ctas<float>()).n_chunks
+                           : make_plan<PairCfg<double>::TPT, PairCfg<double>::TILE>(n_src, n_tgt, pair_ctas<double>()).n_chunks;
+    return (size_t)chunks * (size_t)n_tgt * 2 * (size_t)elem_bytes;
+}
+int csf_pair_forces_f32(const void* s, int64_t ns, const void* t, int64_t nt, const CsfFieldParams* fp, float* frep,
+                        int acc, void* ws, size_t wsb, csf_stream_t st) {
+    return pair_forces<float>(s, ns, t, nt, fp, frep, acc, ws, wsb, (cudaStream_t)st);
+}
+int csf_pair_forces_f64(const void* s, int64_t ns, const void* t, int64_t nt, const CsfFieldParams* fp, double* frep,
+                        int acc, void* ws, size_t wsb, csf_stream_t st) {
+    return pair_forces<double>(s, ns, t, nt, fp, frep, acc, ws, wsb, (cudaStream_t)st);
+}
+int csf_pair_forces_grouped_f32(const void* x, int64_t n, int32_t g, const CsfFieldParams* fp, float* frep,
+                                csf_stream_t st) {
+    return pair_grouped<float>(x, n, g, fp, frep, (cudaStream_t)st);
+}
+int csf_pair_forces_grouped_f64(const void* x, int64_t n, int32_t g, const CsfFieldParams* fp, double* frep,
+                                csf_stream_t st) {
+    return pair_grouped<double>(x, n, g, fp, frep, (cudaStream_t)st);
+}
+int csf_road_forces_f32(const double* x, const double* y, int64_t n, const double* v, int64_t m, double F_0,
+                        double sigma, float* out, int acc, csf_stream_t st) {
+    return road_forces<float>(x, y, n, v, m, F_0, sigma, out, acc, (cudaStream_t)st);
+}
+int csf_road_forces_f64(const double* x, const double* y, int64_t n, const double* v, int64_t m, double F_0,
+                        double sigma, double* out, int acc, csf_stream_t st) {
+    return road_forces<double>(x, y, n, v, m, F_0, sigma, out, acc, (cudaStream_t)st);
+}
+int csf_ffma_peak(int64_t iters, float* sink, double* flops, csf_stream_t st) {
+    const int blocks = csf_sm_count() * 8;
+    ffma_peak_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(iters, sink);
+    CSF_CHECK_LAUNCH("ffma_peak_kernel");
+    if (flops) *flops = (double)blocks * 256.0 * (double)iters * 16.0 * 8.0 * 2.0;
+    return 0;
+}
+
+}  // extern "C"

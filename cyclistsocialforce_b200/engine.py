@@ -1,0 +1,401 @@
+"""Device-resident crowd state and the per-step kernel sequence.
+
+``AgentGroup`` = the agents of one model class as struct-of-arrays torch CUDA
+tensors (the layout of ``CsfAgentState`` in include/csf_b200.h).  ``Engine`` owns the
+pair payload, force buffers and workspace and issues, per step, through the C ABI:
+
+    K1   csf_pair_forces_*      all-pairs repulsive force (one launch per source class)
+         csf_road_forces_*      road-edge force (if any)
+    K2+3 csf_agent_step_*       destination force, assembly, control, dynamics, next payload
+
+which is what ``SocialForceIntersection.step()`` (reference intersection.py:866-896)
+does with Python loops.  PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .parameters import VehicleParameters, choose_q_scale
+
+N_STATES = dict(twod=5, invpendulum=6, balancingrider=8, planarpoint=4, bicycle=5, uncontrolled=4)
+_WRAP_MODELS = ("twod", "invpendulum", "bicycle")
+HIST_CAP = 128
+
+
+def _wrap_angle(a):
+    a = np.asarray(a, float)
+    a = np.floor(a / (2 * np.pi)) * (-2 * np.pi) + a
+    a = np.where(a > np.pi, a - 2 * np.pi, a)
+    return np.where(a < -np.pi, a + 2 * np.pi, a)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class AgentGroup:
+    """Agents of one model class.  ``s0``: (n, >= N_STATES) float64; ``destqueues``: list of
+    (Q_k, 3) arrays [x, y, stop] *including* the start position as entry 0 (the reference's
+    queue convention, vehicle.py:183-185)."""
+
+    def __init__(self, model, s0, params, vd_default=None, destqueues=None, dtype=torch.float32,
+                 device="cuda", q_cap=None):
+        assert model in N_STATES and model != "uncontrolled"
+        self.model = model
+        self.params = params
+        self.dtype = dtype
+        self.device = torch.device(device)
+        ns = N_STATES[model]
+        s0 = np.atleast_2d(np.asarray(s0, dtype=np.float64))
+        if s0.shape[1] < ns:
+            raise ValueError(f"The initial state s0 has to be size {ns}.")
+        s0 = s0[:, :ns].copy()
+        s0[:, 2] = _wrap_angle(s0[:, 2])                     # vehicle.py:155
+        self.n = n = s0.shape[0]
+        dev, T, f64, i32 = self.device, dtype, torch.float64, torch.int32
+
+        def tT(a):
+            return torch.as_tensor(np.ascontiguousarray(a), dtype=T, device=dev)
+
+        def t64(a):
+            return torch.as_tensor(np.ascontiguousarray(a), dtype=f64, device=dev)
+
+        z = np.zeros(n)
+        self.x, self.y = t64(s0[:, 0]), t64(s0[:, 1])
+        self.psi, self.v = tT(s0[:, 2]), tT(s0[:, 3])
+        self.delta = tT(s0[:, 4]) if ns > 4 else None
+        self.theta = tT(s0[:, 5]) if ns > 5 else None
+        self.deltadot = tT(s0[:, 6]) if ns > 6 else None
+        self.thetadot = tT(s0[:, 7]) if ns > 7 else None
+        vd = np.full(n, getattr(params, "v_desired_default", 0.0)) if vd_default is None else np.broadcast_to(
+            np.asarray(vd_default, float), (n,))
+        self.vd_default = tT(vd)
+        self.step_i = torch.zeros(n, dtype=i32, device=dev)
+        # destinations
+        if destqueues is None:
+            destqueues = [np.array([[s0[k, 0], s0[k, 1], 0.0]]) for k in range(n)]
+        lens = np.array([len(q) for q in destqueues], dtype=np.int32)
+        self.q_cap = int(max(int(lens.max()) if n else 1, q_cap or 1))
+        self.destq_host = np.zeros((n, self.q_cap, 3))
+        for k, q in enumerate(destqueues):
+            q = np.asarray(q, float)
+            self.destq_host[k, :len(q), :q.shape[1]] = q
+        self.dest_len_host = lens
+        self.destq = t64(self.destq_host)
+        self.dest_len = torch.as_tensor(lens, dtype=i32, device=dev)
+        self.dest_ptr = torch.zeros(n, dtype=i32, device=dev)
+        self.znav = torch.ones(n, dtype=i32, device=dev)          # [go]   vehicle.py:188
+        self.znav_v0, self.znav_d0, self.znav_d1 = tT(z), tT(z), tT(z)
+        # history (traj[i-1], 1 s look-back ring)
+        needs_hist = model in ("twod", "invpendulum", "planarpoint")
+        self.prev_x = t64(s0[:, 0]) if needs_hist else None
+        self.prev_y = t64(s0[:, 1]) if needs_hist else None
+        if needs_hist:
+            self.hist_x = torch.zeros((HIST_CAP, n), dtype=f64, device=dev)
+            self.hist_y = torch.zeros((HIST_CAP, n), dtype=f64, device=dev)
+            self.hist_x[0] = self.x
+            self.hist_y[0] = self.y
+            self.hist_step = torch.zeros(n, dtype=i32, device=dev)
+        else:
+            self.hist_x = self.hist_y = self.hist_step = None
+        self.ip_x = self.ip_zrid = self.ip_delta_run = None
+        self.dyn_x = self.dyn_v = self.br_gains = None
+        if model == "invpendulum":
+            # vehicle.py:1728-1736
+            self.ip_x = t64(np.stack([s0[:, 4], z, s0[:, 5], z, s0[:, 2]]))
+            walk = s0[:, 3] < params.v_max_walk
+            self.ip_zrid = torch.as_tensor(np.where(walk, 2, 1).astype(np.int32), device=dev)
+            ok = np.abs(s0[:, 4]) < params.delta_max_walk
+            self.ip_delta_run = torch.as_tensor(ok.astype(np.int32), device=dev)
+        elif model == "balancingrider":
+            # dynamics.py:361-399 (CSF frame -> bike frame) and :305-306
+            self.dyn_x = t64(np.stack([s0[:, 5], -s0[:, 4], s0[:, 7], -s0[:, 6], -s0[:, 2]]))
+            self.dyn_v = t64(s0[:, 3])
+            self.br_gains = t64(self._initial_br_gains(s0[:, 3]))
+        elif model == "planarpoint":
+            self.dyn_x = t64(s0[:, 2][None, :])
+            self.dyn_v = t64(s0[:, 3])
+        self.status = torch.zeros(1, dtype=i32, device=dev)
+        self.payload_offset = 0
+        self._cstate = None
+        self._cparams = None
+
+    def _initial_br_gains(self, v0):
+        """BalancingRiderDynamics.__init__ -> _get_gains(v) (dynamics.py:305-306, :602-615):
+        host-side Ackermann, same closed form as the kernel."""
+        from . import whipplecarvallo as wc
+        A0, A1, A2, B = wc.speed_polynomial_state_matrices(self.params.bike)
+        out = np.zeros((5, len(v0)))
+        cache = {}
+        for k, v in enumerate(v0):
+            v = float(v)
+            if v not in cache:
+                A = A0 + v * A1 + v * v * A2
+                poles = self.params.poles_at(v)
+                phi = np.eye(5, dtype=complex)
+                for pl in poles:
+                    phi = phi @ (A - pl * np.eye(5))
+                ctrb = np.stack([np.linalg.matrix_power(A, i) @ B for i in range(5)], axis=1)
+                w = np.linalg.solve(ctrb.T, np.array([0, 0, 0, 0, 1.0]))
+                cache[v] = np.real(w @ phi)
+            out[:, k] = cache[v]
+        return out
+
+    # ---- C structs ------------------------------------------------------------------------
+    def cstate(self):
+        if self._cstate is None:
+            s = _lib.CsfAgentState()
+            s.n = self.n
+            s.first, s.count = 0, self.n
+            s.payload_offset = self.payload_offset
+            for name in ("x", "y", "psi", "v", "delta", "theta", "deltadot", "thetadot", "vd_default",
+                         "step_i", "destq", "dest_len", "dest_ptr", "znav", "znav_v0", "znav_d0",
+                         "znav_d1", "prev_x", "prev_y", "hist_x", "hist_y", "hist_step", "ip_x",
+                         "ip_zrid", "ip_delta_run", "dyn_x", "dyn_v", "br_gains", "status"):
+                t = getattr(self, name)
+                setattr(s, name, t.data_ptr() if t is not None else None)
+            self._cstate = s
+        return self._cstate
+
+    def cparams(self, q_scale):
+        if self._cparams is None or self._cparams.q_scale != q_scale or self._cparams.q_cap != self.q_cap:
+            self._cparams = self.params.to_agent_params(q_scale, self.q_cap, HIST_CAP)
+        return self._cparams
+
+    def invalidate(self):
+        self._cstate = None
+        self._cparams = None
+
+    # ---- host views -----------------------------------------------------------------------
+    def states_numpy(self):
+        """(n, N_STATES) float64 array in the reference's state order."""
+        cols = [self.x, self.y, self.psi, self.v]
+        if self.model in ("twod", "invpendulum", "bicycle", "balancingrider"):
+            cols.append(self.delta)
+        if self.model in ("invpendulum", "balancingrider"):
+            cols.append(self.theta)
+        if self.model == "balancingrider":
+            cols += [self.deltadot, self.thetadot]
+        return torch.stack([c.to(torch.float64) for c in cols], dim=1).cpu().numpy()
+
+    def set_state_row(self, k, s):
+        """Overwrite the CSF state of agent k (host -> device)."""
+        s = np.asarray(s, float)
+        self.x[k], self.y[k] = float(s[0]), float(s[1])
+        self.psi[k], self.v[k] = float(_wrap_angle(s[2])), float(s[3])
+        for name, idx in (("delta", 4), ("theta", 5), ("deltadot", 6), ("thetadot", 7)):
+            t = getattr(self, name)
+            if t is not None and len(s) > idx:
+                t[k] = float(s[idx])
+
+    def set_destqueue(self, k, q):
+        q = np.asarray(q, float).reshape(-1, 3)
+        if len(q) > self.q_cap:
+            new_cap = max(len(q), 2 * self.q_cap)
+            host = np.zeros((self.n, new_cap, 3))
+            host[:, :self.q_cap] = self.destq_host
+            self.destq_host = host
+            self.q_cap = new_cap
+            self.destq = torch.as_tensor(host, dtype=torch.float64, device=self.device)
+            self.invalidate()
+        self.destq_host[k] = 0
+        self.destq_host[k, :len(q)] = q
+        self.dest_len_host[k] = len(q)
+        self.destq[k] = torch.as_tensor(self.destq_host[k], dtype=torch.float64, device=self.device)
+        self.dest_len[k] = len(q)
+
+    def check_status(self):
+        st = int(self.status.item())
+        if st & 1:
+            raise FloatingPointError("non-finite force or state on the device (status bit 0)")
+        if st & 2:
+            raise RuntimeError("Invalid navigation state")             # vehicle.py:455
+        if st & 4:
+            raise OverflowError("agent position left the Q-format range of the f32 payload")
+        return st
+
+
+class ObstacleGroup:
+    """Road users that exert a force but are not stepped by the kernels
+    (UncontrolledVehicle, reference vehicle.py:920-987).  Host-owned x, y, psi."""
+
+    model = "uncontrolled"
+
+    def __init__(self, xypsi, params=None, device="cuda"):
+        self.params = params if params is not None else VehicleParameters()
+        self.device = torch.device(device)
+        self.set(xypsi)
+        self.payload_offset = 0
+
+    def set(self, xypsi):
+        a = np.atleast_2d(np.asarray(xypsi, float))
+        self.n = a.shape[0]
+        self.host = a[:, :3].copy()
+        self.x = torch.as_tensor(a[:, 0].copy(), dtype=torch.float64, device=self.device)
+        self.y = torch.as_tensor(a[:, 1].copy(), dtype=torch.float64, device=self.device)
+        self.psi = torch.as_tensor(_wrap_angle(a[:, 2]), dtype=torch.float64, device=self.device)
+
+
+class Engine:
+    """One interaction domain (``SocialForceIntersection``): groups + obstacles + road edges."""
+
+    def __init__(self, groups, obstacles=None, priority_rule="unregulated", road_edges=(),
+                 dtype=torch.float32, device="cuda", q_scale=None, extent=None, scenario_size=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.CsfError("no CUDA device: the csf_b200 engine has no CPU fallback")
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.f32 = dtype == torch.float32
+        self.sfx = "f32" if self.f32 else "f64"
+        self.groups = [g for g in groups if g.n > 0]
+        self.obstacles = [o for o in (obstacles or []) if o.n > 0]
+        self.p2r = priority_rule == "p2r"
+        self.scenario_size = scenario_size
+        off = 0
+        for g in self.groups + self.obstacles:
+            g.payload_offset = off
+            if hasattr(g, "invalidate"):
+                g.invalidate()
+            off += g.n
+        self.n_agents = sum(g.n for g in self.groups)
+        self.n_total = off
+        # Q-format scale of the f32 payload
+        if q_scale is None:
+            if extent is None:
+                extent = 1.0
+                for g in self.groups:
+                    extent = max(extent, float(g.x.abs().max()), float(g.y.abs().max()),
+                                 float(np.abs(g.destq_host[..., :2]).max()))
+                for o in self.obstacles:
+                    extent = max(extent, float(np.abs(o.host[:, :2]).max()))
+                extent = 2.0 * extent + 1000.0
+            q_scale = choose_q_scale(extent)
+        self.q_scale = float(q_scale)
+        self.elem_bytes = 16 if self.f32 else 32
+        n = max(self.n_total, 1)
+        self.payload = torch.zeros((n, 4), dtype=torch.int32 if self.f32 else torch.float64, device=self.device)
+        self.frep = torch.zeros((max(self.n_agents, 1), 2), dtype=dtype, device=self.device)
+        self.force = torch.zeros_like(self.frep)
+        self.fdest = torch.zeros_like(self.frep)
+        self.froad = None
+        self.set_road_edges(road_edges)
+        # source classes: contiguous payload ranges with identical field parameters
+        self.classes = []
+        for g in self.groups + self.obstacles:
+            key = g.params.field_key()
+            if self.classes and self.classes[-1][2] == key:
+                s, c, k, fp = self.classes[-1]
+                self.classes[-1] = (s, c + g.n, k, fp)
+            else:
+                self.classes.append((g.payload_offset, g.n, key, g.params.to_field_params(self.q_scale, self.p2r)))
+        wsb = 0
+        if self.n_total > 1 and scenario_size is None:
+            for s, c, _, _ in self.classes:
+                wsb = max(wsb, int(self.lib.csf_pair_workspace_bytes(c, self.n_agents, 4 if self.f32 else 8)))
+        self.ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=self.device)
+        self.gpu_launches = 0
+        self.pack()
+
+    # ---- helpers ----------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _fn(self, name):
+        return getattr(self.lib, f"{name}_{self.sfx}")
+
+    def set_road_edges(self, road_edges):
+        """road_edges: iterable of (vertices (M,2), F_0, sigma)."""
+        merged = {}
+        for verts, F_0, sigma in road_edges:
+            merged.setdefault((float(F_0), float(sigma)), []).append(np.asarray(verts, float).reshape(-1, 2))
+        self.road = [(torch.as_tensor(np.ascontiguousarray(np.concatenate(v)), dtype=torch.float64,
+                                      device=self.device).contiguous(), k[0], k[1])
+                     for k, v in merged.items()]
+        self.froad = torch.zeros_like(self.frep) if self.road else None
+
+    def pack(self):
+        """update_road_user_positions (intersection.py:660-677): state -> pair payload."""
+        st = self._stream()
+        for g in self.groups:
+            _lib.check(self._fn("csf_pack_xycs")(C.byref(g.cstate()), C.byref(g.cparams(self.q_scale)),
+                                                 _ptr(self.payload), st), "csf_pack_xycs")
+            self.gpu_launches += 1
+        for o in self.obstacles:
+            dst = C.c_void_p(self.payload.data_ptr() + o.payload_offset * self.elem_bytes)
+            _lib.check(self._fn("csf_pack_xypsi")(_ptr(o.x), _ptr(o.y), _ptr(o.psi), o.n, self.q_scale, dst, st),
+                       "csf_pack_xypsi")
+            self.gpu_launches += 1
+
+    def _pair_and_road(self):
+        st = self._stream()
+        have_rep = self.n_total > 1
+        if have_rep:
+            if self.scenario_size is not None:
+                fp = self.classes[0][3]
+                _lib.check(self._fn("csf_pair_forces_grouped")(_ptr(self.payload), self.n_agents,
+                                                               int(self.scenario_size), C.byref(fp),
+                                                               _ptr(self.frep), st), "csf_pair_forces_grouped")
+                self.gpu_launches += 1
+            else:
+                for ci, (s, c, _, fp) in enumerate(self.classes):
+                    src = C.c_void_p(self.payload.data_ptr() + s * self.elem_bytes)
+                    _lib.check(self._fn("csf_pair_forces")(src, c, _ptr(self.payload), self.n_agents,
+                                                           C.byref(fp), _ptr(self.frep), 1 if ci > 0 else 0,
+                                                           _ptr(self.ws), self.ws.numel(), st), "csf_pair_forces")
+                    self.gpu_launches += 2
+        if self.road:
+            for g in self.groups:
+                out = C.c_void_p(self.froad.data_ptr() + g.payload_offset * 2 * self.froad.element_size())
+                for ei, (verts, F_0, sigma) in enumerate(self.road):
+                    _lib.check(self._fn("csf_road_forces")(_ptr(g.x), _ptr(g.y), g.n, _ptr(verts), verts.shape[0],
+                                                           F_0, sigma, out, 1 if ei > 0 else 0, st),
+                               "csf_road_forces")
+                    self.gpu_launches += 1
+        return have_rep
+
+    def _off(self, t, g):
+        return C.c_void_p(t.data_ptr() + g.payload_offset * 2 * t.element_size()) if t is not None else C.c_void_p(0)
+
+    # ---- the three public operations -----------------------------------------------------------
+    def calc_forces(self):
+        """calc_forces (intersection.py:747-864): returns the device tensor force (N, 2)."""
+        have_rep = self._pair_and_road()
+        st = self._stream()
+        for g in self.groups:
+            _lib.check(self._fn("csf_agent_forces")(
+                _lib.MODEL_IDS[g.model], C.byref(g.cstate()), C.byref(g.cparams(self.q_scale)), self.n_total,
+                self._off(self.frep, g) if have_rep else C.c_void_p(0), self._off(self.froad, g),
+                self._off(self.force, g), self._off(self.fdest, g), st), "csf_agent_forces")
+            self.gpu_launches += 1
+        return self.force
+
+    def advance(self):
+        """vehicles[i].step(Fx[i], Fy[i]) for all i + update_road_user_positions (:891-894)."""
+        st = self._stream()
+        for g in self.groups:
+            _lib.check(self._fn("csf_agent_advance")(
+                _lib.MODEL_IDS[g.model], C.byref(g.cstate()), C.byref(g.cparams(self.q_scale)),
+                self._off(self.force, g), _ptr(self.payload), st), "csf_agent_advance")
+            self.gpu_launches += 1
+
+    def step(self):
+        """SocialForceIntersection.step (intersection.py:866-896), fused per-agent kernel."""
+        if self.n_agents == 0:
+            return
+        have_rep = self._pair_and_road()
+        st = self._stream()
+        for g in self.groups:
+            _lib.check(self._fn("csf_agent_step")(
+                _lib.MODEL_IDS[g.model], C.byref(g.cstate()), C.byref(g.cparams(self.q_scale)), self.n_total,
+                self._off(self.frep, g) if have_rep else C.c_void_p(0), self._off(self.froad, g),
+                self._off(self.force, g), _ptr(self.payload), st), "csf_agent_step")
+            self.gpu_launches += 1
+
+    def check_status(self):
+        return [g.check_status() for g in self.groups]

@@ -1,0 +1,218 @@
+/*
+ * csf_b200.h -- C ABI of the B200-native social-force stepping engine.
+ *
+ * The reference (chris-konrad/cyclistsocialforce, pure Python) has no FFI layer;
+ * this header is the boundary a replacement shared library exports for the one
+ * hot path  SocialForceIntersection.step()  (reference
+ * src/cyclistsocialforce/intersection.py:866-896).  Each entry point names the
+ * reference code it replaces.  All functions are asynchronous on `stream`,
+ * allocate nothing, take plain device pointers owned by the caller, and return
+ * 0 on success or a negative cudaError_t.  One scalar type per entry point:
+ *   _f32  production build   (pair payload: Q-format int32 positions + fp32 cos/sin)
+ *   _f64  verification build (everything double)
+ *
+ * Layouts
+ * -------
+ *  pair payload ("xycs"), one element per road user, array [N]:
+ *     f32: { int32 xq, yq; float cos_psi, sin_psi; }   16 B,  x = xq * q_scale  [m]
+ *     f64: { double x, y, cos_psi, sin_psi; }          32 B
+ *  forces: [n][2] (x,y interleaved) of the scalar type.
+ *  per-agent state: struct of arrays, see CsfAgentState.
+ */
+#ifndef CSF_B200_H
+#define CSF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSF_ABI_VERSION 1
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef void* csf_stream_t; /* cudaStream_t */
+
+/* model ids (reference classes in src/cyclistsocialforce/vehicle.py) */
+enum {
+    CSF_MODEL_TWOD = 0,           /* TwoDBicycle            :1292-1648 */
+    CSF_MODEL_INVPENDULUM = 1,    /* InvPendulumBicycle     :1651-1950 */
+    CSF_MODEL_BALANCINGRIDER = 2, /* BalancingRiderBicycle  :1953-1988 + dynamics.py:261-705 */
+    CSF_MODEL_PLANARPOINT = 3,    /* PlanarPointBicycle     :1991-2028 + dynamics.py:802-1079 */
+    CSF_MODEL_BICYCLE = 4,        /* Bicycle (v0.1)         :990-1289 */
+    CSF_MODEL_COUNT = 5
+};
+
+/* Repulsive force-field parameters of one class of *source* road users
+ * (VehicleParameters f_0,e_0,e_1,sigma_0..3,hfov: parameters.py:430-451;
+ * the reference reads them from the source vehicle, vehicle.py:1587-1612,
+ * intersection.py:733-735). */
+typedef struct CsfFieldParams {
+    double f_0, e_0, e_1;
+    double sigma_0, sigma_1, sigma_2, sigma_3;
+    double hfov;     /* full horizontal field of view [rad] */
+    double q_scale;  /* metres per position unit of the f32 payload (ignored by _f64) */
+    int32_t p2r;     /* priority_rule == "p2r" (intersection.py:738-741) */
+    int32_t field_kind; /* 0: TwoDBicycle field (vehicle.py:1560-1648); 1: Bicycle v0.1 (:1107-1147) */
+    double p_0, p_decay, v_max; /* field_kind 1 only (BicycleParameters p_0, p_decay, v_max_riding[1]) */
+} CsfFieldParams;
+
+/* Crowd-wide parameters of the per-agent kernels (all models share one struct). */
+typedef struct CsfAgentParams {
+    double t_s;
+    double d_arrived_inter, d_arrived_stop, v_max_stop, v_max_harddecel;
+    double a_max[2], a_desired[2], v_max_riding[2];
+    double l, delta_max, k_p_v, k_p_delta, g;
+    /* InvPendulumBicycle (parameters.py:1429-1472, :1832-1892) */
+    double l_2, tau_1_squared, i_steer, c_steer, v_max_walk, delta_max_walk;
+    double kx_table[5][4], ku_table[4];
+    /* PlanarPointBicycle (dynamics.py:933-940) */
+    double k_psi;
+    /* BalancingRiderBicycle: A(v) = br_A0 + v*br_A1 + v*v*br_A2 (row-major 5x5),
+     * steer-torque column br_B, pole(v) = icpt + coef*v (parameters.py:1403-1411) */
+    double br_A0[25], br_A1[25], br_A2[25], br_B[5];
+    double br_pole_icpt[5], br_pole_coef[5];
+    /* payload packing */
+    double q_scale;
+    int32_t traj_len;  /* int(30/t_s) = 3000, vehicle.py:159 */
+    int32_t hist_len;  /* int(1/t_s)  = 100,  vehicle.py:1487 */
+    int32_t hist_cap;  /* rows allocated in hist_x/hist_y (power of two > hist_len) */
+    int32_t q_cap;     /* destination-queue capacity (entries per agent) */
+} CsfAgentParams;
+
+/* Per-agent state, struct of arrays of length n.  "T" is float for _f32 and
+ * double for _f64 entry points; positions are always double (the f32 payload is
+ * derived from them in Q format).  Pointers a model does not use may be NULL. */
+typedef struct CsfAgentState {
+    int64_t n;              /* array length (row stride of the 2-D fields) */
+    int64_t first, count;   /* agents [first, first+count) are processed by a call */
+    int64_t payload_offset; /* index of this group's agent 0 in the payload array */
+    double* x;              /* [n] */
+    double* y;              /* [n] */
+    void* psi;              /* T [n]  yaw in (-pi, pi] */
+    void* v;                /* T [n] */
+    void* delta;            /* T [n]  steer angle            (twod, invpendulum, balancingrider, bicycle) */
+    void* theta;            /* T [n]  roll angle             (invpendulum: theta, balancingrider: phi) */
+    void* deltadot;         /* T [n]                         (balancingrider) */
+    void* thetadot;         /* T [n]                         (balancingrider) */
+    void* vd_default;       /* T [n]  params.v_desired_default per agent */
+    int32_t* step_i;        /* [n]  Vehicle.i (ring index; wraps at traj_len for twod/invpendulum/bicycle) */
+    /* destinations (Vehicle.destqueue/destpointer, vehicle.py:183-185) */
+    const double* destq;    /* [n][q_cap][3]  x, y, stop */
+    const int32_t* dest_len;/* [n] */
+    int32_t* dest_ptr;      /* [n] */
+    /* navigation state machine (vehicle.py:354-457) */
+    int32_t* znav;          /* [n]  bit0 go, bit1 decelerating, bit2 arrived */
+    void* znav_v0;          /* T [n]  znavparams[0..2] */
+    void* znav_d0;          /* T [n] */
+    void* znav_d1;          /* T [n] */
+    /* history needed by the spline destination force (vehicle.py:1468-1492) */
+    double* prev_x;         /* [n]  traj[0, i-1] */
+    double* prev_y;         /* [n] */
+    double* hist_x;         /* [hist_cap][n]  ring of past positions, row = step mod hist_cap */
+    double* hist_y;
+    int32_t* hist_step;     /* [n]  total steps taken (ring write index) */
+    /* InvPendulumBicycle (vehicle.py:1728-1736, :1932-1950) */
+    double* ip_x;           /* [5][n]  delta, deltadot, theta, thetadot, psi (unwrapped) */
+    int32_t* ip_zrid;       /* [n]  bit0 riding, bit1 walking */
+    int32_t* ip_delta_run;  /* [n]  trailing count of samples with |delta| < delta_max_walk */
+    /* BalancingRiderBicycle / PlanarPointBicycle dynamics state (dynamics.py:305-306, :828) */
+    double* dyn_x;          /* balancingrider: [5][n] phi,delta,phidot,deltadot,psi in the bike frame (unwrapped);
+                             * planarpoint: [1][n] psi (unwrapped).  Positions live in x/y. */
+    double* dyn_v;          /* [n] */
+    double* br_gains;       /* [5][n] */
+    /* device-side status word: bit0 non-finite force/state seen, bit1 invalid nav state,
+     * bit2 payload position out of Q range, bit3 degenerate spline (duplicate points) */
+    int32_t* status;        /* [1] */
+} CsfAgentState;
+
+/* ---- library ------------------------------------------------------------------ */
+int csf_version(void);
+const char* csf_last_error_string(void);
+/* sm count of the current device (grid sizing), cached */
+int csf_sm_count(void);
+
+/* ---- K1: all-pairs repulsive force ---------------------------------------------
+ * Replaces get_untracked_foes + the pair loop + np.sum of calc_forces
+ * (intersection.py:690-745, :788-823, :841-843) and TwoDBicycle.calcRepulsiveForce
+ * (vehicle.py:1560-1648) for one class of sources:
+ *     frep[j] (+)= sum_i mask(i,j) * F(source i -> target j),  j in [0, n_tgt)
+ * A coincident pair (rho == 0, which includes i == j) contributes 0.
+ * `workspace` must hold csf_pair_workspace_bytes(n_src, n_tgt, sizeof scalar) bytes. */
+size_t csf_pair_workspace_bytes(int64_t n_src, int64_t n_tgt, int elem_bytes);
+int csf_pair_forces_f32(const void* src_xycs, int64_t n_src, const void* tgt_xycs, int64_t n_tgt,
+                        const CsfFieldParams* fp, float* frep_xy, int accumulate,
+                        void* workspace, size_t workspace_bytes, csf_stream_t stream);
+int csf_pair_forces_f64(const void* src_xycs, int64_t n_src, const void* tgt_xycs, int64_t n_tgt,
+                        const CsfFieldParams* fp, double* frep_xy, int accumulate,
+                        void* workspace, size_t workspace_bytes, csf_stream_t stream);
+/* Batched independent scenarios (block-diagonal interaction): agents
+ * [k*group, (k+1)*group) only see each other. */
+int csf_pair_forces_grouped_f32(const void* xycs, int64_t n, int32_t group, const CsfFieldParams* fp,
+                                float* frep_xy, csf_stream_t stream);
+int csf_pair_forces_grouped_f64(const void* xycs, int64_t n, int32_t group, const CsfFieldParams* fp,
+                                double* frep_xy, csf_stream_t stream);
+
+/* ---- road-edge force ------------------------------------------------------------
+ * Replaces RoadEdge.calcRepulsiveForce summed over edges (intersection.py:226-242,
+ * :36-48, :81-94):  froad[j] (+)= sum_k -F_0 * r^-sigma * (vertex_k - pos_j)/r.
+ * vertices: double [m][2]. */
+int csf_road_forces_f32(const double* x, const double* y, int64_t n, const double* vertices, int64_t m,
+                        double F_0, double sigma, float* froad_xy, int accumulate, csf_stream_t stream);
+int csf_road_forces_f64(const double* x, const double* y, int64_t n, const double* vertices, int64_t m,
+                        double F_0, double sigma, double* froad_xy, int accumulate, csf_stream_t stream);
+
+/* ---- K2/K3: per-agent kernels ---------------------------------------------------
+ * csf_agent_forces_*  = the per-agent part of calc_forces (intersection.py:797-799,
+ *   :841-862): destination force (vehicle.py:281-299, :1416-1558, :2078-2108; mutates the
+ *   destination pointer and navigation state exactly like the reference), clip of the
+ *   repulsive force to |F_dest| (utils.py:56-86), sum, + road force.
+ *   n_total == 1 skips the clip stage (intersection.py:813, :849-851).
+ * csf_agent_advance_* = Vehicle.step / <Model>.step for every agent
+ *   (vehicle.py:301-328, :1218-1272, :1386-1414, :1883-1950; dynamics.py:674-705,
+ *   :1051-1079) + the mirror of positions (intersection.py:660-677), written as the
+ *   next step's pair payload.
+ * csf_agent_step_*    = both fused (what SocialForceIntersection.step() does per agent).
+ * frep_xy / froad_xy may be NULL (treated as 0).  force_xy / fdest_xy may be NULL. */
+int csf_agent_forces_f32(int model, const CsfAgentState* st, const CsfAgentParams* p, int64_t n_total,
+                         const float* frep_xy, const float* froad_xy, float* force_xy, float* fdest_xy,
+                         csf_stream_t stream);
+int csf_agent_forces_f64(int model, const CsfAgentState* st, const CsfAgentParams* p, int64_t n_total,
+                         const double* frep_xy, const double* froad_xy, double* force_xy, double* fdest_xy,
+                         csf_stream_t stream);
+int csf_agent_advance_f32(int model, const CsfAgentState* st, const CsfAgentParams* p,
+                          const float* force_xy, void* next_xycs, csf_stream_t stream);
+int csf_agent_advance_f64(int model, const CsfAgentState* st, const CsfAgentParams* p,
+                          const double* force_xy, void* next_xycs, csf_stream_t stream);
+int csf_agent_step_f32(int model, const CsfAgentState* st, const CsfAgentParams* p, int64_t n_total,
+                       const float* frep_xy, const float* froad_xy, float* force_xy, void* next_xycs,
+                       csf_stream_t stream);
+int csf_agent_step_f64(int model, const CsfAgentState* st, const CsfAgentParams* p, int64_t n_total,
+                       const double* frep_xy, const double* froad_xy, double* force_xy, void* next_xycs,
+                       csf_stream_t stream);
+/* Build the pair payload from the current state (update_road_user_positions,
+ * intersection.py:660-677). */
+int csf_pack_xycs_f32(const CsfAgentState* st, const CsfAgentParams* p, void* xycs, csf_stream_t stream);
+int csf_pack_xycs_f64(const CsfAgentState* st, const CsfAgentParams* p, void* xycs, csf_stream_t stream);
+/* Generic payload packer for road users that are not stepped by this library
+ * (UncontrolledVehicle sources, vehicle.py:920-987). psi: double [n]. */
+int csf_pack_xypsi_f32(const double* x, const double* y, const double* psi, int64_t n, double q_scale,
+                       void* xycs, csf_stream_t stream);
+int csf_pack_xypsi_f64(const double* x, const double* y, const double* psi, int64_t n, double q_scale,
+                       void* xycs, csf_stream_t stream);
+
+/* ---- measurement helper: sustained FP32 FFMA throughput of this device ------------
+ * Runs `iters` dependent-chain FFMA rounds on every SM; returns flops executed
+ * (2 per FFMA) through *flops; the caller times it with CUDA events. */
+int csf_ffma_peak(int64_t iters, float* sink, double* flops, csf_stream_t stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSF_B200_H */

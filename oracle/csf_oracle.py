@@ -172,11 +172,19 @@ def field_params_array(plist):
                      for p in plist], float)
 
 
-def twod_field(x0, y0, psi0, fp, x, y, psi):
+def twod_field(x0, y0, psi0, fp, x, y, psi, literal=False):
     """TwoDBicycle.calcRepulsiveForce, vehicle.py:1584-1648.
 
     Sources (x0,y0,psi0) broadcast against targets (x,y,psi); ``fp`` = columns of
     ``field_params_array`` broadcastable the same way.  Returns Fx, Fy.
+
+    ``literal=True`` reproduces the reference's arithmetic operation by operation,
+    including its far-field failure: for rho*q/sigma > ~372 the squares in
+    ``F = sqrt(Fx**2 + Fy**2)`` (:1644) underflow to 0 and ``P*Fx/F`` is 0/0 = NaN,
+    i.e. any crowd wider than ~100 m yields NaN forces in the reference.  The default
+    evaluates the same expression with the common factor P taken out of the
+    normalisation (identical to 1 ulp wherever the reference is finite, and the
+    correct limit -- P times a unit vector -- where it is not).
     """
     f0, e0, e1, s0, s1, s2_, s3 = (fp[..., k] for k in range(7))
     psi_rel = psi0 - psi
@@ -190,13 +198,14 @@ def twod_field(x0, y0, psi0, fp, x, y, psi):
     phi = limit_angle(np.asarray(phi1 - psi0))
     cosphi = np.cos(phi)
     sinphi = np.sin(phi)
-    with np.errstate(invalid="ignore", divide="ignore"):
+    with np.errstate(invalid="ignore", divide="ignore", under="ignore"):
         sigma = vd0 - vd1 * np.sqrt((1 - cosphi) / 2)
         dsigm = -vd1 * np.sqrt((1 + cosphi) / 2) * np.sign(phi) / 2
         q = np.sqrt(1 - (e * cosphi) ** 2)
         P = f0 * np.exp(-rho * q / sigma)
-        Frho = P * q / sigma
-        Fphi = -P * ((1 - (e * cosphi) ** 2) * dsigm - e**2 * sinphi * cosphi * sigma) / (
+        one = P if literal else 1.0
+        Frho = one * q / sigma
+        Fphi = -one * ((1 - (e * cosphi) ** 2) * dsigm - e**2 * sinphi * cosphi * sigma) / (
             sigma**2 * q)
         Fx = Frho * np.cos(phi1) - Fphi * np.sin(phi1)
         Fy = Frho * np.sin(phi1) + Fphi * np.cos(phi1)

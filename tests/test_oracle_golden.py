@@ -169,3 +169,22 @@ def test_survey_appendix_b_kats(golden):
                             3.432309238526e-04, 4.997244378300], rtol=1e-9)
     pp = g["demo_planarpoint_s"][g["demo_planarpoint_steps"].tolist().index(700)]
     assert np.allclose(pp[0], [22.903499079388, -0.669743650247, 0.05499566999, 4.5], rtol=1e-8)
+
+
+def test_reference_far_field_nan_quirk():
+    """The reference's normalisation underflows for far pairs (vehicle.py:1644-1646): NaN.
+    The oracle's default (and the CUDA kernels) return P * unit vector instead."""
+    p = co.default_params("twod")
+    fp = co.field_params_array([p])[0]
+    x = np.array([0.0, -100.0])       # target 141 m behind/abeam of the source
+    y = np.array([0.0, 100.0])
+    psi = np.array([0.0, 0.1])
+    lit = co.twod_field(x[0], y[0], psi[0], fp, x[1], y[1], psi[1], literal=True)
+    rob = co.twod_field(x[0], y[0], psi[0], fp, x[1], y[1], psi[1])
+    assert np.isnan(lit[0]) and np.isnan(lit[1])
+    assert np.isfinite(rob[0]) and np.isfinite(rob[1]) and abs(rob[0]) < 1e-100
+    # where the reference is finite the two agree to rounding
+    x2, y2 = np.array([3.0]), np.array([1.0])
+    a = co.twod_field(0.0, 0.0, 0.3, fp, x2, y2, np.array([2.0]), literal=True)
+    b = co.twod_field(0.0, 0.0, 0.3, fp, x2, y2, np.array([2.0]))
+    assert abs(a[0] - b[0]).max() < 1e-15 and abs(a[1] - b[1]).max() < 1e-15
