@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""Headline benchmark: agent-steps/sec of a 65,536-cyclist TwoDBicycle open-plane crowd
+(BASELINE.json metric), one process per GPU, agent-range sharding + payload all-gather.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # CPU oracle port, all host threads
+
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for how every field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_AGENTS = int(os.environ.get("CSF_BENCH_N", 65536))
+FLOP_PER_PAIR = 76.0          # 68 FP32 flops + 8 special-function results, dense convention
+BYTES_PER_AGENT_STEP = 124.0  # TwoDBicycle per-agent kernel, fp32 SoA
+SEED = 1
+METRIC = "agent-steps/sec, N=65,536 TwoDBicycle"
+WORKLOAD = f"{N_AGENTS}-cyclist TwoDBicycle open-plane crowd (SURVEY 8d recipe, seed {SEED}, 4 m spacing)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe) during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on host cores (bounded sample of the same workload)
+# ------------------------------------------------------------------------------------------
+def cpu_oracle_run(steps, warmup, sample_agents=None):
+    """Times the CPU oracle on a bounded sample: `sample_agents` agents of the N-agent crowd are
+    stepped per CPU step; each of them interacts with all N sources (full per-agent cost)."""
+    from oracle import cpu_port
+    return cpu_port.timed_sample(N_AGENTS, SEED, steps, warmup, sample_agents)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = cpu_oracle_run(args.steps, args.warmup)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "agent-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "n_agents": N_AGENTS},
+            "cpu_baseline": {"value": r["value"], "unit": "agent-steps/s", "cores": r["cores"],
+                             "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from cyclistsocialforce_b200 import _lib, parameters as P
+    from cyclistsocialforce_b200.distributed import PayloadExchange, shard_bounds
+    from cyclistsocialforce_b200.engine import AgentGroup, Engine
+    from cyclistsocialforce_b200.synthetic import queues_with_start, synthetic_crowd
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+
+    # ---- the crowd, sharded by agent range -------------------------------------------------
+    s0, q = synthetic_crowd(N_AGENTS, seed=SEED)
+    queues = queues_with_start(s0, q)
+    lo, hi = shard_bounds(N_AGENTS, world)[rank]
+    extent = 2.0 * float(max(np.abs(s0[:, :2]).max(), np.abs(q[..., :2]).max())) + 1000.0
+    group = AgentGroup("twod", s0[lo:hi], P.InvPendulumBicycleParameters(), destqueues=list(queues[lo:hi]),
+                       dtype=torch.float32, device=dev)
+    exch = PayloadExchange(N_AGENTS, rank, world)
+    eng = Engine([group], dtype=torch.float32, device=dev, extent=extent, n_global=N_AGENTS, global_offset=lo,
+                 exchange=exch)
+    exch(eng.payload)
+    n_local = hi - lo
+
+    def sync():
+        torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---- FP32 peak of this device (FFMA micro-benchmark; MEASURED_PEAKS.json has no fp32 figure) ----
+    import ctypes as C
+    sink = torch.zeros(1, dtype=torch.float32, device=dev)
+    flops = C.c_double(0.0)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    lib.csf_ffma_peak(2000, sink.data_ptr(), C.byref(flops), st)
+    sync()
+    best = 0.0
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lib.csf_ffma_peak(20000, sink.data_ptr(), C.byref(flops), st)
+        e1.record()
+        sync()
+        best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    fp32_peak_tflops = best
+
+    # ---- L2 flush buffer (126 MB L2): written between timed iterations ---------------------
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    for _ in range(max(args.warmup, 3)):
+        eng.step()
+    sync()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = eng.gpu_launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    sync()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                      # L2 flush, outside the per-step events
+        a, b, c = ev[k]
+        a.record()
+        have_rep = eng._pair_and_road()            # K1 (+ partial-sum reduce)
+        b.record()
+        eng._agent_step(have_rep)                  # K2+K3 fused, + payload all-gather
+        c.record()
+    sync()
+    barrier()
+    launches = eng.gpu_launches - launches0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(c) for a, b, c in ev]
+    pair_ms = [a.elapsed_time(b) for a, b, c in ev]
+    agent_ms = [b.elapsed_time(c) for a, b, c in ev]
+    total_ms = sum(step_ms)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    eng.check_status()
+    value = N_AGENTS * args.steps / (total_ms * 1e-3)
+    ms_per_step = total_ms / args.steps
+
+    # ---- end to end: host buffers in, host buffers out, every step --------------------------
+    host_in = {n: getattr(group, n).cpu().pin_memory() for n in ("x", "y", "psi", "v", "delta")}
+    host_out = {n: torch.empty_like(t).pin_memory() for n, t in host_in.items()}
+    host_force = torch.empty((n_local, 2), dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in host_in.values())
+    d2h = h2d + host_force.numel() * host_force.element_size()
+    for _ in range(2):
+        eng.step_host(host_in, host_out, host_force)
+    barrier()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.step_host(host_in, host_out, host_force)
+        host_in, host_out = host_out, host_in
+    sync()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = N_AGENTS * args.steps / e2e_s
+
+    if rank == 0:
+        pair_s = statistics.mean(pair_ms) * 1e-3
+        pairs_per_launch = float(n_local) * float(N_AGENTS - 1)
+        achieved = pairs_per_launch * FLOP_PER_PAIR / pair_s / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "pair_kernel_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        agent_s = statistics.mean(agent_ms) * 1e-3
+        line = {
+            "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n_agents": N_AGENTS, "parallelism": f"agent-range x{world}",
+                       "l2": "flushed between timed steps (256 MiB write)", "q_scale_m": eng.q_scale,
+                       "pair_interactions_per_s": float(N_AGENTS) * (N_AGENTS - 1) * args.steps / (total_ms * 1e-3)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp32", "kernel": "pair_kernel<float,2,512>", "achieved": achieved,
+                         "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops,
+                         "traffic": traffic, "peak_source": "csf_ffma_peak micro-benchmark in this run",
+                         "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs_per_launch,
+                         "kernel_ms": pair_s * 1e3, "share_of_step": pair_s * 1e3 / statistics.mean(step_ms)},
+            "roofline_agent_kernel": {"bound": "hbm", "kernel": "agent_kernel<float,TWOD,STEP>",
+                                      "achieved": n_local * BYTES_PER_AGENT_STEP / agent_s / 1e9, "peak": hbm_peak,
+                                      "unit": "GB/s", "frac": n_local * BYTES_PER_AGENT_STEP / agent_s / 1e9 / hbm_peak,
+                                      "kernel_ms": agent_s * 1e3,
+                                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
+        }
+        if not args.no_cpu_baseline:
+            r = cpu_oracle_run(steps=2, warmup=1)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "agent-steps/s", "cores": r["cores"],
+                                    "kind": r["kind"], "sample": r["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -8,7 +8,7 @@
 //   c = u . h_i            s = u x h_i (signed)          h = (cos psi, sin psi)
 //   visible  <=>  -(u . h_j) >= cos(hfov/2)              [and (h_j x -u) <= 0 under p2r]
 //   s2 = sin^2(psi_i - psi_j);  A,B,e linear in s2
-//   sigma = A - B |sin(phi/2)|;  sigma' = -B |cos(phi/2)| sign(s)/2;  q^2 = 1-(e c)^2
+//   sigma = A - B |sin(phi/2)|;  sigma' = -B |cos(phi/2)| sign(s)/2;  q^2 = 1-(e c)^2 = 1-e^2+(e s)^2
 //   P = f0 exp(-rho q / sigma)
 //   F = P * unit( R(phi1) (q^2 sigma,  sign(s) [q^2 B sqrt((1+c)/2)/2 + e^2 |s| c sigma]) )
 // (the common positive factor P/(sigma^2 q) of (F_rho, F_phi) is dropped before
@@ -34,6 +34,7 @@ constexpr int kMaxChunks = 64;
 template <typename T> struct PairConst {
     T sg0, sg1, sg2, sg3;  // sigma_0..3 / (q_scale * log2 e)
     T e0, e1;
+    T qa, qb, qc;          // 1 - e^2 = qa + qb s2 + qc s2^2  (qa = 1-e0^2, qb = 2 e0 e1, qc = -e1^2)
     T ncosH;               // -cos(hfov/2); +2 if hfov/2 >= pi (always visible)
     T tiny;                // guard added to rho^2 (coincident pair -> zero contribution)
 };
@@ -84,9 +85,13 @@ __device__ __forceinline__ void pair_eval(const Xycs<T>& sr, const Tgt<T>& tg, c
     const T h1 = fwd ? hsmall : hbig;
     const T h2 = fwd ? hbig : hsmall;
     const T sg = fma(-B, h1, A);
+    // q^2 = 1 - (e c)^2 = (1 - e^2) + (e s)^2: no cancellation when the target sits on the source's
+    // axis (|c| -> 1, q^2 -> 1 - e0^2 = 0.01), where an error of 2^-22 in rinv would otherwise be
+    // amplified 200x into the exponent.
     const T ec = e * c;
-    const T q2 = fma(-ec, ec, (T)1);
-    const T w = (e * fabs(s)) * ec;
+    const T es = e * fabs(s);
+    const T q2 = fma(es, es, fma(fma(k.qc, s2, k.qb), s2, k.qa));
+    const T w = es * ec;
     const T mv = fma(w, sg, (T)0.5 * (q2 * (B * h2)));
     const T grho = q2 * sg;
     const T gphi = (s == (T)0) ? (T)0 : mulsign(mv, s);
@@ -308,6 +313,9 @@ template <typename T> PairConst<T> make_const(const CsfFieldParams* fp, bool is_
     k.sg3 = (T)(fp->sigma_3 / kappa);
     k.e0 = (T)fp->e_0;
     k.e1 = (T)fp->e_1;
+    k.qa = (T)(1.0 - fp->e_0 * fp->e_0);
+    k.qb = (T)(2.0 * fp->e_0 * fp->e_1);
+    k.qc = (T)(-fp->e_1 * fp->e_1);
     k.ncosH = (fp->hfov * 0.5 >= CSF_PI) ? (T)2 : (T)(-cos(fp->hfov * 0.5));
     k.tiny = (T)(is_f32 ? 1e-6 : 1e-200);
     return k;

@@ -46,6 +46,9 @@ class AgentGroup:
     def __init__(self, model, s0, params, vd_default=None, destqueues=None, dtype=torch.float32,
                  device="cuda", q_cap=None):
         assert model in N_STATES and model != "uncontrolled"
+        _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.CsfError("no CUDA device: the csf_b200 engine has no CPU fallback")
         self.model = model
         self.params = params
         self.dtype = dtype
@@ -209,6 +212,41 @@ class AgentGroup:
         self.destq[k] = torch.as_tensor(self.destq_host[k], dtype=torch.float64, device=self.device)
         self.dest_len[k] = len(q)
 
+    _RECORD_FIELDS = ("x", "y", "psi", "v", "delta", "theta", "deltadot", "thetadot", "step_i", "dest_ptr",
+                      "znav", "znav_v0", "znav_d0", "znav_d1", "prev_x", "prev_y", "hist_x", "hist_y",
+                      "hist_step", "ip_x", "ip_zrid", "ip_delta_run", "dyn_x", "dyn_v", "br_gains")
+
+    def export_records(self):
+        """Full per-agent device state as host dicts (kept by vehicles across re-binding)."""
+        host = {n: getattr(self, n).cpu().numpy() for n in self._RECORD_FIELDS if getattr(self, n) is not None}
+        states = self.states_numpy()
+        recs = []
+        for k in range(self.n):
+            r = {"_s": states[k].copy(), "model": self.model}
+            for n, a in host.items():
+                r[n] = a[..., k].copy() if a.ndim == 2 else a[k].copy()
+            recs.append(r)
+        return recs
+
+    def import_record(self, k, rec):
+        if rec.get("model") != self.model:
+            return
+        for n in self._RECORD_FIELDS:
+            t = getattr(self, n)
+            if t is None or n not in rec:
+                continue
+            val = torch.as_tensor(np.asarray(rec[n]), dtype=t.dtype, device=t.device)
+            if t.dim() == 2:
+                t[:, k] = val
+            else:
+                t[k] = val
+
+    def cstate_range(self, first, count):
+        s = _lib.CsfAgentState()
+        C.memmove(C.byref(s), C.byref(self.cstate()), C.sizeof(s))
+        s.first, s.count = first, count
+        return s
+
     def check_status(self):
         st = int(self.status.item())
         if st & 1:
@@ -245,7 +283,12 @@ class Engine:
     """One interaction domain (``SocialForceIntersection``): groups + obstacles + road edges."""
 
     def __init__(self, groups, obstacles=None, priority_rule="unregulated", road_edges=(),
-                 dtype=torch.float32, device="cuda", q_scale=None, extent=None, scenario_size=None):
+                 dtype=torch.float32, device="cuda", q_scale=None, extent=None, scenario_size=None,
+                 n_global=None, global_offset=0, exchange=None):
+        """``n_global`` / ``global_offset`` / ``exchange``: agent-range sharding of one crowd over
+        several GPUs -- this engine owns agents [global_offset, global_offset + n) of an
+        ``n_global``-agent crowd with homogeneous field parameters; ``exchange(payload)`` is
+        called after every step to all-gather the pair payload (see distributed.py)."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.CsfError("no CUDA device: the csf_b200 engine has no CPU fallback")
@@ -257,14 +300,16 @@ class Engine:
         self.obstacles = [o for o in (obstacles or []) if o.n > 0]
         self.p2r = priority_rule == "p2r"
         self.scenario_size = scenario_size
-        off = 0
+        self.exchange = exchange
+        self.global_offset = int(global_offset)
+        off = self.global_offset
         for g in self.groups + self.obstacles:
             g.payload_offset = off
             if hasattr(g, "invalidate"):
                 g.invalidate()
             off += g.n
         self.n_agents = sum(g.n for g in self.groups)
-        self.n_total = off
+        self.n_total = off if n_global is None else int(n_global)
         # Q-format scale of the f32 payload
         if q_scale is None:
             if extent is None:
@@ -287,7 +332,11 @@ class Engine:
         self.set_road_edges(road_edges)
         # source classes: contiguous payload ranges with identical field parameters
         self.classes = []
-        for g in self.groups + self.obstacles:
+        if n_global is not None:
+            g0 = self.groups[0]
+            self.classes.append((0, self.n_total, g0.params.field_key(),
+                                 g0.params.to_field_params(self.q_scale, self.p2r)))
+        for g in (self.groups + self.obstacles if n_global is None else []):
             key = g.params.field_key()
             if self.classes and self.classes[-1][2] == key:
                 s, c, k, fp = self.classes[-1]
@@ -345,13 +394,14 @@ class Engine:
             else:
                 for ci, (s, c, _, fp) in enumerate(self.classes):
                     src = C.c_void_p(self.payload.data_ptr() + s * self.elem_bytes)
-                    _lib.check(self._fn("csf_pair_forces")(src, c, _ptr(self.payload), self.n_agents,
+                    tgt = C.c_void_p(self.payload.data_ptr() + self.global_offset * self.elem_bytes)
+                    _lib.check(self._fn("csf_pair_forces")(src, c, tgt, self.n_agents,
                                                            C.byref(fp), _ptr(self.frep), 1 if ci > 0 else 0,
                                                            _ptr(self.ws), self.ws.numel(), st), "csf_pair_forces")
                     self.gpu_launches += 2
         if self.road:
             for g in self.groups:
-                out = C.c_void_p(self.froad.data_ptr() + g.payload_offset * 2 * self.froad.element_size())
+                out = self._off(self.froad, g)
                 for ei, (verts, F_0, sigma) in enumerate(self.road):
                     _lib.check(self._fn("csf_road_forces")(_ptr(g.x), _ptr(g.y), g.n, _ptr(verts), verts.shape[0],
                                                            F_0, sigma, out, 1 if ei > 0 else 0, st),
@@ -360,7 +410,9 @@ class Engine:
         return have_rep
 
     def _off(self, t, g):
-        return C.c_void_p(t.data_ptr() + g.payload_offset * 2 * t.element_size()) if t is not None else C.c_void_p(0)
+        if t is None:
+            return C.c_void_p(0)
+        return C.c_void_p(t.data_ptr() + (g.payload_offset - self.global_offset) * 2 * t.element_size())
 
     # ---- the three public operations -----------------------------------------------------------
     def calc_forces(self):
@@ -384,11 +436,7 @@ class Engine:
                 self._off(self.force, g), _ptr(self.payload), st), "csf_agent_advance")
             self.gpu_launches += 1
 
-    def step(self):
-        """SocialForceIntersection.step (intersection.py:866-896), fused per-agent kernel."""
-        if self.n_agents == 0:
-            return
-        have_rep = self._pair_and_road()
+    def _agent_step(self, have_rep):
         st = self._stream()
         for g in self.groups:
             _lib.check(self._fn("csf_agent_step")(
@@ -396,6 +444,79 @@ class Engine:
                 self._off(self.frep, g) if have_rep else C.c_void_p(0), self._off(self.froad, g),
                 self._off(self.force, g), _ptr(self.payload), st), "csf_agent_step")
             self.gpu_launches += 1
+        if self.exchange is not None:
+            self.exchange(self.payload)
+
+    def step(self):
+        """SocialForceIntersection.step (intersection.py:866-896), fused per-agent kernel."""
+        if self.n_agents == 0:
+            return
+        self._agent_step(self._pair_and_road())
+
+    def step_host(self, host_in, host_out, host_force=None):
+        """One step driven from HOST buffers (pinned): upload the CSF state (x, y, psi, v, delta ...)
+        of every group-0 agent, step, download the new state and the total force.  This is the
+        call a host-side co-simulation loop makes; bench.py's ``e2e`` times it."""
+        g = self.groups[0]
+        for name, src in host_in.items():
+            getattr(g, name).copy_(src, non_blocking=True)
+        self.pack()
+        if self.exchange is not None:
+            self.exchange(self.payload)
+        self.step()
+        for name, dst in host_out.items():
+            dst.copy_(getattr(g, name), non_blocking=True)
+        if host_force is not None:
+            host_force.copy_(self.force[:g.n], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
 
     def check_status(self):
         return [g.check_status() for g in self.groups]
+
+    # ---- per-vehicle operations (the reference's per-vehicle hooks) -------------------------------
+    def agent_dest_force(self, g, k):
+        """Vehicle.calcDestinationForce() of one agent (mutates its navigation state)."""
+        st = g.cstate_range(k, 1)
+        _lib.check(self._fn("csf_agent_forces")(
+            _lib.MODEL_IDS[g.model], C.byref(st), C.byref(g.cparams(self.q_scale)), 1, C.c_void_p(0),
+            C.c_void_p(0), self._off(self.force, g), self._off(self.fdest, g), self._stream()), "csf_agent_forces")
+        self.gpu_launches += 1
+        f = self.fdest[g.payload_offset + k].to(torch.float64).cpu().numpy()
+        return float(f[0]), float(f[1])
+
+    def agent_advance(self, g, k, F1, F2):
+        """Vehicle.step(F1, F2) of one agent."""
+        self.force[g.payload_offset + k, 0] = float(F1)
+        self.force[g.payload_offset + k, 1] = float(F2)
+        st = g.cstate_range(k, 1)
+        _lib.check(self._fn("csf_agent_advance")(
+            _lib.MODEL_IDS[g.model], C.byref(st), C.byref(g.cparams(self.q_scale)), self._off(self.force, g),
+            _ptr(self.payload), self._stream()), "csf_agent_advance")
+        self.gpu_launches += 1
+
+    def source_field(self, src_xypsi, params, x, y, psi):
+        """Vehicle.calcRepulsiveForce(x, y, psi): field of one source at arbitrary targets,
+        without the field-of-view mask (the reference applies the mask by selecting targets)."""
+        x = np.asarray(x, dtype=float)
+        shape = x.shape
+        xs = np.r_[float(src_xypsi[0]), x.ravel()]
+        ys = np.r_[float(src_xypsi[1]), np.asarray(y, dtype=float).ravel()]
+        ps = np.r_[float(src_xypsi[2]), np.broadcast_to(np.asarray(psi, dtype=float), shape).ravel()]
+        n = xs.shape[0]
+        dev = self.device
+        q = choose_q_scale(2.0 * float(max(np.abs(xs).max(), np.abs(ys).max())) + 1000.0)
+        xd, yd, pd = (torch.as_tensor(a, dtype=torch.float64, device=dev) for a in (xs, ys, ps))
+        pay = torch.zeros((n, 4), dtype=self.payload.dtype, device=dev)
+        st = self._stream()
+        _lib.check(self._fn("csf_pack_xypsi")(_ptr(xd), _ptr(yd), _ptr(pd), n, q, _ptr(pay), st), "csf_pack_xypsi")
+        fp = params.to_field_params(q, False)
+        fp.hfov = 2 * math.pi
+        out = torch.zeros((n - 1, 2), dtype=self.dtype, device=dev)
+        wsb = int(self.lib.csf_pair_workspace_bytes(1, n - 1, 4 if self.f32 else 8))
+        ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
+        tgt = C.c_void_p(pay.data_ptr() + self.elem_bytes)
+        _lib.check(self._fn("csf_pair_forces")(_ptr(pay), 1, tgt, n - 1, C.byref(fp), _ptr(out), 0, _ptr(ws),
+                                               ws.numel(), st), "csf_pair_forces")
+        self.gpu_launches += 3
+        o = out.to(torch.float64).cpu().numpy()
+        return o[:, 0].reshape(shape), o[:, 1].reshape(shape)

@@ -1,0 +1,418 @@
+"""``SocialForceIntersection`` and the road elements with the reference's interface
+(reference src/cyclistsocialforce/intersection.py), stepping on the GPU.
+
+``step()`` issues the kernel sequence of ``engine.Engine.step`` -- nothing in this
+module computes forces or dynamics on the host.  Road geometry construction
+(``StraightRoadSegment`` / ``CurvedRoadSegment`` vertices) is host-side set-up and
+follows the reference formulas so that the same vertices reach the road-force kernel.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import AgentGroup, Engine, ObstacleGroup
+from .parameters import RoadElementParameters
+from .vehicle import UncontrolledVehicle, Vehicle
+
+
+# ---------------------------------------------------------------------------------------
+# road elements (reference intersection.py:32-250)
+# ---------------------------------------------------------------------------------------
+class RoadEdge:
+    """Polyline exerting a repulsive force on road users (reference :214-250)."""
+
+    def __init__(self, vertices, params=None):
+        self.vertices = np.ascontiguousarray(np.asarray(vertices, dtype=float))
+        self.params = params if params is not None else RoadElementParameters()
+
+    def edges_flat(self):
+        return [(self.vertices, self.params.F_0, self.params.sigma)]
+
+    def calcRepulsiveForce(self, x, y):
+        """reference :226-242, evaluated by the road-force kernel."""
+        return _road_force_on_device(self.edges_flat(), x, y)
+
+
+class RoadSegment:
+    """reference :72-115."""
+
+    def __init__(self, x0, width, ds=0.1, params=None):
+        self.params = RoadElementParameters()
+        self.x0 = x0
+        self.x1 = x0
+        self.width = width
+        self.edges = []
+        self.ds = ds
+
+    def edges_flat(self):
+        return [e.edges_flat()[0] for e in self.edges]
+
+    def calcRepulsiveForce(self, x, y):
+        return _road_force_on_device(self.edges_flat(), x, y)
+
+
+class StraightRoadSegment(RoadSegment):
+    """reference :118-146."""
+
+    def __init__(self, x0, width, length, ds=0.1, params=None):
+        params = params if params is not None else RoadElementParameters()
+        RoadSegment.__init__(self, x0, width, ds, params)
+        x0 = np.asarray(x0, dtype=float)
+        self.length = length
+        x = np.arange(0, length + self.ds, self.ds)
+        yr = -(width / 2) * np.ones_like(x)
+        yl = (width / 2) * np.ones_like(x)
+        R = np.array([[np.cos(x0[2]), -np.sin(x0[2])], [np.sin(x0[2]), np.cos(x0[2])]])
+        vert_r = R @ np.c_[x, yr].T + np.reshape(x0[:2], (2, 1))
+        vert_l = R @ np.c_[x, yl].T + np.reshape(x0[:2], (2, 1))
+        self.edges.append(RoadEdge(vert_r.T, params=params))
+        self.edges.append(RoadEdge(vert_l.T, params=params))
+        self.x1 = np.zeros_like(x0)
+        self.x1[:2] = x0[:2] + self.length * np.array([np.cos(x0[2]), np.sin(x0[2])])
+        self.x1[2] = x0[2]
+
+
+class CurvedRoadSegment(RoadSegment):
+    """reference :149-211."""
+
+    def __init__(self, x0, width, radius, angle, direction, ds=0.1, params=None):
+        params = params if params is not None else RoadElementParameters()
+        RoadSegment.__init__(self, x0, width, ds, params)
+        x0 = np.asarray(x0, dtype=float)
+        self.length = radius * angle
+        self.radius = radius
+        self.angle = angle
+        self.direction = direction
+        dir_flag = -1 * (direction == "right") + 1 * (direction == "left")
+        assert dir_flag in (-1, 1), f'direction has to be "left" or "right, instead it was {direction}'
+        beta = x0[2] - np.pi / 2
+        radius_r = radius + dir_flag * width / 2
+        radius_l = radius - dir_flag * width / 2
+        angle_r = np.linspace(0, angle, int(radius_r * angle / self.ds))
+        angle_l = np.linspace(0, angle, int(radius_l * angle / self.ds))
+        x_r = dir_flag * (radius_r * np.cos(angle_r) - radius)
+        y_r = radius_r * np.sin(angle_r)
+        x_l = dir_flag * (radius_l * np.cos(angle_l) - radius)
+        y_l = radius_l * np.sin(angle_l)
+        x1 = dir_flag * (radius * np.cos(angle) - radius)
+        y1 = radius * np.sin(angle)
+        R = np.array([[np.cos(beta), -np.sin(beta)], [np.sin(beta), np.cos(beta)]])
+        vert_r = R @ np.c_[x_r, y_r].T + np.reshape(x0[:2], (2, 1))
+        vert_l = R @ np.c_[x_l, y_l].T + np.reshape(x0[:2], (2, 1))
+        self.edges.append(RoadEdge(vert_r.T, params=params))
+        self.edges.append(RoadEdge(vert_l.T, params=params))
+        self.x1 = np.zeros((3))
+        self.x1[:2] = (R @ np.c_[x1, y1].T).flatten() + x0[:2]
+        self.x1[2] = x0[2] + dir_flag * angle
+
+
+class RoadSegmentCollection:
+    """reference :32-69."""
+
+    def __init__(self, segs):
+        self.segs = segs
+
+    def edges_flat(self):
+        return [e for seg in self.segs for e in seg.edges_flat()]
+
+    def calcRepulsiveForce(self, x, y):
+        return _road_force_on_device(self.edges_flat(), x, y)
+
+    def get_destinations_from_segments(self):
+        return [seg.x1[0] for seg in self.segs], [seg.x1[1] for seg in self.segs]
+
+    def __getitem__(self, i):
+        if not isinstance(i, int):
+            raise ValueError("Subscription index must be integer!")
+        return self.segs[i]
+
+
+def _road_force_on_device(edges, x, y):
+    """Evaluate the road force of ``edges`` at arbitrary points through the C ABI (f64)."""
+    lib = _lib.load()
+    x = np.asarray(x, dtype=float)
+    shape = x.shape
+    xd = torch.as_tensor(np.ascontiguousarray(x.ravel()), device="cuda")
+    yd = torch.as_tensor(np.ascontiguousarray(np.asarray(y, dtype=float).ravel()), device="cuda")
+    out = torch.zeros((xd.numel(), 2), dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for k, (verts, F_0, sigma) in enumerate(edges):
+        vd = torch.as_tensor(np.ascontiguousarray(verts), device="cuda").contiguous()
+        _lib.check(lib.csf_road_forces_f64(xd.data_ptr(), yd.data_ptr(), xd.numel(), vd.data_ptr(), vd.shape[0],
+                                           float(F_0), float(sigma), out.data_ptr(), 1 if k else 0, st),
+                   "csf_road_forces_f64")
+    o = out.cpu().numpy()
+    return o[:, 0].reshape(shape), o[:, 1].reshape(shape)
+
+
+# ---------------------------------------------------------------------------------------
+# the interaction manager
+# ---------------------------------------------------------------------------------------
+class SocialForceIntersection:
+    """Manages a social force intersection or open space (reference :253-915).
+
+    Extra keyword arguments of this implementation (all optional):
+      dtype        torch.float32 (production build, default) or torch.float64 (verification)
+      record_traj  keep the per-vehicle ``traj`` / ``trajF`` / ``F`` histories on the host
+                   (one device->host copy per step); default: on for <= 64 road users.
+    """
+
+    def __init__(self, vehicleList, id="", priority_rule="unregulated", animate=False, axes=None,
+                 activate_sumo_cosimulation=False, net=None, road_elements=(), bicycle_drawing_kwargs=None,
+                 dtype=torch.float32, record_traj=None, device="cuda", _private=False):
+        if animate:
+            raise NotImplementedError("matplotlib animation is outside the accelerated stepping path")
+        if activate_sumo_cosimulation:
+            raise NotImplementedError("SUMO/TraCI co-simulation stays host-side and is out of scope here")
+        assert isinstance(id, str), "Intersection ID has to be a string."
+        assert priority_rule in ("p2r", "unregulated"), "Priority rule has to be one of ('p2r','unregulated')"
+        self.id = id
+        self.priority_rule = priority_rule
+        self.animate = False
+        self.ax = axes
+        self.activate_sumo_cosimulation = False
+        self.road_elements = list(road_elements)
+        self.is_first_step = True
+        self.hist_n_vecs = []
+        self.dtype = dtype
+        self.device = device
+        self._record_traj_opt = record_traj
+        self._private = _private
+        self.vehicles = list(vehicleList)
+        self._engine = None
+        self._rebuild()
+
+    # ---- construction of the device crowd ---------------------------------------------------------
+    def _rebuild(self):
+        """(Re)create the device crowd from the vehicle list; per-vehicle device records are
+        carried over (add_road_user / remove_road_user, reference :458-539, :576-634)."""
+        if self._engine is not None:
+            self._pull_records()
+        self.n_bikes = len(self.vehicles)
+        controlled = [v for v in self.vehicles if v.MODEL is not None]
+        obstacles = [v for v in self.vehicles if v.MODEL is None]
+        # one group per (model, params object identity-equivalent field/agent parameters)
+        groups, order = [], {}
+        for v in controlled:
+            key = (v.MODEL, _params_key(v.params))
+            order.setdefault(key, []).append(v)
+        for (model, _), vs in order.items():
+            s0 = np.stack([v._s for v in vs])
+            g = AgentGroup(model, s0, vs[0].params, vd_default=[v.params.v_desired_default for v in vs],
+                           destqueues=[v._destqueue for v in vs], dtype=self.dtype, device=self.device)
+            for k, v in enumerate(vs):
+                if v._record is not None:
+                    g.import_record(k, v._record)
+                v._owner, v._group, v._k = self, g, k
+            groups.append(g)
+        obs = []
+        if obstacles:
+            pk = {}
+            for v in obstacles:
+                pk.setdefault(_params_key(v.params), []).append(v)
+            for vs in pk.values():
+                o = ObstacleGroup(np.stack([v._s[:3] for v in vs]), vs[0].params, device=self.device)
+                o.vehicles = vs
+                for v in vs:
+                    v._owner, v._group, v._k = self, None, -1
+                obs.append(o)
+        self._groups, self._obstacle_groups = groups, obs
+        self._obstacles_dirty = False
+        edges = [e for el in self.road_elements for e in el.edges_flat()]
+        if self.n_bikes > 0:
+            self._engine = Engine(groups, obstacles=obs, priority_rule=self.priority_rule, road_edges=edges,
+                                  dtype=self.dtype, device=self.device)
+        else:
+            self._engine = None
+        self._invalidate()
+        rt = self._record_traj_opt
+        self.record_traj = (self.n_bikes <= 64) if rt is None else bool(rt)
+
+    def _pull_records(self):
+        for g in self._groups:
+            recs = g.export_records()
+            for v in self.vehicles:
+                if v._group is g:
+                    v._record = recs[v._k]
+                    v._s = recs[v._k]["_s"]
+                    v._i = int(recs[v._k]["step_i"])
+                    v._destpointer = int(recs[v._k]["dest_ptr"])
+
+    # ---- cached host snapshots -----------------------------------------------------------------------
+    def _invalidate(self):
+        self._cache = {}
+
+    def _host_state(self, g):
+        key = ("s", id(g))
+        if key not in self._cache:
+            self._cache[key] = g.states_numpy()
+        return self._cache[key]
+
+    def _host_field(self, g, name):
+        key = (name, id(g))
+        if key not in self._cache:
+            self._cache[key] = getattr(g, name).cpu().numpy()
+        return self._cache[key]
+
+    def _host_force(self):
+        if "force" not in self._cache:
+            self._cache["force"] = self._engine.force.to(torch.float64).cpu().numpy()
+        return self._cache["force"]
+
+    # ---- reference attributes ------------------------------------------------------------------------------
+    def _xypsi(self):
+        out = np.zeros((self.n_bikes, 3))
+        for i, v in enumerate(self.vehicles):
+            out[i] = v.s[:3]
+        return out
+
+    @property
+    def vehicleX(self):
+        return self._xypsi()[:, 0:1]
+
+    @property
+    def vehicleY(self):
+        return self._xypsi()[:, 1:2]
+
+    @property
+    def vehicleTheta(self):
+        return self._xypsi()[:, 2:3]
+
+    def update_road_user_positions(self):
+        """reference :660-688: state -> pair payload (device side)."""
+        if self._engine is not None:
+            self._sync_obstacles()
+            self._engine.pack()
+
+    def _sync_obstacles(self):
+        if self._obstacles_dirty:
+            for o in self._obstacle_groups:
+                o.set(np.stack([v._s[:3] for v in o.vehicles]))
+            self._engine.pack()
+            self._obstacles_dirty = False
+
+    # ---- road users --------------------------------------------------------------------------------------
+    def add_road_user(self, user):
+        """reference :458-539."""
+        self.vehicles.append(user)
+        self._rebuild()
+
+    def get_road_user_ids(self):
+        return [v.id for v in self.vehicles]
+
+    def remove_road_user(self, i):
+        """reference :576-616."""
+        self._pull_records()
+        v = self.vehicles.pop(i)
+        v._owner = v._group = None
+        self._rebuild()
+        return v
+
+    def remove_road_users_by_id(self, ids):
+        """reference :618-634."""
+        self._pull_records()
+        keep = []
+        for v in self.vehicles:
+            if v.id in ids:
+                v._owner = v._group = None
+            else:
+                keep.append(v)
+        self.vehicles = keep
+        self._rebuild()
+
+    # ---- the hot path ---------------------------------------------------------------------------------------
+    def _force_in_vehicle_order(self):
+        f = self._host_force()
+        out = np.zeros((self.n_bikes, 2))
+        for i, v in enumerate(self.vehicles):
+            if v._group is not None:
+                out[i] = f[v._group.payload_offset + v._k]
+        return out
+
+    def calc_forces(self):
+        """reference :747-864 -> (Fx, Fy) ndarrays of shape (n_bikes,)."""
+        if self._engine is None:
+            return np.zeros(0), np.zeros(0)
+        self._sync_obstacles()
+        self._engine.calc_forces()
+        self._invalidate()
+        f = self._force_in_vehicle_order()
+        if self.record_traj:
+            for i, v in enumerate(self.vehicles):
+                v.F.append(float(np.hypot(f[i, 0], f[i, 1])))
+        return f[:, 0].copy(), f[:, 1].copy()
+
+    def step(self):
+        """reference :866-896."""
+        self.is_first_step = False
+        if self.n_bikes > 0 and self._engine is not None:
+            self._sync_obstacles()
+            self._engine.step()
+            for o in self._obstacle_groups:
+                for v in o.vehicles:
+                    v.step()
+            self._invalidate()
+            if self.record_traj:
+                self._record_histories()
+        self.hist_n_vecs.append(self.n_bikes)
+
+    def _record_histories(self):
+        f = self._force_in_vehicle_order()
+        for i, v in enumerate(self.vehicles):
+            if v._group is None:
+                continue
+            s = self._host_state(v._group)[v._k]
+            idx = int(self._host_field(v._group, "step_i")[v._k]) % v._traj.shape[1]
+            v._traj[:, idx] = s
+            v.F.append(float(np.hypot(f[i, 0], f[i, 1])))
+            if v.trajF is not None:
+                v.trajF[:, idx] = f[i]
+        self._engine.check_status()
+
+    def check_status(self):
+        """Raise if the device flagged non-finite values, an invalid navigation state or a
+        position outside the payload range (the reference raises from Python in these cases)."""
+        if self._engine is not None:
+            return self._engine.check_status()
+        return []
+
+    def set_animated(self, animated):
+        pass
+
+    # ---- per-vehicle operations (Vehicle.calcDestinationForce / calcRepulsiveForce / step) ---------------------
+    def _vehicle_dest_force(self, v):
+        f = self._engine.agent_dest_force(v._group, v._k)
+        self._invalidate()
+        return f
+
+    def _vehicle_rep_force(self, v, x, y, psi):
+        return self._engine.source_field(v.s[:3], v.params, x, y, psi)
+
+    def _vehicle_step(self, v, F1, F2):
+        self._engine.agent_advance(v._group, v._k, F1, F2)
+        self._invalidate()
+        if self.record_traj:
+            s = self._host_state(v._group)[v._k]
+            idx = int(self._host_field(v._group, "step_i")[v._k]) % v._traj.shape[1]
+            v._traj[:, idx] = s
+            if v.trajF is not None:
+                v.trajF[:, idx] = (F1, F2)
+
+
+def _params_key(p):
+    """Vehicles share a device group when every kernel-visible parameter agrees
+    (``v_desired_default`` is per agent and therefore excluded)."""
+    items = []
+    for k, val in sorted(vars(p).items()):
+        if k in ("_v_desired_default", "verbose", "calib_mode", "rep_force", "dest_force", "dynamics"):
+            continue
+        if isinstance(val, (list, tuple, np.ndarray)):
+            val = tuple(np.asarray(val).ravel().tolist())
+        elif isinstance(val, dict):
+            val = tuple(sorted((kk, float(vv)) for kk, vv in val.items() if isinstance(vv, (int, float))))
+        elif not isinstance(val, (int, float, str, bool, type(None))):
+            continue
+        items.append((k, val))
+    return (type(p).__name__, tuple(items))

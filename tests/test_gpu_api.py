@@ -1,0 +1,233 @@
+"""The reference-facing Python API on the GPU: scenarios written the way the reference's
+demo / scenario scripts write them, checked against the oracle and the golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import csf_oracle as co
+from helpers import oracle_world
+from cyclistsocialforce_b200 import parameters as P
+from cyclistsocialforce_b200.intersection import (CurvedRoadSegment, RoadSegmentCollection,
+                                                  SocialForceIntersection, StraightRoadSegment)
+from cyclistsocialforce_b200.scenario import Scenario
+from cyclistsocialforce_b200.vehicle import (BalancingRiderBicycle, InvPendulumBicycle, PlanarPointBicycle,
+                                             TwoDBicycle, UncontrolledVehicle)
+
+pytestmark = pytest.mark.gpu
+
+
+def _demo_bikes(cls):
+    """demo/demoCSFstandalone.py:101-118."""
+    bike1 = cls((-23 + 17, 0, 0, 5, 0, 0, 0, 0), id="a", saveForces=True)
+    bike1.params.v_desired_default = 4.5
+    bike2 = cls((0 + 15, -20, np.pi / 2, 5, 0, 0, 0, 0), id="b", saveForces=True)
+    bike2.params.v_desired_default = 5.0
+    bike3 = cls((-2 + 15, -20, np.pi / 2, 5, 0, 0, 0, 0), id="c", saveForces=True)
+    bike3.params.v_desired_default = 5.0
+    bike1.setDestinations((35, 64, 65), (0, 0, 0))
+    bike2.setDestinations((15, 15, 15), (20, 49, 50))
+    bike3.setDestinations((13, 13, 13), (20, 49, 50))
+    return bike1, bike2, bike3
+
+
+@pytest.mark.parametrize("cls,model", [(TwoDBicycle, "twod"), (PlanarPointBicycle, "planarpoint"),
+                                       (InvPendulumBicycle, "invpendulum")])
+def test_demo_scenario_f64(golden, cls, model):
+    """BASELINE config 1, written like the reference's DemoScenario."""
+    bikes = _demo_bikes(cls)
+
+    class DemoScenario(Scenario):
+        def __init__(self):
+            self.intersection = SocialForceIntersection(bikes, activate_sumo_cosimulation=False,
+                                                        dtype=torch.float64)
+            Scenario.__init__(self, self._step_func, verbose=False, realtime=False)
+
+        def _step_func(self):
+            self.intersection.step()
+
+    scn = DemoScenario()
+    scn.run(7)
+    assert scn.i == 700
+    s = np.array([b.s for b in scn.intersection.vehicles])
+    k = golden[f"demo_{model}_steps"].tolist().index(700)
+    assert np.abs(s - golden[f"demo_{model}_s"][k]).max() < 1e-8
+    f = np.array([b.force for b in scn.intersection.vehicles])
+    assert np.abs(f - golden[f"demo_{model}_F"][k]).max() < 1e-8
+    # histories like the reference keeps them
+    b = scn.intersection.vehicles[0]
+    assert b.i == 700 and len(b.F) == 700 and np.array_equal(b.traj[:, 700], b.s)
+    assert np.allclose(b.trajF[:, 700], f[0])
+    assert scn.intersection.hist_n_vecs == [3] * 700
+
+
+def test_demo_scenario_f32_drift(golden):
+    """fp32 production build on the demo: bounded trajectory drift over 700 steps (reported)."""
+    ins = SocialForceIntersection(_demo_bikes(TwoDBicycle), dtype=torch.float32)
+    for _ in range(700):
+        ins.step()
+    s = np.array([b.s for b in ins.vehicles])
+    ref = golden["demo_twod_s"][golden["demo_twod_steps"].tolist().index(700)]
+    drift = np.abs(s - ref)
+    from test_gpu_parity import report
+    report(test="demo_f32_drift_700_steps", max_pos_m=float(drift[:, :2].max()), max_other=float(drift[:, 2:].max()))
+    assert drift[:, :2].max() < 5e-3 and drift[:, 2:].max() < 5e-3
+
+
+def test_parcours_scenario_f64(golden):
+    """BASELINE config 2 (scenarios/parcours-scenario.py:31-40)."""
+    ins = SocialForceIntersection([], dtype=torch.float64)
+    b = BalancingRiderBicycle((0, 0, np.pi / 2, 5, 0, 0, 0, 0), id="BalancingRiderBike", saveForces=True)
+    b.params.v_desired_default = 4.0
+    destx = [0, 10, 0, 5, 10, 20, 21, 22, 23]
+    desty = [10, 20, 30, 40, 40, 40, 40, 40, 40]
+    b.setDestinations(destx, desty)
+    ins.add_road_user(b)
+    scn = Scenario(ins.step, verbose=False, realtime=False)
+    scn.run(15)
+    assert np.abs(b.s - golden["parcours_s"][-1][0]).max() < 1e-7
+    assert b.destpointer == int(golden["parcours_ptr"][0])
+
+
+def test_add_and_remove_road_users():
+    """Churn (reference :458-539, :576-634): results equal a crowd that never changed."""
+    s0, q = co.synthetic_crowd(12, seed=4, spacing=3.0)
+
+    def mk(k):
+        b = TwoDBicycle(tuple(s0[k]), id=f"v{k}")
+        b.setDestinations(q[k, :, 0], q[k, :, 1])
+        return b
+
+    ins = SocialForceIntersection([mk(k) for k in range(12)], dtype=torch.float64)
+    ref = SocialForceIntersection([mk(k) for k in range(12)], dtype=torch.float64)
+    for _ in range(30):
+        ins.step()
+        ref.step()
+    extra = TwoDBicycle((200.0, 200.0, 0.0, 5.0, 0.0), id="far")      # far away: negligible interaction
+    extra.setDestinations((260.0,), (200.0,))
+    ins.add_road_user(extra)
+    assert ins.n_bikes == 13 and ins.get_road_user_ids()[-1] == "far"
+    for _ in range(5):
+        ins.step()
+        ref.step()
+    ins.remove_road_users_by_id(["far"])
+    assert ins.n_bikes == 12 and extra._owner is None
+    for _ in range(20):
+        ins.step()
+        ref.step()
+    a = np.array([v.s for v in ins.vehicles])
+    b = np.array([v.s for v in ref.vehicles])
+    assert np.abs(a - b).max() < 1e-9
+    assert [v.i for v in ins.vehicles] == [55] * 12
+
+
+def test_vehicle_hooks_match_oracle():
+    """Vehicle.calcRepulsiveForce / calcDestinationForce / step used on their own."""
+    b = TwoDBicycle((1.0, 2.0, 0.4, 5.0, 0.0), id="solo")
+    b.setDestinations((40.0, 80.0), (10.0, 30.0))
+    ins = SocialForceIntersection([b], dtype=torch.float64)
+    rng = np.random.default_rng(0)
+    x, y, psi = rng.uniform(-8, 10, 50), rng.uniform(-8, 10, 50), rng.uniform(-3, 3, 50)
+    fx, fy = b.calcRepulsiveForce(x, y, psi)
+    p = co.default_params("twod")
+    ox, oy = co.twod_field(1.0, 2.0, 0.4, co.field_params_array([p])[0], x, y, psi)
+    assert np.abs(fx - ox).max() < 1e-12 and np.abs(fy - oy).max() < 1e-12
+    A = co.Agents("twod", np.array([[1.0, 2.0, 0.4, 5.0, 0.0]]))
+    A.set_destinations(0, (40.0, 80.0), (10.0, 30.0))
+    for _ in range(5):
+        f = b.calcDestinationForce()
+        fo = A.calc_destination_force(0)
+        assert np.abs(np.array(f) - np.array(fo)).max() < 1e-11
+        b.step(*f)
+        A.step_agent(0, *fo)
+        assert np.abs(b.s - A.s[0]).max() < 1e-12
+    assert b.i == 5
+
+
+def test_obstacle_and_mixed_parameters():
+    """UncontrolledVehicle sources (hfov = 2 pi) + two bicycle parameter sets in one intersection."""
+    s0, q = co.synthetic_crowd(10, seed=8, spacing=2.5)
+    wide = P.InvPendulumBicycleParameters(hfov=np.pi, f_0=5.0)
+    bikes = []
+    for k in range(10):
+        b = TwoDBicycle(tuple(s0[k]), id=f"v{k}", params=wide if k >= 6 else None)
+        b.setDestinations(q[k, :, 0], q[k, :, 1])
+        bikes.append(b)
+    traj = np.array([[3.0 + 0.02 * t, 3.0, 0.0, 2.0] for t in range(200)]).T
+    car = UncontrolledVehicle((3.0, 3.0, 0.0, 2.0), trajectory=traj, id="car")
+    ins = SocialForceIntersection(bikes + [car], dtype=torch.float64)
+    g1 = co.Agents("twod", s0[:6], destqueue=None)
+    g2 = co.Agents("twod", s0[6:], params=co.default_params("twod", hfov=np.pi, f_0=5.0))
+    for k in range(6):
+        g1.set_destinations(k, q[k, :, 0], q[k, :, 1])
+    for k in range(4):
+        g2.set_destinations(k, q[6 + k, :, 0], q[6 + k, :, 1])
+    g3 = co.Agents("uncontrolled", np.array([[3.0, 3.0, 0.0, 2.0]]), uncontrolled_traj=[traj])
+    W = co.World([g1, g2, g3])
+    for _ in range(40):
+        ins.step()
+        W.step()
+    got = np.array([b.s for b in bikes])
+    ref = np.vstack([g1.s, g2.s])
+    assert np.abs(got - ref).max() < 1e-9
+    assert abs(car.s[0] - g3.s[0, 0]) < 1e-15
+
+
+def test_road_elements_in_intersection():
+    """scenarios/curve-scenario.py geometry: road-edge force added after the clip (:854-857)."""
+    roadparams = P.RoadElementParameters(sigma=2.0, F_0=0.15)
+    seg1 = StraightRoadSegment(np.array((0, -20, np.pi / 2)), 5, 25, params=roadparams, ds=0.1)
+    seg2 = CurvedRoadSegment(seg1.x1, 5, 10, np.pi / 2, "right", params=roadparams, ds=0.1)
+    segs = RoadSegmentCollection((seg1, seg2))
+    bikes = []
+    for k, (x, y) in enumerate([(0.5, -19.0), (-0.8, -15.0)]):
+        b = TwoDBicycle((x, y, np.pi / 2, 4.0, 0.0), id=f"r{k}")
+        b.setDestinations((0.0, 3.0, 10.0), (0.0, 12.0, 15.0))
+        bikes.append(b)
+    ins = SocialForceIntersection(bikes, road_elements=[segs], dtype=torch.float64)
+    A = co.Agents("twod", np.array([b.s for b in bikes]))
+    for k in range(2):
+        A.set_destinations(k, (0.0, 3.0, 10.0), (0.0, 12.0, 15.0))
+    W = co.World([A], road_edges=segs.edges_flat())
+    for _ in range(150):
+        ins.step()
+        W.step()
+    assert np.abs(np.array([b.s for b in bikes]) - A.s).max() < 1e-9
+    fx, fy = ins.calc_forces()
+    ofx, ofy = W.calc_forces()
+    assert np.abs(fx - ofx).max() < 1e-9 and np.abs(fy - ofy).max() < 1e-9
+
+
+def test_f32_per_step_error_against_f64_build():
+    """Per-step error of the fp32 production build: both builds start every step from the
+    same (fp64-build) state; north_star tolerance 1e-4 relative per step."""
+    from gpu_helpers import make_engine
+    from test_gpu_parity import report, _vec_rel, _rel
+    n = 2048
+    s0, q = co.synthetic_crowd(n, seed=33, spacing=3.0)
+    e64, g64 = make_engine("twod", s0, 5.0, q, dtype=torch.float64)
+    e32, g32 = make_engine("twod", s0, 5.0, q, dtype=torch.float32, q_scale=e64.q_scale)
+    worst_f = worst_s = 0.0
+    fields = ("x", "y", "psi", "v", "delta", "step_i", "dest_ptr", "znav", "znav_v0", "znav_d0", "znav_d1",
+              "prev_x", "prev_y", "hist_x", "hist_y", "hist_step")
+    for step in range(30):
+        for name in fields:
+            getattr(g32, name).copy_(getattr(g64, name).to(getattr(g32, name).dtype))
+        e32.pack()
+        e64.step()
+        e32.step()
+        f64 = e64.force.cpu().numpy()
+        f32 = e32.force.cpu().numpy().astype(float)
+        s64, s32 = g64.states_numpy(), g32.states_numpy()
+        # total force = clipped repulsive + destination term (|.| ~ v_d = 5) which may cancel:
+        # the error is taken relative to max(|F|, 1).  States: positions / speed relative to
+        # max(|.|, 1), steer angle relative to max(|.|, 0.1 rad), yaw absolute [rad].
+        ef = _vec_rel(f32, f64, 1.0)
+        es = np.maximum(_rel(s32[:, [0, 1, 3]], s64[:, [0, 1, 3]], 1.0).max(axis=1),
+                        _rel(s32[:, 4], s64[:, 4], 0.1))
+        es = np.maximum(es, np.abs(np.angle(np.exp(1j * (s32[:, 2] - s64[:, 2])))))
+        # agents whose FOV mask flips between the builds (pair exactly on the boundary) are
+        # tolerated: at most 2 of 2048 per step
+        worst_f = max(worst_f, np.sort(ef)[-3])
+        worst_s = max(worst_s, np.sort(es)[-3])
+        assert (ef > 1e-4).sum() <= 2 and (es > 1e-4).sum() <= 2, (step, np.sort(ef)[-6:], np.sort(es)[-6:])
+    report(test="f32_per_step_vs_f64", n=n, steps=30, force_rel_3rd_worst=float(worst_f), state_rel_3rd_worst=float(worst_s))

@@ -1,0 +1,152 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, the host
+mirror of the reference interface behaves like the reference, and the product path fails
+loudly without a GPU (no fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import csf_oracle as co
+from cyclistsocialforce_b200 import _lib, parameters as P, vehicle as V
+from cyclistsocialforce_b200 import intersection as I
+from cyclistsocialforce_b200.scenario import Scenario
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAS_CUDA = torch.cuda.is_available()
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "csf_b200.h")).read()
+    declared = set(re.findall(r"\b(csf_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.csf_version() == 1
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirrors vs the C compiler's sizeof (gcc on the header)."""
+    import subprocess, tempfile, ctypes
+    src = ('#include "csf_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu\\n",'
+           'sizeof(CsfAgentParams),sizeof(CsfAgentState),sizeof(CsfFieldParams));return 0;}')
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(d, "s")])
+        out = subprocess.check_output([os.path.join(d, "s")]).decode().split()
+    assert [int(x) for x in out] == [ctypes.sizeof(_lib.CsfAgentParams), ctypes.sizeof(_lib.CsfAgentState),
+                                     ctypes.sizeof(_lib.CsfFieldParams)]
+
+
+@pytest.mark.parametrize("model,cls", [("twod", P.InvPendulumBicycleParameters),
+                                       ("balancingrider", P.BalancingRiderBicycleParameters),
+                                       ("planarpoint", P.PlanarPointBicycleParameters),
+                                       ("bicycle", P.BicycleParameters), ("uncontrolled", P.CarParameters)])
+def test_parameter_defaults_match_reference(model, cls):
+    """Defaults equal the oracle's table, which is pinned to the reference (Appendix C)."""
+    ref = co.default_params(model)
+    p = cls()
+    for name, val in vars(ref).items():
+        if name in ("bike", "pole_model", "k_psi", "tau_1_squared"):
+            continue
+        got = getattr(p, name)
+        assert np.allclose(np.asarray(got, float), np.asarray(val, float), rtol=0, atol=0), name
+    if model == "twod":
+        assert p.tau_1_squared == ref.tau_1_squared
+        ap = p.to_agent_params(2.0 ** -20, 6, 128)
+        assert ap.traj_len == 3000 and ap.hist_len == 100
+        kx, ku = co.invpend_gains(4.0)
+        assert np.allclose(p.fullstate_feedback_gains(4.0)[0].ravel(), kx) and p.fullstate_feedback_gains(4.0)[1] == ku
+
+
+def test_balancingrider_constants_match_oracle():
+    p = P.BalancingRiderBicycleParameters()
+    ap = p.to_agent_params(1.0, 4, 128)
+    for v in (1.5, 4.0, 6.5):
+        A, B = co.balancingrider_matrices(co.BALANCEASSIST, v)
+        Ak = (np.array(ap.br_A0) + v * np.array(ap.br_A1) + v * v * np.array(ap.br_A2)).reshape(5, 5)
+        assert np.abs(Ak - A).max() < 1e-12
+        assert np.abs(np.array(ap.br_B) - B).max() < 1e-15
+        assert np.allclose(np.sort_complex(np.array(p.poles_at(v))),
+                           np.sort_complex(co.balancingrider_poles(("BR1", 0), v)))
+    assert abs(p.l - 1.113) < 1e-15 and abs(p.m - 102.12) < 1e-9
+
+
+def test_parameter_error_behaviour():
+    with pytest.raises(TypeError):
+        P.RoadElementParameters(F_0=1)           # reference: "F_0 must be a float."
+    with pytest.raises(ValueError):
+        P.RoadElementParameters(sigma=-1.0)
+    r = P.RoadElementParameters()
+    with pytest.raises(AttributeError):
+        r.F_0 = 0.3                               # immutable (parameters.py:385-386)
+    with pytest.raises(TypeError):
+        V.TwoDBicycle((0, 0, 0, 5, 0), params=P.BicycleParameters())
+    with pytest.raises(ValueError):
+        V.TwoDBicycle((0, 0, 0))                  # too few states (vehicle.py:149-150)
+    with pytest.raises(NotImplementedError):
+        V.Vehicle((0, 0, 0, 1), rep_force_func=lambda *a: (0, 0))
+
+
+def test_vehicle_host_logic():
+    b = V.TwoDBicycle((1, 2, 7.0, 5, 0.1, 9, 9), id="a")       # extra states are cut (vehicle.py:151-152)
+    assert b.s.shape == (5,) and abs(b.s[2] - co.limit_angle(7.0)) < 1e-15
+    assert b.N_STATES == 5 and b.STATE_NAMES[4] == "delta[rad]"
+    assert np.array_equal(b.destqueue, [[1, 2, 0]])            # vehicle.py:183-185
+    b.setDestinations((10, 20), (0, 5))
+    assert b.destqueue.shape == (3, 3) and not b.isLastDest()
+    b.setDestinations(3.0, 4.0, stop=1.0, reset=True)
+    assert np.array_equal(b.destqueue, [[3, 4, 1]]) and b.isLastDest() and b.destpointer == 0
+    assert abs(b.getDestinationDistance() - np.hypot(2, 2)) < 1e-15
+    assert b.traj.shape == (5, 3000) and np.array_equal(b.traj[:, 0], b.s)
+    assert V.InvertedPendulumBicycle is V.InvPendulumBicycle
+    ip = V.InvPendulumBicycle((0, 0, 0, 1.0, 0, 0))
+    assert ip.zrid.tolist() == [False, True]                   # starts walking below v_max_walk
+    u = V.UncontrolledVehicle((0, 0, 0, 0), trajectory=np.array([[0, 1, 2], [0, 0, 0], [0, 0, 0], [1, 1, 1]]))
+    u.step()
+    assert u.s[0] == 1.0
+    assert u.calcDestinationForce() == (0, 0)
+
+
+def test_road_geometry_matches_reference(golden):
+    seg1 = I.StraightRoadSegment(np.array([0.0, 0.0, np.pi / 2]), 3.0, 20.0,
+                                 params=P.RoadElementParameters(F_0=0.15, sigma=2.0))
+    seg2 = I.CurvedRoadSegment(seg1.x1, 3.0, 8.0, np.pi / 2, "right",
+                               params=P.RoadElementParameters(F_0=0.15, sigma=2.0))
+    col = I.RoadSegmentCollection([seg1, seg2])
+    flat = col.edges_flat()
+    assert len(flat) == 4
+    for k, (verts, F_0, sigma) in enumerate(flat):
+        assert np.abs(verts - golden[f"road_edge{k}"]).max() < 1e-13
+        assert (F_0, sigma) == (0.15, 2.0)
+    assert np.abs(np.array([seg1.x1, seg2.x1]) - golden["road_x1"]).max() < 1e-13
+
+
+def test_scenario_loop():
+    calls = []
+    scn = Scenario(lambda: calls.append(1), t_s=0.01, t_r=0.0, verbose=False)
+    scn.run(0.25)
+    assert len(calls) == 25 and scn.i == 25 and abs(scn.t - 0.25) < 1e-12
+    scn.reset()
+    assert scn.i == 0 and scn.t == 0
+    with pytest.raises(NotImplementedError):
+        Scenario(lambda: None, animate=True)
+
+
+@pytest.mark.skipif(HAS_CUDA, reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    b = V.TwoDBicycle((0, 0, 0, 5, 0))
+    with pytest.raises(_lib.CsfError):
+        I.SocialForceIntersection([b])
+    with pytest.raises(_lib.CsfError):
+        b.calcDestinationForce()
+
+
+def test_q_scale_choice():
+    q = P.choose_q_scale(5000.0)
+    assert 5000.0 / q <= 2 ** 30 < 2 * 5000.0 / q * 1.0000001 * 2
+    assert np.log2(q) == np.floor(np.log2(q))
