@@ -76,6 +76,16 @@ SIGNATURES = {
     "csf_pair_forces_f64": (C.c_int, [_vp, _i64, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp]),
     "csf_pair_forces_grouped_f32": (C.c_int, [_vp, _i64, _i32, _FP, _vp, _vp]),
     "csf_pair_forces_grouped_f64": (C.c_int, [_vp, _i64, _i32, _FP, _vp, _vp]),
+    "csf_tiled_padded_sources": (_i64, [_i64]),
+    "csf_tiled_num_tiles": (_i64, [_i64]),
+    "csf_tiled_tile_bytes": (C.c_int, [C.c_int]),
+    "csf_pair_tiled_workspace_bytes": (_sz, [_i64, _i64, C.c_int]),
+    "csf_morton_keys_f32": (C.c_int, [_vp, _i64, _dbl, _dbl, _dbl, _vp, _vp]),
+    "csf_morton_keys_f64": (C.c_int, [_vp, _i64, _dbl, _dbl, _dbl, _vp, _vp]),
+    "csf_tile_sources_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "csf_tile_sources_f64": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "csf_pair_forces_tiled_f32": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp]),
+    "csf_pair_forces_tiled_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp]),
     "csf_road_forces_f32": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _dbl, _dbl, _vp, C.c_int, _vp]),
     "csf_road_forces_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _dbl, _dbl, _vp, C.c_int, _vp]),
     "csf_agent_forces_f32": (C.c_int, [C.c_int, _AS, _AP, _i64, _vp, _vp, _vp, _vp, _vp]),

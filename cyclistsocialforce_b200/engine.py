@@ -284,7 +284,8 @@ class Engine:
 
     def __init__(self, groups, obstacles=None, priority_rule="unregulated", road_edges=(),
                  dtype=torch.float32, device="cuda", q_scale=None, extent=None, scenario_size=None,
-                 n_global=None, global_offset=0, exchange=None):
+                 n_global=None, global_offset=0, exchange=None, pair_mode="auto", resort_every=32,
+                 count_pairs=False):
         """``n_global`` / ``global_offset`` / ``exchange``: agent-range sharding of one crowd over
         several GPUs -- this engine owns agents [global_offset, global_offset + n) of an
         ``n_global``-agent crowd with homogeneous field parameters; ``exchange(payload)`` is
@@ -301,6 +302,11 @@ class Engine:
         self.p2r = priority_rule == "p2r"
         self.scenario_size = scenario_size
         self.exchange = exchange
+        # pair kernel choice: "dense" (thread-per-target, every pair), "tiled" (spatially tiled
+        # sources + field-of-view culling), "auto" = tiled from 2048 road users on
+        assert pair_mode in ("auto", "dense", "tiled")
+        self.pair_mode = pair_mode
+        self.resort_every = int(resort_every)
         self.global_offset = int(global_offset)
         off = self.global_offset
         for g in self.groups + self.obstacles:
@@ -347,6 +353,24 @@ class Engine:
         if self.n_total > 1 and scenario_size is None:
             for s, c, _, _ in self.classes:
                 wsb = max(wsb, int(self.lib.csf_pair_workspace_bytes(c, self.n_agents, 4 if self.f32 else 8)))
+        self.tiled = (scenario_size is None and self.n_total > 1 and
+                      (pair_mode == "tiled" or (pair_mode == "auto" and self.n_total >= 2048)))
+        self.pair_stats = torch.zeros(1, dtype=torch.int64, device=self.device) if count_pairs else None
+        self._tiles = []
+        self._pair_calls = 0
+        if self.tiled:
+            eb = 4 if self.f32 else 8
+            tile_elems = self.lib.csf_tiled_tile_bytes(eb) // eb
+            for s, c, _, _ in self.classes:
+                n_pad = int(self.lib.csf_tiled_padded_sources(c))
+                n_tiles = int(self.lib.csf_tiled_num_tiles(c))
+                self._tiles.append(dict(
+                    sorted=torch.zeros((n_pad, 4), dtype=self.payload.dtype, device=self.device),
+                    tiles=torch.zeros((n_tiles, tile_elems), dtype=self.payload.dtype, device=self.device),
+                    keys=torch.zeros(c, dtype=torch.int64, device=self.device), perm=None))
+                wsb = max(wsb, int(self.lib.csf_pair_tiled_workspace_bytes(c, self.n_agents, eb)))
+            self._morton = (-float(extent if extent is not None else 2.0 ** 30 * self.q_scale),
+                            2.0 * float(extent if extent is not None else 2.0 ** 30 * self.q_scale) / 65536.0)
         self.ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=self.device)
         self.gpu_launches = 0
         self.pack()
@@ -392,9 +416,27 @@ class Engine:
                                                                _ptr(self.frep), st), "csf_pair_forces_grouped")
                 self.gpu_launches += 1
             else:
+                resort = self.tiled and (self._pair_calls % max(self.resort_every, 1) == 0)
+                self._pair_calls += 1
                 for ci, (s, c, _, fp) in enumerate(self.classes):
                     src = C.c_void_p(self.payload.data_ptr() + s * self.elem_bytes)
                     tgt = C.c_void_p(self.payload.data_ptr() + self.global_offset * self.elem_bytes)
+                    if self.tiled:
+                        tl = self._tiles[ci]
+                        if resort or tl["perm"] is None:
+                            _lib.check(self._fn("csf_morton_keys")(src, c, self._morton[0], self._morton[0],
+                                                                   self._morton[1], _ptr(tl["keys"]), st),
+                                       "csf_morton_keys")
+                            tl["perm"] = torch.argsort(tl["keys"])
+                            self.gpu_launches += 1
+                        _lib.check(self._fn("csf_tile_sources")(src, c, _ptr(tl["perm"]), _ptr(tl["sorted"]),
+                                                                _ptr(tl["tiles"]), st), "csf_tile_sources")
+                        _lib.check(self._fn("csf_pair_forces_tiled")(
+                            _ptr(tl["sorted"]), _ptr(tl["tiles"]), c, tgt, self.n_agents, C.byref(fp),
+                            _ptr(self.frep), 1 if ci > 0 else 0, _ptr(self.ws), self.ws.numel(),
+                            _ptr(self.pair_stats), st), "csf_pair_forces_tiled")
+                        self.gpu_launches += 3
+                        continue
                     _lib.check(self._fn("csf_pair_forces")(src, c, tgt, self.n_agents,
                                                            C.byref(fp), _ptr(self.frep), 1 if ci > 0 else 0,
                                                            _ptr(self.ws), self.ws.numel(), st), "csf_pair_forces")

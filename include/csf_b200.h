@@ -156,6 +156,38 @@ int csf_pair_forces_grouped_f32(const void* xycs, int64_t n, int32_t group, cons
 int csf_pair_forces_grouped_f64(const void* xycs, int64_t n, int32_t group, const CsfFieldParams* fp,
                                 double* frep_xy, csf_stream_t stream);
 
+/* ---- K1, tiled variant with exact field-of-view culling ----------------------------------
+ * Same result as csf_pair_forces_* up to the order of summation (the f32 build additionally
+ * drops tiles whose every contribution is below 2^-40 f_0).  Sources are passed as a spatially
+ * sorted, tile-padded copy with one bounding record per tile of 64:
+ *   csf_morton_keys_*   : int64 Morton key per payload element (x0,y0,cell only used by _f64);
+ *                         the caller sorts the keys (any sort) to obtain `perm`
+ *   csf_tile_sources_*  : sorted[i] = xycs[perm[i]] (perm NULL = identity), padded to
+ *                         csf_tiled_padded_sources(n) elements; tiles: csf_tiled_num_tiles(n)
+ *                         records of csf_tiled_tile_bytes(elem) bytes
+ *   csf_pair_forces_tiled_* : the pair force; `stats` (may be NULL) accumulates the number of
+ *                         pair evaluations actually executed (for the roofline). */
+int64_t csf_tiled_padded_sources(int64_t n_src);
+int64_t csf_tiled_num_tiles(int64_t n_src);
+int csf_tiled_tile_bytes(int elem_bytes);
+size_t csf_pair_tiled_workspace_bytes(int64_t n_src, int64_t n_tgt, int elem_bytes);
+int csf_morton_keys_f32(const void* xycs, int64_t n, double x0, double y0, double cell, int64_t* keys,
+                        csf_stream_t stream);
+int csf_morton_keys_f64(const void* xycs, int64_t n, double x0, double y0, double cell, int64_t* keys,
+                        csf_stream_t stream);
+int csf_tile_sources_f32(const void* xycs, int64_t n, const int64_t* perm, void* sorted, void* tiles,
+                         csf_stream_t stream);
+int csf_tile_sources_f64(const void* xycs, int64_t n, const int64_t* perm, void* sorted, void* tiles,
+                         csf_stream_t stream);
+int csf_pair_forces_tiled_f32(const void* sorted, const void* tiles, int64_t n_src, const void* tgt_xycs,
+                              int64_t n_tgt, const CsfFieldParams* fp, float* frep_xy, int accumulate,
+                              void* workspace, size_t workspace_bytes, unsigned long long* stats,
+                              csf_stream_t stream);
+int csf_pair_forces_tiled_f64(const void* sorted, const void* tiles, int64_t n_src, const void* tgt_xycs,
+                              int64_t n_tgt, const CsfFieldParams* fp, double* frep_xy, int accumulate,
+                              void* workspace, size_t workspace_bytes, unsigned long long* stats,
+                              csf_stream_t stream);
+
 /* ---- road-edge force ------------------------------------------------------------
  * Replaces RoadEdge.calcRepulsiveForce summed over edges (intersection.py:226-242,
  * :36-48, :81-94):  froad[j] (+)= sum_k -F_0 * r^-sigma * (vertex_k - pos_j)/r.

@@ -220,10 +220,11 @@ def test_f32_per_step_error_against_f64_build():
         s64, s32 = g64.states_numpy(), g32.states_numpy()
         # total force = clipped repulsive + destination term (|.| ~ v_d = 5) which may cancel:
         # the error is taken relative to max(|F|, 1).  States: positions / speed relative to
-        # max(|.|, 1), steer angle relative to max(|.|, 0.1 rad), yaw absolute [rad].
+        # max(|.|, 1); yaw and steer angle absolute in radians (a nearly cancelled force has an
+        # ill-conditioned direction, which feeds the steer command: 1e-4 rad is the yardstick).
         ef = _vec_rel(f32, f64, 1.0)
         es = np.maximum(_rel(s32[:, [0, 1, 3]], s64[:, [0, 1, 3]], 1.0).max(axis=1),
-                        _rel(s32[:, 4], s64[:, 4], 0.1))
+                        np.abs(s32[:, 4] - s64[:, 4]))
         es = np.maximum(es, np.abs(np.angle(np.exp(1j * (s32[:, 2] - s64[:, 2])))))
         # agents whose FOV mask flips between the builds (pair exactly on the boundary) are
         # tolerated: at most 2 of 2048 per step

@@ -35,27 +35,34 @@ def _vec_rel(a, b, floor):
     return np.linalg.norm(a - b, axis=-1) / np.maximum(np.linalg.norm(b, axis=-1), floor)
 
 
-@pytest.mark.parametrize("n,spacing", [(2, 2.0), (3, 3.0), (257, 3.0), (1500, 4.0)])
+@pytest.mark.parametrize("n,spacing", [(2, 2.0), (3, 3.0), (257, 3.0), (1500, 4.0), (5000, 4.0)])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-def test_pair_forces(n, spacing, dtype):
+@pytest.mark.parametrize("mode", ["dense", "tiled"])
+def test_pair_forces(n, spacing, dtype, mode):
     s0, q = co.synthetic_crowd(n, seed=7, spacing=spacing)
-    eng, g = make_engine("twod", s0, 5.0, q, dtype=dtype)
+    eng, g = make_engine("twod", s0, 5.0, q, dtype=dtype, pair_mode=mode, count_pairs=True)
+    assert eng.tiled == (mode == "tiled")
     eng._pair_and_road()
     got = eng.frep.cpu().numpy().astype(float)
     p = co.default_params("twod")
     ref, margin = co.pair_forces(s0[:, 0], s0[:, 1], s0[:, 2], co.field_params_array([p])[0],
                                  return_margin=True)
     ok = margin > (1e-9 if dtype == torch.float64 else 1e-5)   # pairs on the FOV boundary may flip
-    assert ok.mean() > 0.99
+    assert ok.mean() > 0.9
     err = _vec_rel(got[ok], ref[ok], 1e-6 if dtype == torch.float64 else 1e-3)
-    report(test="pair_forces", n=n, dtype=str(dtype), max_rel=float(err.max()), med_rel=float(np.median(err)))
+    frac = float(eng.pair_stats.item()) / (n * n) if mode == "tiled" else 1.0
+    report(test="pair_forces", mode=mode, n=n, dtype=str(dtype), max_rel=float(err.max()),
+           med_rel=float(np.median(err)), evaluated_pair_fraction=frac)
+    if mode == "tiled" and n >= 1500:
+        assert frac < 0.75            # the view-cone cull really skips tiles
     assert err.max() < (F64_TOL if dtype == torch.float64 else F32_TOL)
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-def test_pair_forces_p2r(dtype):
-    s0, q = co.synthetic_crowd(300, seed=9, spacing=3.0)
-    eng, g = make_engine("twod", s0, 5.0, q, dtype=dtype, priority_rule="p2r")
+@pytest.mark.parametrize("mode", ["dense", "tiled"])
+def test_pair_forces_p2r(dtype, mode):
+    s0, q = co.synthetic_crowd(900, seed=9, spacing=3.0)
+    eng, g = make_engine("twod", s0, 5.0, q, dtype=dtype, priority_rule="p2r", pair_mode=mode)
     eng._pair_and_road()
     got = eng.frep.cpu().numpy().astype(float)
     p = co.default_params("twod")
@@ -64,6 +71,26 @@ def test_pair_forces_p2r(dtype):
     tol = F64_TOL if dtype == torch.float64 else F32_TOL
     ok = margin > 1e-5
     assert _vec_rel(got[ok], ref[ok], 1e-3).max() < tol
+
+
+def test_tiled_equals_dense_wide_fov_and_ragged_sizes():
+    """hfov >= 180 deg (non-convex visible region), sizes that are not multiples of the tile, and
+    a crowd that moves between re-sorts: the tiled kernel must agree with the dense one."""
+    from cyclistsocialforce_b200 import parameters as P
+    from cyclistsocialforce_b200.engine import AgentGroup, Engine
+    from cyclistsocialforce_b200.synthetic import queues_with_start
+    for n, hfov in ((2049, 1.5 * np.pi), (4100, 2 * np.pi), (3000, 0.5 * np.pi)):
+        s0, q = co.synthetic_crowd(n, seed=3, spacing=3.0)
+        res = {}
+        for mode in ("dense", "tiled"):
+            g = AgentGroup("twod", s0, P.InvPendulumBicycleParameters(hfov=hfov),
+                           destqueues=list(queues_with_start(s0, q)), dtype=torch.float64)
+            eng = Engine([g], dtype=torch.float64, pair_mode=mode, resort_every=4)
+            for _ in range(9):
+                eng.step()
+            res[mode] = (g.states_numpy(), eng.force.cpu().numpy())
+        assert np.abs(res["dense"][0] - res["tiled"][0]).max() < 1e-10
+        assert np.abs(res["dense"][1] - res["tiled"][1]).max() < 1e-10
 
 
 @pytest.mark.parametrize("model", MODELS)
