@@ -33,6 +33,7 @@ class PayloadExchange:
         self.lo, self.hi = self.bounds[rank]
         self.equal = len({hi - lo for lo, hi in self.bounds}) == 1
         self.calls = 0
+        self._slab = self._mine = None
 
     def __call__(self, payload):
         """payload: (n_global, 4) tensor whose rows [lo, hi) were just written by this rank."""
@@ -42,8 +43,16 @@ class PayloadExchange:
         if self.equal:
             dist.all_gather_into_tensor(payload, payload[self.lo:self.hi], group=self.group)
         else:
-            parts = [payload[lo:hi] for lo, hi in self.bounds]
-            dist.all_gather(parts, payload[self.lo:self.hi].clone(), group=self.group)
+            # ragged shards: gather max-sized slabs, then copy the valid rows out
+            m = max(hi - lo for lo, hi in self.bounds)
+            if self._slab is None or self._slab.device != payload.device or self._slab.dtype != payload.dtype:
+                self._slab = payload.new_zeros((self.world, m, payload.shape[1]))
+                self._mine = payload.new_zeros((m, payload.shape[1]))
+            self._mine[:self.hi - self.lo] = payload[self.lo:self.hi]
+            dist.all_gather_into_tensor(self._slab.view(-1, payload.shape[1]), self._mine, group=self.group)
+            for r, (lo, hi) in enumerate(self.bounds):
+                if r != self.rank:
+                    payload[lo:hi] = self._slab[r, :hi - lo]
 
 
 def gather_rows_host(local_rows: np.ndarray, n_global: int, rank: int, world: int, group=None):

@@ -1,0 +1,60 @@
+"""Host-side logic of the N>1 path with world_size-2 gloo on CPU: agent-range sharding and the
+per-step payload all-gather (the one exchange step of the sharded crowd)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cyclistsocialforce_b200.distributed import PayloadExchange, gather_rows_host, shard_bounds
+
+
+def test_shard_bounds():
+    assert shard_bounds(10, 1) == [(0, 10)]
+    assert shard_bounds(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    assert shard_bounds(65536, 8)[-1] == (57344, 65536)
+    for n, w in ((7, 2), (1000, 8), (3, 4)):
+        b = shard_bounds(n, w)
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        sizes = [hi - lo for lo, hi in b]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ex = PayloadExchange(n, rank, world)
+        ref = torch.arange(n * 4, dtype=torch.int32).reshape(n, 4)
+        payload = torch.full((n, 4), -1, dtype=torch.int32)
+        payload[ex.lo:ex.hi] = ref[ex.lo:ex.hi]           # "this rank's agent kernel wrote its rows"
+        ex(payload)
+        ok = bool(torch.equal(payload, ref))
+        # a second step with changed local rows
+        payload[ex.lo:ex.hi] += 7
+        ex(payload)
+        ok = ok and bool(torch.equal(payload, ref + 7))
+        rows = gather_rows_host(np.full((ex.hi - ex.lo, 2), float(rank)), n, rank, world)
+        ok = ok and rows.shape == (n, 2) and rows[0, 0] == 0.0 and rows[-1, 0] == float(world - 1)
+        ret[rank] = (ok, ex.calls)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [64, 65])          # equal shards (all_gather_into_tensor) and ragged
+def test_payload_exchange_gloo_world2(n):
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), n, ret), nprocs=world, join=True)
+    assert all(ret[r][0] for r in range(world)), dict(ret)
+    assert all(ret[r][1] == 2 for r in range(world))
