@@ -138,15 +138,26 @@ def main():
     # ---- the crowd, sharded by agent range -------------------------------------------------
     s0, q = synthetic_crowd(N_AGENTS, seed=SEED)
     queues = queues_with_start(s0, q)
-    lo, hi = shard_bounds(N_AGENTS, world)[rank]
+    # CSF_BENCH_EMULATE_WORLD=8: time ONE rank's shard of an 8-way split on a single GPU (tuning aid;
+    # the payload of the other shards stays frozen, no exchange) -- never used for reported numbers
+    emu = int(os.environ.get("CSF_BENCH_EMULATE_WORLD", 0))
+    lo, hi = shard_bounds(N_AGENTS, emu)[0] if emu else shard_bounds(N_AGENTS, world)[rank]
     extent = 2.0 * float(max(np.abs(s0[:, :2]).max(), np.abs(q[..., :2]).max())) + 1000.0
     group = AgentGroup("twod", s0[lo:hi], P.InvPendulumBicycleParameters(), destqueues=list(queues[lo:hi]),
                        dtype=torch.float32, device=dev)
     exch = PayloadExchange(N_AGENTS, rank, world)
+    if emu:
+        full = AgentGroup("twod", s0, P.InvPendulumBicycleParameters(), destqueues=list(queues),
+                          dtype=torch.float32, device=dev)
+        e_full = Engine([full], dtype=torch.float32, device=dev, extent=extent, pair_mode="dense")
+        frozen_payload = e_full.payload.clone()
+        del e_full, full
     pair_mode = os.environ.get("CSF_PAIR_MODE", "tiled")
     eng = Engine([group], dtype=torch.float32, device=dev, extent=extent, n_global=N_AGENTS, global_offset=lo,
                  exchange=exch, pair_mode=pair_mode, count_pairs=True)
     exch(eng.payload)
+    if emu:
+        eng.payload.copy_(frozen_payload)
     n_local = hi - lo
 
     def sync():
@@ -271,7 +282,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_agents": N_AGENTS, "parallelism": f"agent-range x{world}", "pair_kernel": "tiled+culled" if eng.tiled else "dense",
+            "config": {"workload": WORKLOAD, "n_agents": N_AGENTS, "parallelism": f"agent-range x{world}" + (f" (EMULATED 1/{emu} shard, not a result)" if emu else ""), "pair_kernel": "tiled+culled" if eng.tiled else "dense",
                        "l2": "flushed between timed steps (256 MiB write)", "q_scale_m": eng.q_scale,
                        "pair_interactions_per_s": float(N_AGENTS) * (N_AGENTS - 1) * args.steps / (total_ms * 1e-3)},
             "clocks": clocks,

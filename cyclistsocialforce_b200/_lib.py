@@ -76,6 +76,10 @@ SIGNATURES = {
     "csf_pair_forces_f64": (C.c_int, [_vp, _i64, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp]),
     "csf_pair_forces_grouped_f32": (C.c_int, [_vp, _i64, _i32, _FP, _vp, _vp]),
     "csf_pair_forces_grouped_f64": (C.c_int, [_vp, _i64, _i32, _FP, _vp, _vp]),
+    "csf_pair_forces_bicycle_f32": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _FP, _vp, C.c_int, _vp]),
+    "csf_pair_forces_bicycle_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _FP, _vp, C.c_int, _vp]),
+    "csf_bicycle_eccentricity_f32": (C.c_int, [_vp, _i64, _dbl, _vp, _vp]),
+    "csf_bicycle_eccentricity_f64": (C.c_int, [_vp, _i64, _dbl, _vp, _vp]),
     "csf_tiled_padded_sources": (_i64, [_i64]),
     "csf_tiled_num_tiles": (_i64, [_i64]),
     "csf_tiled_tile_bytes": (C.c_int, [C.c_int]),

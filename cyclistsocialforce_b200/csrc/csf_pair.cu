@@ -171,6 +171,95 @@ __global__ void pair_grouped_kernel(const Xycs<T>* __restrict__ xycs, int64_t n,
     frep[j * 2 + 1] = f0 * ay;
 }
 
+// ---- Bicycle v0.1 elliptic field (reference vehicle.py:1054-1147) --------------------------------
+// e_i = min((v_i / v_max)^0.1, 0.7) per source (updateExcentricity :1054-1064), passed as src_e.
+//   b = rho (1 - e cos phi0) / (sqrt(1-e^2) p_decay);  P = p_0 exp(-b) / p_decay
+//   F_rho = P (1 - e cos phi0)/sqrt(1-e^2);  F_phi = P e sin phi0 / sqrt(1-e^2);  rotated by phi.
+// Classic shared-memory N-body (thread per target); this legacy field is not on the headline path.
+template <typename T> struct BikeConst {
+    T ncosH, tiny;
+    T kexp;   // log2(e) * q_scale / p_decay   (payload units -> exponent)
+    T pscale; // p_0 / p_decay
+};
+template <typename T, bool P2R>
+__global__ void __launch_bounds__(128) pair_bicycle_kernel(const Xycs<T>* __restrict__ src, const T* __restrict__ src_e,
+                                                           int64_t n_src, const Xycs<T>* __restrict__ tgt,
+                                                           int64_t n_tgt, BikeConst<T> k, T* __restrict__ frep,
+                                                           int accumulate) {
+    __shared__ Xycs<T> ssrc[128];
+    __shared__ T se[128];
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const Xycs<T> et = tgt[min(j, n_tgt - 1)];
+    const Tgt<T> tg = *reinterpret_cast<const Tgt<T>*>(&et);
+    T ax = (T)0, ay = (T)0;
+    for (int64_t s0 = 0; s0 < n_src; s0 += 128) {
+        const int cnt = (int)min((int64_t)128, n_src - s0);
+        __syncthreads();
+        if (threadIdx.x < cnt) {
+            ssrc[threadIdx.x] = src[s0 + threadIdx.x];
+            se[threadIdx.x] = src_e[s0 + threadIdx.x];
+        }
+        __syncthreads();
+        for (int i = 0; i < cnt; ++i) {
+            const Xycs<T> sr = ssrc[i];
+            const T e = se[i];
+            T dx, dy;
+            delta(sr, tg, dx, dy);
+            const T r2 = fma(dy, dy, fma(dx, dx, k.tiny));
+            const T rinv = M<T>::rsqrt(r2);
+            const T ux = dx * rinv, uy = dy * rinv;
+            const T c = fma(uy, sr.s, ux * sr.c);
+            const T s = fma(-ux, sr.s, uy * sr.c);
+            const T t = fma(uy, tg.s, ux * tg.c);
+            bool vis = t <= k.ncosH;
+            if (P2R) vis = vis && (fma(tg.s, ux, -(tg.c * uy)) <= (T)0);
+            const T ke = M<T>::rsqrt(fma(-e, e, (T)1));
+            const T g = fma(-e, c, (T)1) * ke;          // (1 - e cos phi0)/sqrt(1-e^2)
+            const T rho = r2 * rinv;
+            const T P = k.pscale * M<T>::ex2(-(rho * g * k.kexp));
+            const T fr = vis ? P * g : (T)0;
+            const T fp = vis ? P * (e * s * ke) : (T)0;
+            ax = fma(fr, ux, ax);
+            ax = fma(-fp, uy, ax);
+            ay = fma(fr, uy, ay);
+            ay = fma(fp, ux, ay);
+        }
+    }
+    if (j < n_tgt) {
+        frep[j * 2] = accumulate ? frep[j * 2] + ax : ax;
+        frep[j * 2 + 1] = accumulate ? frep[j * 2 + 1] + ay : ay;
+    }
+}
+template <typename T>
+__global__ void eccentricity_kernel(const T* __restrict__ v, int64_t n, T v_max, T* __restrict__ e) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) e[i] = (T)fmin(pow((double)v[i] / (double)v_max, 0.1), 0.7);   // vehicle.py:1062-1064
+}
+template <typename T>
+int pair_bicycle(const void* src, const void* src_e, int64_t n_src, const void* tgt, int64_t n_tgt,
+                 const CsfFieldParams* fp, T* frep, int accumulate, cudaStream_t st) {
+    if (n_tgt <= 0) return 0;
+    if (n_src <= 0) {
+        if (!accumulate) cudaMemsetAsync(frep, 0, sizeof(T) * 2 * n_tgt, st);
+        return 0;
+    }
+    const bool f32 = sizeof(T) == 4;
+    BikeConst<T> k;
+    k.ncosH = (fp->hfov * 0.5 >= CSF_PI) ? (T)2 : (T)(-cos(fp->hfov * 0.5));
+    k.tiny = (T)(f32 ? 1e-6 : 1e-200);
+    k.kexp = (T)(1.4426950408889634 * (f32 ? fp->q_scale : 1.0) / fp->p_decay);
+    k.pscale = (T)(fp->p_0 / fp->p_decay);
+    const unsigned grid = (unsigned)((n_tgt + 127) / 128);
+    if (fp->p2r)
+        pair_bicycle_kernel<T, true><<<grid, 128, 0, st>>>((const Xycs<T>*)src, (const T*)src_e, n_src,
+                                                           (const Xycs<T>*)tgt, n_tgt, k, frep, accumulate);
+    else
+        pair_bicycle_kernel<T, false><<<grid, 128, 0, st>>>((const Xycs<T>*)src, (const T*)src_e, n_src,
+                                                            (const Xycs<T>*)tgt, n_tgt, k, frep, accumulate);
+    CSF_CHECK_LAUNCH("pair_bicycle_kernel");
+    return 0;
+}
+
 // ---- road-edge force -----------------------------------------------------------------
 // intersection.py:226-242: F = sum_k -F_0 r^-sigma (v_k - p)/r ; one thread per agent,
 // vertices staged through shared memory in tiles.
@@ -281,8 +370,8 @@ int pair_forces(const void* src_xycs, int64_t n_src, const void* tgt_xycs, int64
         return 0;
     }
     if (fp->field_kind != 0) {
-        csf_set_error("csf_pair_forces: field_kind != 0 not supported yet", cudaErrorNotSupported);
-        return -(int)cudaErrorNotSupported;
+        csf_set_error("csf_pair_forces: field_kind 1 goes through csf_pair_forces_bicycle_*", cudaErrorInvalidValue);
+        return -(int)cudaErrorInvalidValue;
     }
     const PairPlan pl = make_plan<C::TPT, C::TILE>(n_src, n_tgt, pair_ctas<T>());
     const size_t need = (size_t)pl.n_chunks * n_tgt * 2 * sizeof(T);
@@ -374,6 +463,26 @@ int csf_pair_forces_grouped_f32(const void* x, int64_t n, int32_t g, const CsfFi
 int csf_pair_forces_grouped_f64(const void* x, int64_t n, int32_t g, const CsfFieldParams* fp, double* frep,
                                 csf_stream_t st) {
     return pair_grouped<double>(x, n, g, fp, frep, (cudaStream_t)st);
+}
+int csf_pair_forces_bicycle_f32(const void* s, const void* e, int64_t ns, const void* t, int64_t nt,
+                                const CsfFieldParams* fp, float* frep, int acc, csf_stream_t st) {
+    return pair_bicycle<float>(s, e, ns, t, nt, fp, frep, acc, (cudaStream_t)st);
+}
+int csf_pair_forces_bicycle_f64(const void* s, const void* e, int64_t ns, const void* t, int64_t nt,
+                                const CsfFieldParams* fp, double* frep, int acc, csf_stream_t st) {
+    return pair_bicycle<double>(s, e, ns, t, nt, fp, frep, acc, (cudaStream_t)st);
+}
+int csf_bicycle_eccentricity_f32(const float* v, int64_t n, double v_max, float* e, csf_stream_t st) {
+    if (n <= 0) return 0;
+    eccentricity_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)st>>>(v, n, (float)v_max, e);
+    CSF_CHECK_LAUNCH("eccentricity_kernel");
+    return 0;
+}
+int csf_bicycle_eccentricity_f64(const double* v, int64_t n, double v_max, double* e, csf_stream_t st) {
+    if (n <= 0) return 0;
+    eccentricity_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)st>>>(v, n, v_max, e);
+    CSF_CHECK_LAUNCH("eccentricity_kernel");
+    return 0;
 }
 int csf_road_forces_f32(const double* x, const double* y, int64_t n, const double* v, int64_t m, double F_0,
                         double sigma, float* out, int acc, csf_stream_t st) {

@@ -343,17 +343,24 @@ class Engine:
             self.classes.append((0, self.n_total, g0.params.field_key(),
                                  g0.params.to_field_params(self.q_scale, self.p2r)))
         for g in (self.groups + self.obstacles if n_global is None else []):
-            key = g.params.field_key()
-            if self.classes and self.classes[-1][2] == key:
+            kind = 1 if g.model == "bicycle" else 0      # v0.1 elliptic field (vehicle.py:1107-1147)
+            key = g.params.field_key(kind)
+            if self.classes and self.classes[-1][2] == key and kind == 0:
                 s, c, k, fp = self.classes[-1]
                 self.classes[-1] = (s, c + g.n, k, fp)
             else:
-                self.classes.append((g.payload_offset, g.n, key, g.params.to_field_params(self.q_scale, self.p2r)))
+                self.classes.append((g.payload_offset, g.n, key,
+                                     g.params.to_field_params(self.q_scale, self.p2r, kind)))
+        # per-source eccentricity of Bicycle-field sources (refreshed every step from their speed)
+        self._ecc = {}
+        for g in self.groups:
+            if g.model == "bicycle":
+                self._ecc[g.payload_offset] = (g, torch.zeros(g.n, dtype=dtype, device=self.device))
         wsb = 0
         if self.n_total > 1 and scenario_size is None:
             for s, c, _, _ in self.classes:
                 wsb = max(wsb, int(self.lib.csf_pair_workspace_bytes(c, self.n_agents, 4 if self.f32 else 8)))
-        self.tiled = (scenario_size is None and self.n_total > 1 and
+        self.tiled = (scenario_size is None and self.n_total > 1 and not self._ecc and
                       (pair_mode == "tiled" or (pair_mode == "auto" and self.n_total >= 2048)))
         self.pair_stats = torch.zeros(1, dtype=torch.int64, device=self.device) if count_pairs else None
         self._tiles = []
@@ -421,6 +428,16 @@ class Engine:
                 for ci, (s, c, _, fp) in enumerate(self.classes):
                     src = C.c_void_p(self.payload.data_ptr() + s * self.elem_bytes)
                     tgt = C.c_void_p(self.payload.data_ptr() + self.global_offset * self.elem_bytes)
+                    if fp.field_kind == 1:
+                        g, ecc = self._ecc[s]
+                        _lib.check(self._fn("csf_bicycle_eccentricity")(_ptr(g.v), g.n, fp.v_max, _ptr(ecc), st),
+                                   "csf_bicycle_eccentricity")
+                        _lib.check(self._fn("csf_pair_forces_bicycle")(src, _ptr(ecc), c, tgt, self.n_agents,
+                                                                       C.byref(fp), _ptr(self.frep),
+                                                                       1 if ci > 0 else 0, st),
+                                   "csf_pair_forces_bicycle")
+                        self.gpu_launches += 2
+                        continue
                     if self.tiled:
                         tl = self._tiles[ci]
                         if resort or tl["perm"] is None:

@@ -101,21 +101,23 @@ class VehicleParameters:
             raise ValueError("e_0 must be in [0,1[.")
 
     # -- flatten ---------------------------------------------------------------------------
-    def to_field_params(self, q_scale: float, p2r: bool) -> "_lib.CsfFieldParams":
+    def to_field_params(self, q_scale: float, p2r: bool, field_kind: int = 0) -> "_lib.CsfFieldParams":
         fp = _lib.CsfFieldParams()
         fp.f_0, fp.e_0, fp.e_1 = self.f_0, self.e_0, self.e_1
         fp.sigma_0, fp.sigma_1, fp.sigma_2, fp.sigma_3 = self.sigma_0, self.sigma_1, self.sigma_2, self.sigma_3
         fp.hfov = self.hfov
         fp.q_scale = q_scale
         fp.p2r = 1 if p2r else 0
-        fp.field_kind = 0
+        fp.field_kind = int(field_kind)
         fp.p_0 = getattr(self, "p_0", 0.0)
         fp.p_decay = getattr(self, "p_decay", 1.0)
         fp.v_max = getattr(self, "v_max_riding", [0.0, 1.0])[1]
         return fp
 
-    def field_key(self):
-        return (self.f_0, self.e_0, self.e_1, self.sigma_0, self.sigma_1, self.sigma_2, self.sigma_3, self.hfov)
+    def field_key(self, field_kind: int = 0):
+        if field_kind == 1:
+            return (1, self.p_0, self.p_decay, self.v_max_riding[1], self.hfov)
+        return (0, self.f_0, self.e_0, self.e_1, self.sigma_0, self.sigma_1, self.sigma_2, self.sigma_3, self.hfov)
 
     def to_agent_params(self, q_scale: float, q_cap: int, hist_cap: int) -> "_lib.CsfAgentParams":
         p = _lib.CsfAgentParams()

@@ -156,6 +156,19 @@ int csf_pair_forces_grouped_f32(const void* xycs, int64_t n, int32_t group, cons
 int csf_pair_forces_grouped_f64(const void* xycs, int64_t n, int32_t group, const CsfFieldParams* fp,
                                 double* frep_xy, csf_stream_t stream);
 
+/* ---- K1 for sources with the v0.1 `Bicycle` elliptic field (field_kind 1) ---------------------
+ * Replaces Bicycle.calcRepulsiveForce / calcPotential / updateExcentricity (vehicle.py:1054-1147)
+ * inside the same masked sum.  src_e[i] = eccentricity of source i (csf_bicycle_eccentricity_*:
+ * e = min((v / v_max_riding[1])^0.1, 0.7)). */
+int csf_pair_forces_bicycle_f32(const void* src_xycs, const void* src_e, int64_t n_src, const void* tgt_xycs,
+                                int64_t n_tgt, const CsfFieldParams* fp, float* frep_xy, int accumulate,
+                                csf_stream_t stream);
+int csf_pair_forces_bicycle_f64(const void* src_xycs, const void* src_e, int64_t n_src, const void* tgt_xycs,
+                                int64_t n_tgt, const CsfFieldParams* fp, double* frep_xy, int accumulate,
+                                csf_stream_t stream);
+int csf_bicycle_eccentricity_f32(const float* v, int64_t n, double v_max, float* e, csf_stream_t stream);
+int csf_bicycle_eccentricity_f64(const double* v, int64_t n, double v_max, double* e, csf_stream_t stream);
+
 /* ---- K1, tiled variant with exact field-of-view culling ----------------------------------
  * Same result as csf_pair_forces_* up to the order of summation (the f32 build additionally
  * drops tiles whose every contribution is below 2^-40 f_0).  Sources are passed as a spatially

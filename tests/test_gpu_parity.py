@@ -9,9 +9,8 @@ from gpu_helpers import make_engine
 
 pytestmark = pytest.mark.gpu
 
-# the v0.1 ``Bicycle`` force field (vehicle.py:1107-1147) is a "next" row
-BICYCLE_XFAIL = pytest.param("bicycle", marks=pytest.mark.skip(reason="Bicycle v0.1 field kernel: next row"))
-MODELS = ["twod", "planarpoint", "invpendulum", "balancingrider", BICYCLE_XFAIL]
+BICYCLE_XFAIL = "bicycle"      # v0.1 ``Bicycle`` elliptic field (vehicle.py:1107-1147)
+MODELS = ["twod", "planarpoint", "invpendulum", "balancingrider", "bicycle"]
 
 
 def report(**kw):
@@ -199,3 +198,31 @@ def test_road_forces(golden):
                       out.data_ptr(), 0, None), "road")
         torch.cuda.synchronize()
         assert _vec_rel(out.cpu().numpy().astype(float), gd["road_F"], 1e-6).max() < tol
+
+
+@pytest.mark.parametrize("model", ["invpendulum", "twod"])
+def test_batched_independent_scenarios(model):
+    """BASELINE config 4: many independent 8-agent scenarios in one batch (block-diagonal pair
+    interaction, no communication): each scenario must equal the oracle run on its own."""
+    n_scen, per = 48, 8
+    S0, Q = [], []
+    for k in range(n_scen):
+        s0, q = co.synthetic_crowd(per, seed=100 + k, spacing=4.0, n_states=8)
+        S0.append(s0)
+        Q.append(q)
+    s0 = np.concatenate(S0)
+    q = np.concatenate(Q)
+    eng, g = make_engine(model, s0, 5.0, q, dtype=torch.float64, scenario_size=per)
+    steps = 20
+    for _ in range(steps):
+        eng.step()
+    eng.check_status()
+    got = g.states_numpy()
+    worst = 0.0
+    for k in (0, 7, 23, 47):
+        W = oracle_world(model, S0[k], np.full(per, 5.0), Q[k])
+        for _ in range(steps):
+            W.step()
+        worst = max(worst, np.abs(got[k * per:(k + 1) * per] - W.groups[0].s).max())
+    report(test="batched_scenarios", model=model, scenarios=n_scen, per=per, steps=steps, max_abs=float(worst))
+    assert worst < 1e-9
