@@ -21,6 +21,7 @@ class CsfFieldParams(C.Structure):
         ("hfov", C.c_double), ("q_scale", C.c_double),
         ("p2r", C.c_int32), ("field_kind", C.c_int32),
         ("p_0", C.c_double), ("p_decay", C.c_double), ("v_max", C.c_double),
+        ("cutoff_log2", C.c_double),
     ]
 
 
@@ -88,8 +89,9 @@ SIGNATURES = {
     "csf_morton_keys_f64": (C.c_int, [_vp, _i64, _dbl, _dbl, _dbl, _vp, _vp]),
     "csf_tile_sources_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "csf_tile_sources_f64": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
-    "csf_pair_forces_tiled_f32": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp]),
-    "csf_pair_forces_tiled_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp]),
+    "csf_pair_forces_tiled_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp]),
+    "csf_pair_forces_tiled_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp]),
+    "csf_field_cutoff_distance": (_dbl, [_FP]),
     "csf_road_forces_f32": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _dbl, _dbl, _vp, C.c_int, _vp]),
     "csf_road_forces_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _dbl, _dbl, _vp, C.c_int, _vp]),
     "csf_agent_forces_f32": (C.c_int, [C.c_int, _AS, _AP, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -84,6 +84,101 @@ __device__ __forceinline__ void pair_eval(const Xycs<T>& sr, const Tgt<T>& tg, c
     ay = fma(b, ux, ay);
 }
 
+// ---- packed FP32x2 evaluation (Blackwell FFMA2) ------------------------------------------------------
+// Two sources against one target per lane, every FP32 add/mul/fma as one fma.rn.f32x2 (SASS FFMA2:
+// same FP32-pipe throughput as two FFMA, half the issue slots -- the kernel is issue bound).  The
+// operation sequence per half is exactly pair_eval<float>'s.  neg/abs of both halves and scalar
+// broadcasts are written as plain moves; ptxas folds them into FFMA2 operand modifiers.
+struct F2 { unsigned long long v; };
+__device__ __forceinline__ F2 pk(float lo, float hi) { F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void up(F2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ F2 splat(float s) { return pk(s, s); }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) { F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) { F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ F2 add2(F2 a, F2 b) { F2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ F2 neg2(F2 a) { float l, h; up(a, l, h); return pk(-l, -h); }
+__device__ __forceinline__ F2 abs2(F2 a) { float l, h; up(a, l, h); return pk(fabsf(l), fabsf(h)); }
+
+// sources (x0,y0,c0,s0) and (x1,y1,c1,s1); accumulators hold one partial sum per half
+template <bool P2R>
+__device__ __forceinline__ void pair_eval2(int32_t x0, int32_t x1, int32_t y0, int32_t y1, float c0, float c1, float s0,
+                                           float s1, const Tgt<float>& tg, const PairConst<float>& k, F2& ax, F2& ay) {
+    const F2 DX = pk((float)(tg.xq - x0), (float)(tg.xq - x1));
+    const F2 DY = pk((float)(tg.yq - y0), (float)(tg.yq - y1));
+    const F2 R2 = fma2(DY, DY, fma2(DX, DX, splat(k.tiny)));
+    float r2a, r2b;
+    up(R2, r2a, r2b);
+    const F2 RINV = pk(M<float>::rsqrt(r2a), M<float>::rsqrt(r2b));
+    const F2 UX = mul2(DX, RINV), UY = mul2(DY, RINV);
+    const F2 SC = pk(c0, c1), SS = pk(s0, s1), TC = splat(tg.c), TS = splat(tg.s);
+    const F2 C = fma2(UY, SS, mul2(UX, SC));
+    const F2 S = fma2(neg2(UX), SS, mul2(UY, SC));
+    const F2 TT = fma2(UY, TS, mul2(UX, TC));
+    float ta, tb;
+    up(TT, ta, tb);
+    bool visa = ta <= k.ncosH, visb = tb <= k.ncosH;
+    if (P2R) {
+        const F2 L = fma2(TS, UX, neg2(mul2(TC, UY)));
+        float la, lb;
+        up(L, la, lb);
+        visa = visa && (la <= 0.f);
+        visb = visb && (lb <= 0.f);
+    }
+    const F2 SR = fma2(SS, TC, neg2(mul2(SC, TS)));
+    const F2 S2 = mul2(SR, SR);
+    const F2 A = fma2(splat(k.sg1), S2, splat(k.sg0));
+    const F2 B = fma2(splat(k.sg3), S2, splat(k.sg2));
+    const F2 E = fma2(splat(-k.e1), S2, splat(k.e0));
+    const F2 AS = abs2(S);
+    const F2 HM = fma2(splat(0.5f), abs2(C), splat(0.5f));
+    float hma, hmb;
+    up(HM, hma, hmb);
+    const F2 RM = pk(M<float>::rsqrt(hma), M<float>::rsqrt(hmb));
+    const F2 HBIG = mul2(HM, RM);
+    const F2 HSMALL = mul2(AS, mul2(splat(0.5f), RM));
+    float ca, cb, sa, sb, hba, hbb, hsa, hsb;
+    up(C, ca, cb);
+    up(S, sa, sb);
+    up(HBIG, hba, hbb);
+    up(HSMALL, hsa, hsb);
+    const bool fwa = ca >= 0.f, fwb = cb >= 0.f;
+    const F2 H1 = pk(fwa ? hsa : hba, fwb ? hsb : hbb);
+    const F2 H2 = pk((fwa && sa != 0.f) ? hba : hsa, (fwb && sb != 0.f) ? hbb : hsb);
+    const F2 SG = fma2(neg2(B), H1, A);
+    const F2 EC = mul2(E, C);
+    const F2 ES = mul2(E, AS);
+    const F2 Q2 = fma2(ES, ES, fma2(fma2(splat(k.qc), S2, splat(k.qb)), S2, splat(k.qa)));
+    const F2 W = mul2(ES, EC);
+    const F2 MV = fma2(W, SG, mul2(splat(0.5f), mul2(Q2, mul2(B, H2))));
+    const F2 GRHO = mul2(Q2, SG);
+    float mva, mvb;
+    up(MV, mva, mvb);
+    const F2 GPHI = pk(mulsign(mva, sa), mulsign(mvb, sb));
+    const F2 RYA = mul2(GRHO, SG);
+    float rya, ryb;
+    up(RYA, rya, ryb);
+    const F2 RY = pk(M<float>::rsqrt(rya), M<float>::rsqrt(ryb));
+    const F2 QS = mul2(Q2, RY);
+    const F2 RHO = mul2(R2, RINV);
+    const F2 PE = mul2(RHO, QS);
+    float pea, peb;
+    up(PE, pea, peb);
+    const F2 P = pk(M<float>::ex2(-pea), M<float>::ex2(-peb));
+    const F2 RNA = fma2(GPHI, GPHI, mul2(GRHO, GRHO));
+    float rna, rnb;
+    up(RNA, rna, rnb);
+    const F2 RN = pk(M<float>::rsqrt(rna), M<float>::rsqrt(rnb));
+    const F2 SCL = mul2(P, RN);
+    float sca, scb;
+    up(SCL, sca, scb);
+    const F2 SCV = pk(visa ? sca : 0.f, visb ? scb : 0.f);
+    const F2 FA = mul2(SCV, GRHO), FB = mul2(SCV, GPHI);
+    ax = fma2(FA, UX, ax);
+    ax = fma2(neg2(FB), UY, ax);
+    ay = fma2(FA, UY, ay);
+    ay = fma2(FB, UX, ay);
+}
+
 // ---- mbarrier / TMA bulk-copy primitives (sm_90+/sm_100a) --------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -1,115 +1,170 @@
-// K1 (tiled): all-pairs repulsive force with exact field-of-view culling.
+// K1 (tiled): all-pairs repulsive force with hierarchical culling.
 //
-// ~2/3 of the ordered pairs of a crowd are masked by the target's field of view
-// (reference intersection.py:733-736; hfov = 2 pi / 3).  The mask depends on the target's
-// heading, so a thread-per-target kernel cannot skip them (every lane sees a different cone).
-// This kernel turns the mapping around:
-//   * sources are kept in a spatially sorted copy (Morton order, refreshed by the host every
-//     few steps) cut into tiles of 64 with a bounding circle each (csf_tile_sources_*);
-//   * a warp works on ONE target at a time: the lanes first test one tile each against the
-//     target's view cone expanded by the tile radius (a conservative, warp-uniform decision
-//     after a ballot), then the lanes evaluate the surviving tiles two sources per lane with
-//     the same pair_eval as the dense kernel (which still applies the exact per-pair mask);
-//   * lane partial sums are combined with warp shuffles once per (target, source chunk).
-// Culled pairs are exactly pairs whose mask is 0, so the result equals the dense kernel's up
-// to the order of summation.  In the f32 build tiles whose nearest point is so far that every
-// contribution is below 2^-40 f_0 are skipped too (bounded, documented truncation; never in f64).
-//
-// Source chunks (16 tiles + their records) are streamed into a shared-memory ring by a
-// producer warp with TMA bulk copies, exactly like the dense kernel.
+// The masked sum  Frep_j = sum_i mask(i,j) F(i -> j)  (reference intersection.py:788-843,
+// vehicle.py:1560-1648) has two sources of exact or negligible zeros:
+//   * ~2/3 of the ordered pairs are masked by the *target's* field of view
+//     (intersection.py:733-736; hfov = 2 pi / 3);
+//   * |F(i -> j)| = f_0 exp(-rho q / sigma) (vehicle.py:1613-1648): beyond rho = d_cut every
+//     contribution is below 2^-cutoff_log2 f_0 (f32 build only; d_cut ~ 160 m with the default
+//     parameters; the f64 verification build never truncates).
+// Both are turned into skipped work at three levels:
+//   1. sources live in a spatially sorted copy (Morton order, re-sorted by the host every few
+//      steps) cut into tiles of 64 and chunks of 16 tiles, each with a bounding circle; targets are
+//      visited in Morton order too, in blocks of 8 warps x tpw targets with a bounding circle;
+//   2. the producer warp of a CTA streams only the chunks that can be within d_cut of the
+//      target block (lane-parallel circle/circle test) into a shared-memory ring with TMA bulk
+//      copies + mbarriers;
+//   3. a consumer warp works on ONE target at a time: its lanes test one tile each against the
+//      target's view cone expanded by the tile radius and the cut-off distance (warp-uniform
+//      decision after a ballot), then evaluate the surviving tiles two sources per lane with the
+//      same pair_eval as the dense kernel (which still applies the exact per-pair mask).
+// Culled pairs are pairs whose contribution is exactly 0 (mask) or < 2^-cutoff_log2 f_0 (f32), so
+// the result equals the dense kernel's up to the order of summation and that bound.
+// Work items (target block x chunk group) are handed out dynamically (atomic counter); partial
+// sums per chunk group are reduced in fixed order (deterministic, no float atomics).
 #include "csf_common.cuh"
 #include "csf_pair_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
 #ifndef CSF_TILED_WARPS
 #define CSF_TILED_WARPS 8        // consumer warps per CTA
 #endif
-#ifndef CSF_TILED_TPW
-#define CSF_TILED_TPW 16         // targets per warp per work item
-#endif
-#ifndef CSF_TILED_CHUNK_TILES
-#define CSF_TILED_CHUNK_TILES 16 // tiles per shared-memory stage (<= 32: one tile per lane in the cull test)
-#endif
 #ifndef CSF_TILED_MINB
-#define CSF_TILED_MINB 2
-#endif
-#ifndef CSF_TILED_ILP4
-#define CSF_TILED_ILP4 1         // evaluate two surviving tiles per loop iteration
+#define CSF_TILED_MINB 3
 #endif
 constexpr int kTW = CSF_TILED_WARPS;
 constexpr int kTThreads = (kTW + 1) * 32;
-constexpr int kTPW = CSF_TILED_TPW;
-constexpr int kTB = kTW * kTPW;          // targets per work item
+constexpr int kMaxTPW = 16;              // targets per warp per item (runtime tpw <= kMaxTPW)
 constexpr int kTileS = 64;               // sources per tile (2 per lane)
-constexpr int kCT = CSF_TILED_CHUNK_TILES;
+constexpr int kCT = 16;                  // tiles per chunk = one shared-memory stage
 constexpr int kCS = kCT * kTileS;        // sources per chunk
-constexpr int kTStages = 3;
 constexpr int kTMaxGroups = 64;
-static_assert(kTPW * 2 <= 32, "per-warp accumulator update uses one lane per scalar");
-static_assert(kCT <= 32, "one tile per lane in the cull test");
+template <typename T> struct Stages { static constexpr int n = sizeof(T) == 4 ? 4 : 3; };
 
 template <typename T> struct Tile;
 template <> struct __align__(16) Tile<float> { int32_t cx, cy; float R; int32_t cnt; };
 template <> struct __align__(16) Tile<double> { double cx, cy, R; int64_t cnt; };
 
+// Sorted-copy layout, per tile of 64 (lane l owns sources l and l + 32 of the tile):
+//   SrcA[32] = {x_l, x_{l+32}, y_l, y_{l+32}}   then   SrcB[32] = {c_l, c_{l+32}, s_l, s_{l+32}}
+// so a lane fetches both of its sources with two 16-byte (f64: 32-byte) conflict-free loads.
+template <typename T> struct SrcA;
+template <> struct __align__(16) SrcA<float> { int32_t x0, x1, y0, y1; };
+template <> struct __align__(16) SrcA<double> { double x0, x1, y0, y1; };
+template <typename T> struct __align__(16) SrcB { T c0, c1, s0, s1; };
+template <typename T> struct TileBytes { static constexpr size_t v = (size_t)kTileS * sizeof(Xycs<T>); };
+
 template <typename T> struct CullConst {
     T ca, sa;    // cos / sin of hfov/2
-    T dmax;      // distance (payload units) beyond which a whole tile contributes < 2^-40 f_0 (inf: never)
+    T dmax;      // cut-off distance d_cut in payload units (huge: never)
 };
 
-// ---- tile builder: one warp per tile -----------------------------------------------------------
+__device__ __forceinline__ void split(const Xycs<float>& a, const Xycs<float>& b, SrcA<float>& A, SrcB<float>& B) {
+    A.x0 = a.xq; A.x1 = b.xq; A.y0 = a.yq; A.y1 = b.yq;
+    B.c0 = a.c; B.c1 = b.c; B.s0 = a.s; B.s1 = b.s;
+}
+__device__ __forceinline__ void split(const Xycs<double>& a, const Xycs<double>& b, SrcA<double>& A, SrcB<double>& B) {
+    A.x0 = a.x; A.x1 = b.x; A.y0 = a.y; A.y1 = b.y;
+    B.c0 = a.c; B.c1 = b.c; B.s0 = a.s; B.s1 = b.s;
+}
+__device__ __forceinline__ Xycs<float> src0(const SrcA<float>& A, const SrcB<float>& B) { return {A.x0, A.y0, B.c0, B.s0}; }
+__device__ __forceinline__ Xycs<float> src1(const SrcA<float>& A, const SrcB<float>& B) { return {A.x1, A.y1, B.c1, B.s1}; }
+__device__ __forceinline__ Xycs<double> src0(const SrcA<double>& A, const SrcB<double>& B) { return {A.x0, A.y0, B.c0, B.s0}; }
+__device__ __forceinline__ Xycs<double> src1(const SrcA<double>& A, const SrcB<double>& B) { return {A.x1, A.y1, B.c1, B.s1}; }
+
+// Both sources of this lane in one tile against target tg: (ax, ay) and (bx, by) each take one source.
+// f32: packed FFMA2 evaluation, the two halves of (ax, ay) are the two sources' partial sums.
+template <bool P2R> struct TileAcc32 {
+    F2 x, y;
+    __device__ __forceinline__ TileAcc32() : x(splat(0.f)), y(splat(0.f)) {}
+    __device__ __forceinline__ void eval(const SrcA<float>& A, const SrcB<float>& B, const Tgt<float>& tg,
+                                         const PairConst<float>& k) {
+        pair_eval2<P2R>(A.x0, A.x1, A.y0, A.y1, B.c0, B.c1, B.s0, B.s1, tg, k, x, y);
+    }
+    __device__ __forceinline__ void merge(const TileAcc32& o) { x = add2(x, o.x); y = add2(y, o.y); }
+    __device__ __forceinline__ void total(float& sx, float& sy) const {
+        float a, b;
+        up(x, a, b); sx = a + b;
+        up(y, a, b); sy = a + b;
+    }
+};
+template <bool P2R> struct TileAcc64 {
+    double x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    __device__ __forceinline__ void eval(const SrcA<double>& A, const SrcB<double>& B, const Tgt<double>& tg,
+                                         const PairConst<double>& k) {
+        pair_eval<double, P2R>(src0(A, B), tg, k, x0, y0);
+        pair_eval<double, P2R>(src1(A, B), tg, k, x1, y1);
+    }
+    __device__ __forceinline__ void merge(const TileAcc64& o) { x0 += o.x0; y0 += o.y0; x1 += o.x1; y1 += o.y1; }
+    __device__ __forceinline__ void total(double& sx, double& sy) const { sx = x0 + x1; sy = y0 + y1; }
+};
+template <typename T, bool P2R> struct TileAccSel;
+template <bool P2R> struct TileAccSel<float, P2R> { typedef TileAcc32<P2R> type; };
+template <bool P2R> struct TileAccSel<double, P2R> { typedef TileAcc64<P2R> type; };
+
+// ---- bounding circles ---------------------------------------------------------------------------
 __device__ __forceinline__ void pad_entry(Xycs<float>& e) { e.xq = 1 << 30; e.yq = 1 << 30; e.c = 1.f; e.s = 0.f; }
 __device__ __forceinline__ void pad_entry(Xycs<double>& e) { e.x = 1e150; e.y = 1e150; e.c = 1.0; e.s = 0.0; }
-__device__ __forceinline__ void tile_bounds(const Xycs<float>& a, const Xycs<float>& b, bool va, bool vb, int cnt,
-                                            Tile<float>* out, int lane) {
-    int xmin = va ? a.xq : INT32_MAX, xmax = va ? a.xq : INT32_MIN, ymin = va ? a.yq : INT32_MAX,
-        ymax = va ? a.yq : INT32_MIN;
-    if (vb) { xmin = min(xmin, b.xq); xmax = max(xmax, b.xq); ymin = min(ymin, b.yq); ymax = max(ymax, b.yq); }
+
+// running bounding box of payload positions (integer for the Q-format payload: exact)
+template <typename T> struct BBox;
+template <> struct BBox<float> {
+    int xmin = INT32_MAX, xmax = INT32_MIN, ymin = INT32_MAX, ymax = INT32_MIN;
+    __device__ __forceinline__ void add(int x, int y) { xmin = min(xmin, x); xmax = max(xmax, x); ymin = min(ymin, y); ymax = max(ymax, y); }
+    __device__ __forceinline__ void add(const Xycs<float>& e) { add(e.xq, e.yq); }
+    __device__ __forceinline__ void warp_reduce() {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
-        xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
-        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
-        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        for (int o = 16; o > 0; o >>= 1) {
+            xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+            xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+            ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+            ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        }
     }
-    if (lane == 0) {
+    __device__ __forceinline__ Tile<float> circle(int64_t cnt) const {
         Tile<float> t;
+        if (cnt <= 0) { t.cx = 1 << 30; t.cy = 1 << 30; t.R = 0.f; t.cnt = 0; return t; }
         t.cx = (int)(((int64_t)xmin + xmax) >> 1);
         t.cy = (int)(((int64_t)ymin + ymax) >> 1);
         const float hx = (float)((int64_t)xmax - xmin) * 0.5f + 1.f, hy = (float)((int64_t)ymax - ymin) * 0.5f + 1.f;
         t.R = sqrtf(hx * hx + hy * hy) * 1.000001f + 1.f;
-        t.cnt = cnt;
-        *out = t;
+        t.cnt = (int32_t)cnt;
+        return t;
     }
-}
-__device__ __forceinline__ void tile_bounds(const Xycs<double>& a, const Xycs<double>& b, bool va, bool vb, int cnt,
-                                            Tile<double>* out, int lane) {
-    double xmin = va ? a.x : 1e300, xmax = va ? a.x : -1e300, ymin = va ? a.y : 1e300, ymax = va ? a.y : -1e300;
-    if (vb) { xmin = fmin(xmin, b.x); xmax = fmax(xmax, b.x); ymin = fmin(ymin, b.y); ymax = fmax(ymax, b.y); }
+};
+template <> struct BBox<double> {
+    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+    __device__ __forceinline__ void add(double x, double y) { xmin = fmin(xmin, x); xmax = fmax(xmax, x); ymin = fmin(ymin, y); ymax = fmax(ymax, y); }
+    __device__ __forceinline__ void add(const Xycs<double>& e) { add(e.x, e.y); }
+    __device__ __forceinline__ void warp_reduce() {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
-        xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
-        ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
-        ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        for (int o = 16; o > 0; o >>= 1) {
+            xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+            xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+            ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+            ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        }
     }
-    if (lane == 0) {
+    __device__ __forceinline__ Tile<double> circle(int64_t cnt) const {
         Tile<double> t;
+        if (cnt <= 0) { t.cx = 1e150; t.cy = 1e150; t.R = 0.0; t.cnt = 0; return t; }
         t.cx = 0.5 * (xmin + xmax);
         t.cy = 0.5 * (ymin + ymax);
         const double hx = 0.5 * (xmax - xmin), hy = 0.5 * (ymax - ymin);
         t.R = sqrt(hx * hx + hy * hy) * (1.0 + 1e-12) + 1e-9;
         t.cnt = cnt;
-        *out = t;
+        return t;
     }
-}
+};
 
-// sorted[t*64 + l] = xycs[perm[t*64 + l]] (perm == nullptr: identity); entries past n are padded
-// with a far-away sentinel that contributes exactly 0.
+// One warp per tile: gather the tile's 64 sources through `perm` (nullptr: identity), write them in
+// the SrcA/SrcB layout and the tile's bounding circle.  Entries past n are padded with a far-away
+// sentinel that contributes exactly 0 and is not part of any bounding circle.
 template <typename T>
 __global__ void tile_sources_kernel(const Xycs<T>* __restrict__ xycs, int64_t n, const int64_t* __restrict__ perm,
-                                    Xycs<T>* __restrict__ sorted, Tile<T>* __restrict__ tiles, int64_t n_tiles) {
+                                    unsigned char* __restrict__ sorted, Tile<T>* __restrict__ tiles, int64_t n_tiles) {
     const int lane = threadIdx.x & 31;
     const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (t >= n_tiles) return;
@@ -118,10 +173,52 @@ __global__ void tile_sources_kernel(const Xycs<T>* __restrict__ xycs, int64_t n,
     const bool va = i0 < n, vb = i1 < n;
     if (va) a = xycs[perm ? perm[i0] : i0]; else pad_entry(a);
     if (vb) b = xycs[perm ? perm[i1] : i1]; else pad_entry(b);
-    sorted[i0] = a;
-    sorted[i1] = b;
+    SrcA<T> A;
+    SrcB<T> B;
+    split(a, b, A, B);
+    unsigned char* base = sorted + (size_t)t * TileBytes<T>::v;
+    reinterpret_cast<SrcA<T>*>(base)[lane] = A;
+    reinterpret_cast<SrcB<T>*>(base + 32 * sizeof(SrcA<T>))[lane] = B;
+    BBox<T> bb;
+    if (va) bb.add(a);
+    if (vb) bb.add(b);
+    bb.warp_reduce();
     const int64_t rem = n - t * kTileS;
-    tile_bounds(a, b, va, vb, (int)(rem < kTileS ? rem : kTileS), tiles + t, lane);
+    if (lane == 0) tiles[t] = bb.circle(rem < kTileS ? rem : kTileS);
+}
+
+// One warp per chunk: bounding circle of the chunk's sources, read back from the sorted copy.
+template <typename T>
+__global__ void chunk_bounds_kernel(const unsigned char* __restrict__ sorted, int64_t n, int64_t n_tiles,
+                                    Tile<T>* __restrict__ chunks, int64_t n_chunks) {
+    const int lane = threadIdx.x & 31;
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= n_chunks) return;
+    BBox<T> bb;
+    const int64_t t_end = min(n_tiles, (c + 1) * kCT);
+    for (int64_t t = c * kCT; t < t_end; ++t) {
+        const SrcA<T> A = reinterpret_cast<const SrcA<T>*>(sorted + (size_t)t * TileBytes<T>::v)[lane];
+        const int64_t i0 = t * kTileS + lane;
+        if (i0 < n) bb.add(A.x0, A.y0);
+        if (i0 + 32 < n) bb.add(A.x1, A.y1);
+    }
+    bb.warp_reduce();
+    const int64_t cnt = min(n, (c + 1) * (int64_t)kCS) - c * (int64_t)kCS;
+    if (lane == 0) chunks[c] = bb.circle(cnt);
+}
+
+// One warp per target block: bounding circle of targets tgt[perm[b*group .. (b+1)*group)).
+template <typename T>
+__global__ void block_bounds_kernel(const Xycs<T>* __restrict__ tgt, const int64_t* __restrict__ perm, int64_t n,
+                                    int group, Tile<T>* __restrict__ blocks, int64_t n_blocks) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= n_blocks) return;
+    BBox<T> bb;
+    const int64_t i_end = min(n, (b + 1) * (int64_t)group);
+    for (int64_t i = b * (int64_t)group + lane; i < i_end; i += 32) bb.add(tgt[perm ? perm[i] : i]);
+    bb.warp_reduce();
+    if (lane == 0) blocks[b] = bb.circle(i_end - b * (int64_t)group);
 }
 
 // Morton key of a payload position (host sorts the keys; any stable order works)
@@ -152,11 +249,12 @@ __global__ void morton_kernel(const Xycs<T>* __restrict__ xycs, int64_t n, doubl
     keys[i] = (int64_t)(part1by1(kx) | (part1by1(ky) << 1));
 }
 
-// ---- cull test: tile circle (c, R) against target j's view cone --------------------------------
-// u = c - p_j in the target's frame: along = u . h_j, cross = u x h_j.  Every point of the circle
-// is outside the (closed) cone of half angle a if  |cross| cos a - along sin a > R  (distance to the
-// supporting half-plane; also valid for a >= 90 deg, where it states that the circle lies in the
-// complementary cone).  p2r additionally hides sources to the left of the heading.
+// ---- cull tests ----------------------------------------------------------------------------------
+// Tile circle (c, R) against target j's view cone: u = c - p_j in the target's frame,
+// along = u . h_j, cross = u x h_j.  Every point of the circle is outside the (closed) cone of half
+// angle a if  |cross| cos a - along sin a > R  (distance to the supporting half-plane; also valid
+// for a >= 90 deg, where it states that the circle lies in the complementary cone).  p2r additionally
+// hides sources to the left of the heading.  Beyond d_cut + R every source of the tile is negligible.
 __device__ __forceinline__ void tile_delta(const Tile<float>& t, const Tgt<float>& g, float& dx, float& dy) {
     dx = (float)(t.cx - g.xq);
     dy = (float)(t.cy - g.yq);
@@ -178,22 +276,16 @@ __device__ __forceinline__ bool tile_visible(const Tile<T>& t, const Tgt<T>& g, 
     vis = vis && (fma(dx, dx, dy * dy) <= far * far);
     return vis;
 }
-
-__device__ __forceinline__ Tgt<float> bcast(const Tgt<float>& v, int src) {
-    Tgt<float> r;
-    r.xq = __shfl_sync(0xffffffffu, v.xq, src);
-    r.yq = __shfl_sync(0xffffffffu, v.yq, src);
-    r.c = __shfl_sync(0xffffffffu, v.c, src);
-    r.s = __shfl_sync(0xffffffffu, v.s, src);
-    return r;
+// chunk circle against target-block circle: can any pair be within d_cut?
+__device__ __forceinline__ bool circles_near(const Tile<float>& a, const Tile<float>& b, float dmax) {
+    const float dx = (float)((int64_t)a.cx - b.cx), dy = (float)((int64_t)a.cy - b.cy);
+    const float far = (a.R + b.R + dmax) * 1.000001f;
+    return a.cnt > 0 && b.cnt > 0 && fmaf(dx, dx, dy * dy) <= far * far;
 }
-__device__ __forceinline__ Tgt<double> bcast(const Tgt<double>& v, int src) {
-    Tgt<double> r;
-    r.x = __shfl_sync(0xffffffffu, v.x, src);
-    r.y = __shfl_sync(0xffffffffu, v.y, src);
-    r.c = __shfl_sync(0xffffffffu, v.c, src);
-    r.s = __shfl_sync(0xffffffffu, v.s, src);
-    return r;
+__device__ __forceinline__ bool circles_near(const Tile<double>& a, const Tile<double>& b, double dmax) {
+    const double dx = a.cx - b.cx, dy = a.cy - b.cy;
+    const double far = a.R + b.R + dmax;
+    return a.cnt > 0 && b.cnt > 0 && fma(dx, dx, dy * dy) <= far * far;
 }
 
 template <typename T> __device__ __forceinline__ T warp_sum(T v) {
@@ -204,22 +296,28 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 
 // ---- the tiled pair kernel ---------------------------------------------------------------------------
 // item -> (target block tb = item % n_tblocks, chunk group cg = item / n_tblocks); a group is
-// `group_chunks` consecutive chunks of kCT tiles.  partial[cg][target][2].
+// `group_chunks` consecutive chunks.  partial[cg][target][2].
+// Stage protocol: the producer fills hdr[stage] = {item, chunk} and the stage's bytes; chunk == -1
+// closes the item (consumers write their partial sums), chunk == -2 ends the kernel.
 template <typename T, bool P2R>
-__global__ void __launch_bounds__(kTThreads, CSF_TILED_MINB)
-pair_tiled_kernel(const Xycs<T>* __restrict__ sorted, const Tile<T>* __restrict__ tiles, int64_t n_tiles,
-                  const Xycs<T>* __restrict__ tgt, int64_t n_tgt, PairConst<T> k, CullConst<T> cc,
-                  T* __restrict__ partial, int group_chunks, int n_groups, int n_tblocks,
+__global__ void __launch_bounds__(kTThreads, sizeof(T) == 4 ? CSF_TILED_MINB : 1)
+pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __restrict__ tiles, int64_t n_tiles,
+                  const Xycs<T>* __restrict__ tgt, const int64_t* __restrict__ tgt_perm, int64_t n_tgt,
+                  const Tile<T>* __restrict__ tblocks, PairConst<T> k, CullConst<T> cc, T* __restrict__ partial,
+                  int tpw, int group_chunks, int n_groups, int n_tblocks, unsigned int* __restrict__ counter,
                   unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int kStages = Stages<T>::n;
     constexpr size_t kStageBytes = (size_t)kCS * sizeof(Xycs<T>) + (size_t)kCT * sizeof(Tile<T>);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kTStages * kStageBytes);
-    uint64_t* empty = full + kTStages;
-    T* acc = reinterpret_cast<T*>(empty + kTStages);  // [kTW][kTPW][2]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * kStageBytes);
+    uint64_t* empty = full + kStages;
+    int2* hdr = reinterpret_cast<int2*>(empty + kStages);
+    Xycs<T>* wtgt_all = reinterpret_cast<Xycs<T>*>(hdr + kStages + (kStages & 1));   // 16-byte aligned
+    T* wacc_all = reinterpret_cast<T*>(wtgt_all + kTW * kMaxTPW);                  // [kTW][kMaxTPW][2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kTStages; ++s) {
+        for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kTW);
         }
@@ -227,29 +325,63 @@ pair_tiled_kernel(const Xycs<T>* __restrict__ sorted, const Tile<T>* __restrict_
     }
     __syncthreads();
 
-    const int64_t n_items = (int64_t)n_tblocks * n_groups;
+    const unsigned int n_items = (unsigned int)n_tblocks * (unsigned int)n_groups;
     const int64_t n_chunks = (n_tiles + kCT - 1) / kCT;
+    const Tile<T>* chunks = tiles + n_tiles;
 
     if (warp == kTW) {
-        // ===== producer: stream the chunks of every item's chunk group =====
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int64_t cg = item / n_tblocks;
-                const int64_t c_end = min(n_chunks, (cg + 1) * (int64_t)group_chunks);
-                for (int64_t ch = cg * group_chunks; ch < c_end; ++ch, ++it) {
-                    const int stage = it % kTStages;
-                    const uint32_t phase = (it / kTStages) & 1;
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    const int64_t t0 = ch * kCT;
-                    const uint32_t nt = (uint32_t)min((int64_t)kCT, n_tiles - t0);
-                    const uint32_t bsrc = nt * kTileS * (uint32_t)sizeof(Xycs<T>), btile = nt * (uint32_t)sizeof(Tile<T>);
-                    unsigned char* base = smem_raw + stage * kStageBytes;
-                    mbar_expect_tx(&full[stage], bsrc + btile);
-                    tma_bulk_g2s(base, sorted + t0 * kTileS, bsrc, &full[stage]);
-                    tma_bulk_g2s(base + (size_t)kCS * sizeof(Xycs<T>), tiles + t0, btile, &full[stage]);
+        // ===== producer warp: fetch items, cull chunks against the target block, stream the rest =====
+        uint32_t it = 0;
+        for (;;) {
+            unsigned int item = 0;
+            if (lane == 0) item = atomicAdd(counter, 1u);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item >= n_items) break;
+            const int tb = (int)(item % (unsigned int)n_tblocks), cg = (int)(item / (unsigned int)n_tblocks);
+            const Tile<T> tbr = tblocks[tb];
+            const int64_t c_begin = (int64_t)cg * group_chunks, c_end = min(n_chunks, c_begin + group_chunks);
+            for (int64_t c0 = c_begin; c0 < c_end; c0 += 32) {
+                const int64_t c = c0 + lane;
+                bool near = false;
+                if (c < c_end) near = circles_near(chunks[c], tbr, cc.dmax);
+                uint32_t m = __ballot_sync(0xffffffffu, near);
+                while (m) {
+                    const int64_t ch = c0 + (__ffs(m) - 1);
+                    m &= m - 1;
+                    const int stage = it % kStages;
+                    const uint32_t phase = (it / kStages) & 1;
+                    if (lane == 0) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        const int64_t t0 = ch * kCT;
+                        const uint32_t nt = (uint32_t)min((int64_t)kCT, n_tiles - t0);
+                        const uint32_t bsrc = nt * (uint32_t)TileBytes<T>::v, btile = nt * (uint32_t)sizeof(Tile<T>);
+                        unsigned char* base = smem_raw + stage * kStageBytes;
+                        hdr[stage] = make_int2((int)item, (int)ch);
+                        mbar_expect_tx(&full[stage], bsrc + btile);
+                        tma_bulk_g2s(base, sorted + (size_t)t0 * TileBytes<T>::v, bsrc, &full[stage]);
+                        tma_bulk_g2s(base + (size_t)kCS * sizeof(Xycs<T>), tiles + t0, btile, &full[stage]);
+                    }
+                    ++it;
                 }
             }
+            {   // close the item
+                const int stage = it % kStages;
+                const uint32_t phase = (it / kStages) & 1;
+                if (lane == 0) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    hdr[stage] = make_int2((int)item, -1);
+                    mbar_arrive(&full[stage]);
+                }
+                ++it;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            const int stage = it % kStages;
+            const uint32_t phase = (it / kStages) & 1;
+            mbar_wait(&empty[stage], phase ^ 1);
+            hdr[stage] = make_int2(0, -2);
+            mbar_arrive(&full[stage]);
         }
         return;
     }
@@ -257,76 +389,78 @@ pair_tiled_kernel(const Xycs<T>* __restrict__ sorted, const Tile<T>* __restrict_
     // ===== consumer warps: one target at a time =====
     uint32_t it = 0;
     unsigned long long n_eval = 0;
-    T* wacc = acc + warp * kTPW * 2;
-    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int64_t tb = item % n_tblocks, cg = item / n_tblocks;
-        const int64_t c_end = min(n_chunks, (cg + 1) * (int64_t)group_chunks);
-        const int64_t t_first = tb * kTB + warp * kTPW;
-        if (lane < kTPW * 2) wacc[lane] = (T)0;
-        // lane q keeps target q of this warp in registers for the whole item
-        Tgt<T> mine;
-        {
-            const int64_t jm = min(t_first + (lane % kTPW), n_tgt - 1);
-            const Xycs<T> e = tgt[jm < 0 ? 0 : jm];
-            mine = *reinterpret_cast<const Tgt<T>*>(&e);
+    Xycs<T>* wtgt = wtgt_all + warp * kMaxTPW;
+    T* wacc = wacc_all + warp * kMaxTPW * 2;
+    int cur = -1, cg = 0, nq = 0;
+    long long myj = -1;
+    for (;;) {
+        const int stage = it % kStages;
+        const uint32_t phase = (it / kStages) & 1;
+        mbar_wait(&full[stage], phase);
+        const int2 h = hdr[stage];
+        if (h.y == -2) break;
+        if (h.x != cur) {
+            // open the item: lane q < tpw keeps target q of this warp
+            cur = h.x;
+            const int tb = cur % n_tblocks;
+            cg = cur / n_tblocks;
+            const int64_t t_first = ((int64_t)tb * kTW + warp) * tpw;
+            const int64_t left = n_tgt - t_first;
+            nq = (int)(left < 0 ? 0 : (left < tpw ? left : tpw));
+            __syncwarp();
+            myj = -1;
+            if (lane < nq) {
+                myj = tgt_perm ? tgt_perm[t_first + lane] : (t_first + lane);
+                wtgt[lane] = tgt[myj];
+            }
+            wacc[lane] = (T)0;
+            __syncwarp();
         }
-        __syncwarp();
-        for (int64_t ch = cg * group_chunks; ch < c_end; ++ch, ++it) {
-            const int stage = it % kTStages;
-            const uint32_t phase = (it / kTStages) & 1;
+        if (h.y == -1) {
+            // close the item: write this warp's partial sums
+            const long long jj = __shfl_sync(0xffffffffu, myj, (lane >> 1) & (kMaxTPW - 1));
+            if ((lane >> 1) < nq) partial[((size_t)cg * n_tgt + (size_t)jj) * 2 + (lane & 1)] = wacc[lane];
+        } else {
+            const int64_t ch = h.y;
             const int nt = (int)min((int64_t)kCT, n_tiles - ch * kCT);
-            mbar_wait(&full[stage], phase);
-            const Xycs<T>* src = reinterpret_cast<const Xycs<T>*>(smem_raw + stage * kStageBytes);
-            const Tile<T>* trec = reinterpret_cast<const Tile<T>*>(smem_raw + stage * kStageBytes +
-                                                                  (size_t)kCS * sizeof(Xycs<T>));
+            const unsigned char* base = smem_raw + stage * kStageBytes;
+            const Tile<T>* trec = reinterpret_cast<const Tile<T>*>(base + (size_t)kCS * sizeof(Xycs<T>));
             Tile<T> mytile;
             if (lane < nt) mytile = trec[lane];
 #pragma unroll 1
-            for (int q = 0; q < kTPW; ++q) {
-                const int64_t j = t_first + q;
-                if (j >= n_tgt) break;
-                const Tgt<T> tg = bcast(mine, q);
+            for (int q = 0; q < nq; ++q) {
+                const Xycs<T> te = wtgt[q];
+                const Tgt<T> tg = *reinterpret_cast<const Tgt<T>*>(&te);
                 const bool v = (lane < nt) && tile_visible<T, P2R>(mytile, tg, cc);
                 uint32_t mask = __ballot_sync(0xffffffffu, v);
                 if (mask == 0) continue;
-                T ax = (T)0, ay = (T)0;
                 if (stats) n_eval += (unsigned long long)__popc(mask) * kTileS;
-#if CSF_TILED_ILP4
+                typename TileAccSel<T, P2R>::type acc0, acc1;
                 // two surviving tiles per iteration: four independent pair evaluations in flight
-                T bx = (T)0, by = (T)0;
                 while (mask & (mask - 1)) {
                     const int t0 = __ffs(mask) - 1;
                     mask &= mask - 1;
                     const int t1 = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    const Xycs<T> s0 = src[t0 * kTileS + lane];
-                    const Xycs<T> s1 = src[t0 * kTileS + 32 + lane];
-                    const Xycs<T> s2 = src[t1 * kTileS + lane];
-                    const Xycs<T> s3 = src[t1 * kTileS + 32 + lane];
-                    pair_eval<T, P2R>(s0, tg, k, ax, ay);
-                    pair_eval<T, P2R>(s1, tg, k, bx, by);
-                    pair_eval<T, P2R>(s2, tg, k, ax, ay);
-                    pair_eval<T, P2R>(s3, tg, k, bx, by);
+                    const unsigned char* p0 = base + (size_t)t0 * TileBytes<T>::v;
+                    const unsigned char* p1 = base + (size_t)t1 * TileBytes<T>::v;
+                    const SrcA<T> A0 = reinterpret_cast<const SrcA<T>*>(p0)[lane];
+                    const SrcB<T> B0 = reinterpret_cast<const SrcB<T>*>(p0 + 32 * sizeof(SrcA<T>))[lane];
+                    const SrcA<T> A1 = reinterpret_cast<const SrcA<T>*>(p1)[lane];
+                    const SrcB<T> B1 = reinterpret_cast<const SrcB<T>*>(p1 + 32 * sizeof(SrcA<T>))[lane];
+                    acc0.eval(A0, B0, tg, k);
+                    acc1.eval(A1, B1, tg, k);
                 }
                 if (mask) {
-                    const int t = __ffs(mask) - 1;
-                    const Xycs<T> s0 = src[t * kTileS + lane];
-                    const Xycs<T> s1 = src[t * kTileS + 32 + lane];
-                    pair_eval<T, P2R>(s0, tg, k, ax, ay);
-                    pair_eval<T, P2R>(s1, tg, k, bx, by);
+                    const int t0 = __ffs(mask) - 1;
+                    const unsigned char* p0 = base + (size_t)t0 * TileBytes<T>::v;
+                    const SrcA<T> A0 = reinterpret_cast<const SrcA<T>*>(p0)[lane];
+                    const SrcB<T> B0 = reinterpret_cast<const SrcB<T>*>(p0 + 32 * sizeof(SrcA<T>))[lane];
+                    acc0.eval(A0, B0, tg, k);
                 }
-                ax += bx;
-                ay += by;
-#else
-                while (mask) {
-                    const int t = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const Xycs<T> s0 = src[t * kTileS + lane];
-                    const Xycs<T> s1 = src[t * kTileS + 32 + lane];
-                    pair_eval<T, P2R>(s0, tg, k, ax, ay);
-                    pair_eval<T, P2R>(s1, tg, k, ax, ay);
-                }
-#endif
+                acc0.merge(acc1);
+                T ax, ay;
+                acc0.total(ax, ay);
                 ax = warp_sum(ax);
                 ay = warp_sum(ay);
                 if (lane == 0) {
@@ -334,15 +468,10 @@ pair_tiled_kernel(const Xycs<T>* __restrict__ sorted, const Tile<T>* __restrict_
                     wacc[q * 2 + 1] += ay;
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
         }
         __syncwarp();
-        if (lane < kTPW * 2) {
-            const int64_t j = t_first + (lane >> 1);
-            if (j < n_tgt) partial[((size_t)cg * n_tgt + j) * 2 + (lane & 1)] = wacc[lane];
-        }
-        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        ++it;
     }
     if (stats && lane == 0 && n_eval) atomicAdd(stats, n_eval);
 }
@@ -359,8 +488,10 @@ __global__ void reduce_groups_kernel(const T* __restrict__ partial, int n_groups
 }
 
 template <typename T> size_t tiled_smem_bytes() {
-    return kTStages * ((size_t)kCS * sizeof(Xycs<T>) + (size_t)kCT * sizeof(Tile<T>)) + 2 * kTStages * sizeof(uint64_t) +
-           (size_t)kTW * kTPW * 2 * sizeof(T);
+    constexpr int kStages = Stages<T>::n;
+    return kStages * ((size_t)kCS * sizeof(Xycs<T>) + (size_t)kCT * sizeof(Tile<T>)) + 2 * kStages * sizeof(uint64_t) +
+           (kStages + (kStages & 1)) * sizeof(int2) + (size_t)kTW * kMaxTPW * sizeof(Xycs<T>) +
+           (size_t)kTW * kMaxTPW * 2 * sizeof(T);
 }
 
 int g_tiled_ctas[2] = {0, 0};
@@ -388,19 +519,34 @@ template <typename T> int tiled_ctas() {
     return g_tiled_ctas[idx];
 }
 
-struct TiledPlan { int n_tblocks, n_groups, group_chunks, grid; int64_t n_tiles; };
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+// Work decomposition: target blocks of kTW * tpw targets; if there are too few blocks to keep every
+// CTA slot busy with several items, shrink tpw (down to 4) and then split the chunk range in groups.
+struct TiledPlan { int tpw, n_tblocks, n_groups, group_chunks, grid; int64_t n_tiles, n_chunks; };
 template <typename T> TiledPlan tiled_plan(int64_t n_src, int64_t n_tgt) {
+    static const int env_tpw = env_int("CSF_TILED_TPW", 0), env_groups = env_int("CSF_TILED_GROUPS", 0),
+                     env_ipw = env_int("CSF_TILED_ITEMS_PER_SLOT", 8);
     TiledPlan p;
     p.n_tiles = (n_src + kTileS - 1) / kTileS;
-    const int64_t n_chunks = (p.n_tiles + kCT - 1) / kCT;
-    const int64_t tb = (n_tgt + kTB - 1) / kTB;
+    p.n_chunks = (p.n_tiles + kCT - 1) / kCT;
     const int64_t slots = (int64_t)csf_sm_count() * tiled_ctas<T>();
-    int64_t groups = (64 * slots + tb - 1) / tb;      // items >= 64 x slots (item cost varies with culling)
+    const int64_t want = (int64_t)env_ipw * slots;
+    int tpw = kMaxTPW;
+    while (tpw > 4 && (n_tgt + (int64_t)kTW * tpw - 1) / ((int64_t)kTW * tpw) < want) tpw >>= 1;
+    if (env_tpw >= 1 && env_tpw <= kMaxTPW) tpw = env_tpw;
+    const int64_t tb = (n_tgt + (int64_t)kTW * tpw - 1) / ((int64_t)kTW * tpw);
+    int64_t groups = (want + tb - 1) / tb;
+    if (env_groups >= 1) groups = env_groups;
     if (groups < 1) groups = 1;
     if (groups > kTMaxGroups) groups = kTMaxGroups;
-    if (groups > n_chunks) groups = n_chunks;
-    const int64_t gc = (n_chunks + groups - 1) / groups;
-    groups = (n_chunks + gc - 1) / gc;
+    if (groups > p.n_chunks) groups = p.n_chunks;
+    const int64_t gc = (p.n_chunks + groups - 1) / groups;
+    groups = (p.n_chunks + gc - 1) / gc;
+    p.tpw = tpw;
     p.n_tblocks = (int)tb;
     p.n_groups = (int)groups;
     p.group_chunks = (int)gc;
@@ -409,21 +555,54 @@ template <typename T> TiledPlan tiled_plan(int64_t n_src, int64_t n_tgt) {
     return p;
 }
 
+// Rigorous lower bound of the decay rate q/sigma [1/m] of |F| = f_0 exp(-rho q / sigma) over
+// s2 = sin^2(psi_i - psi_j) in [0,1] and c = cos(phi) in [-1,1] (vehicle.py:1596-1613), by interval
+// arithmetic on a grid of cells.  0 if the field has no positive bound (then nothing is truncated).
+double field_min_decay_rate(const CsfFieldParams* fp) {
+    const int NS = 256, NC = 512;
+    double best = 1e300;
+    for (int i = 0; i < NS; ++i) {
+        const double s_lo = (double)i / NS, s_hi = (double)(i + 1) / NS;
+        const double e_a = fp->e_0 - fp->e_1 * s_lo, e_b = fp->e_0 - fp->e_1 * s_hi;
+        const double emax = fmax(fabs(e_a), fabs(e_b));
+        const double A_hi = fmax(fp->sigma_0 + fp->sigma_1 * s_lo, fp->sigma_0 + fp->sigma_1 * s_hi);
+        const double B_a = fp->sigma_2 + fp->sigma_3 * s_lo, B_b = fp->sigma_2 + fp->sigma_3 * s_hi;
+        for (int j = 0; j < NC; ++j) {
+            const double c_lo = -1.0 + 2.0 * j / NC, c_hi = -1.0 + 2.0 * (j + 1) / NC;
+            const double cmax = fmax(fabs(c_lo), fabs(c_hi));
+            const double q2 = 1.0 - emax * emax * cmax * cmax;
+            if (!(q2 > 0.0)) return 0.0;
+            const double h_lo = sqrt(fmax(0.0, (1.0 - c_hi) * 0.5)), h_hi = sqrt(fmax(0.0, (1.0 - c_lo) * 0.5));
+            const double bh = fmin(fmin(B_a * h_lo, B_a * h_hi), fmin(B_b * h_lo, B_b * h_hi));
+            const double sig_hi = A_hi - bh;
+            if (!(sig_hi > 0.0)) return 0.0;
+            best = fmin(best, sqrt(q2) / sig_hi);
+        }
+    }
+    return best < 1e300 ? best : 0.0;
+}
+
 template <typename T> CullConst<T> make_cull(const CsfFieldParams* fp, bool is_f32) {
     CullConst<T> c;
     const double a = fmin(fp->hfov * 0.5, CSF_PI);
     c.ca = (T)cos(a);
     c.sa = (T)sin(a);
     if (a >= CSF_PI) { c.ca = (T)-1; c.sa = (T)0; }
+    c.dmax = (T)(is_f32 ? 3.0e9 : 1e150);                 // never (payload positions span < 2^31 units)
     if (is_f32) {
-        // every pair of the tile has rho >= d - R; exponent rho q / sigma >= rho * qmin / sigma_max
-        const double emax = fmax(fabs(fp->e_0), fabs(fp->e_0 - fp->e_1));
-        const double qmin = sqrt(fmax(1.0 - emax * emax, 1e-12));
-        const double smax = fmax(fp->sigma_0, fp->sigma_0 + fp->sigma_1);
-        const double d_m = 40.0 * 0.6931471805599453 * smax / qmin;   // metres: exp(-d qmin/smax) = 2^-40
-        c.dmax = (T)(d_m / fp->q_scale);
-    } else {
-        c.dmax = (T)1e150;
+        // exp(-d * rate) = 2^-cutoff_log2  ->  d_cut; cached per parameter set
+        static CsfFieldParams cached;
+        static double cached_rate = -1.0;
+        if (cached_rate < 0.0 || cached.e_0 != fp->e_0 || cached.e_1 != fp->e_1 || cached.sigma_0 != fp->sigma_0 ||
+            cached.sigma_1 != fp->sigma_1 || cached.sigma_2 != fp->sigma_2 || cached.sigma_3 != fp->sigma_3) {
+            cached = *fp;
+            cached_rate = field_min_decay_rate(fp);
+        }
+        const double bits = fp->cutoff_log2 > 0.0 ? fp->cutoff_log2 : 40.0;
+        if (cached_rate > 0.0) {
+            const double d_units = bits * 0.6931471805599453 / cached_rate * 1.0001 / fp->q_scale;
+            if (d_units < 3.0e9) c.dmax = (T)d_units;
+        }
     }
     return c;
 }
@@ -431,25 +610,33 @@ template <typename T> CullConst<T> make_cull(const CsfFieldParams* fp, bool is_f
 template <typename T>
 int tile_sources(const void* xycs, int64_t n, const int64_t* perm, void* sorted, void* tiles, cudaStream_t st) {
     if (n <= 0) return 0;
-    const int64_t n_tiles = (n + kTileS - 1) / kTileS;
-    const int64_t threads = n_tiles * 32;
-    tile_sources_kernel<T><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
-        (const Xycs<T>*)xycs, n, perm, (Xycs<T>*)sorted, (Tile<T>*)tiles, n_tiles);
+    const int64_t n_tiles = (n + kTileS - 1) / kTileS, n_chunks = (n_tiles + kCT - 1) / kCT;
+    tile_sources_kernel<T><<<(unsigned)((n_tiles * 32 + 127) / 128), 128, 0, st>>>(
+        (const Xycs<T>*)xycs, n, perm, (unsigned char*)sorted, (Tile<T>*)tiles, n_tiles);
     CSF_CHECK_LAUNCH("tile_sources_kernel");
+    chunk_bounds_kernel<T><<<(unsigned)((n_chunks * 32 + 127) / 128), 128, 0, st>>>(
+        (const unsigned char*)sorted, n, n_tiles, (Tile<T>*)tiles + n_tiles, n_chunks);
+    CSF_CHECK_LAUNCH("chunk_bounds_kernel");
     return 0;
 }
 
+constexpr size_t kWsHeader = 256;   // item counter
+template <typename T> size_t tiled_ws_blocks_bytes(const TiledPlan& pl) {
+    return (((size_t)pl.n_tblocks * sizeof(Tile<T>)) + 255) / 256 * 256;
+}
+
 template <typename T>
-int pair_tiled(const void* sorted, const void* tiles, int64_t n_src, const void* tgt, int64_t n_tgt,
-               const CsfFieldParams* fp, T* frep, int accumulate, void* ws, size_t wsb, unsigned long long* stats,
-               cudaStream_t st) {
+int pair_tiled(const void* sorted, const void* tiles, int64_t n_src, const void* tgt, const int64_t* tgt_perm,
+               int64_t n_tgt, const CsfFieldParams* fp, T* frep, int accumulate, void* ws, size_t wsb,
+               unsigned long long* stats, cudaStream_t st) {
     if (n_tgt <= 0) return 0;
     if (n_src <= 0 || fp->f_0 == 0.0) {
         if (!accumulate) cudaMemsetAsync(frep, 0, sizeof(T) * 2 * n_tgt, st);
         return 0;
     }
     const TiledPlan pl = tiled_plan<T>(n_src, n_tgt);
-    const size_t need = (size_t)pl.n_groups * n_tgt * 2 * sizeof(T);
+    const size_t off_partial = kWsHeader + tiled_ws_blocks_bytes<T>(pl);
+    const size_t need = off_partial + (size_t)pl.n_groups * n_tgt * 2 * sizeof(T);
     if (ws == nullptr || wsb < need) {
         csf_set_error("csf_pair_forces_tiled: workspace too small", cudaErrorInvalidValue);
         return -(int)cudaErrorInvalidValue;
@@ -457,15 +644,22 @@ int pair_tiled(const void* sorted, const void* tiles, int64_t n_src, const void*
     const PairConst<T> k = make_const<T>(fp, sizeof(T) == 4);
     const CullConst<T> cc = make_cull<T>(fp, sizeof(T) == 4);
     const size_t smem = tiled_smem_bytes<T>();
-    T* partial = reinterpret_cast<T*>(ws);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
+    Tile<T>* tblocks = reinterpret_cast<Tile<T>*>((unsigned char*)ws + kWsHeader);
+    T* partial = reinterpret_cast<T*>((unsigned char*)ws + off_partial);
+    cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
+    block_bounds_kernel<T><<<(unsigned)(((int64_t)pl.n_tblocks * 32 + 127) / 128), 128, 0, st>>>(
+        (const Xycs<T>*)tgt, tgt_perm, n_tgt, kTW * pl.tpw, tblocks, pl.n_tblocks);
+    CSF_CHECK_LAUNCH("block_bounds_kernel");
+    tiled_ctas<T>();   // sets the dynamic shared-memory attribute
     if (fp->p2r)
         pair_tiled_kernel<T, true><<<pl.grid, kTThreads, smem, st>>>(
-            (const Xycs<T>*)sorted, (const Tile<T>*)tiles, pl.n_tiles, (const Xycs<T>*)tgt, n_tgt, k, cc, partial,
-            pl.group_chunks, pl.n_groups, pl.n_tblocks, stats);
+            (const unsigned char*)sorted, (const Tile<T>*)tiles, pl.n_tiles, (const Xycs<T>*)tgt, tgt_perm, n_tgt,
+            tblocks, k, cc, partial, pl.tpw, pl.group_chunks, pl.n_groups, pl.n_tblocks, counter, stats);
     else
         pair_tiled_kernel<T, false><<<pl.grid, kTThreads, smem, st>>>(
-            (const Xycs<T>*)sorted, (const Tile<T>*)tiles, pl.n_tiles, (const Xycs<T>*)tgt, n_tgt, k, cc, partial,
-            pl.group_chunks, pl.n_groups, pl.n_tblocks, stats);
+            (const unsigned char*)sorted, (const Tile<T>*)tiles, pl.n_tiles, (const Xycs<T>*)tgt, tgt_perm, n_tgt,
+            tblocks, k, cc, partial, pl.tpw, pl.group_chunks, pl.n_groups, pl.n_tblocks, counter, stats);
     CSF_CHECK_LAUNCH("pair_tiled_kernel");
     const int64_t n2 = n_tgt * 2;
     reduce_groups_kernel<T><<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(partial, pl.n_groups, n_tgt, (T)fp->f_0, frep,
@@ -479,12 +673,24 @@ int pair_tiled(const void* sorted, const void* tiles, int64_t n_src, const void*
 extern "C" {
 
 int64_t csf_tiled_padded_sources(int64_t n_src) { return ((n_src + kTileS - 1) / kTileS) * kTileS; }
-int64_t csf_tiled_num_tiles(int64_t n_src) { return (n_src + kTileS - 1) / kTileS; }
+int64_t csf_tiled_num_tiles(int64_t n_src) {
+    const int64_t t = (n_src + kTileS - 1) / kTileS;
+    return t + (t + kCT - 1) / kCT;          // tile records followed by chunk records
+}
 int csf_tiled_tile_bytes(int elem_bytes) { return elem_bytes == 4 ? (int)sizeof(Tile<float>) : (int)sizeof(Tile<double>); }
 size_t csf_pair_tiled_workspace_bytes(int64_t n_src, int64_t n_tgt, int elem_bytes) {
     if (n_src <= 0 || n_tgt <= 0) return 0;
-    const int groups = elem_bytes == 4 ? tiled_plan<float>(n_src, n_tgt).n_groups : tiled_plan<double>(n_src, n_tgt).n_groups;
-    return (size_t)groups * (size_t)n_tgt * 2 * (size_t)elem_bytes;
+    if (elem_bytes == 4) {
+        const TiledPlan pl = tiled_plan<float>(n_src, n_tgt);
+        return kWsHeader + tiled_ws_blocks_bytes<float>(pl) + (size_t)pl.n_groups * (size_t)n_tgt * 2 * 4;
+    }
+    const TiledPlan pl = tiled_plan<double>(n_src, n_tgt);
+    return kWsHeader + tiled_ws_blocks_bytes<double>(pl) + (size_t)pl.n_groups * (size_t)n_tgt * 2 * 8;
+}
+double csf_field_cutoff_distance(const CsfFieldParams* fp) {
+    const double rate = field_min_decay_rate(fp);
+    const double bits = fp->cutoff_log2 > 0.0 ? fp->cutoff_log2 : 40.0;
+    return rate > 0.0 ? bits * 0.6931471805599453 / rate : INFINITY;
 }
 int csf_morton_keys_f32(const void* xycs, int64_t n, double x0, double y0, double cell, int64_t* keys, csf_stream_t st) {
     if (n <= 0) return 0;
@@ -506,15 +712,17 @@ int csf_tile_sources_f32(const void* xycs, int64_t n, const int64_t* perm, void*
 int csf_tile_sources_f64(const void* xycs, int64_t n, const int64_t* perm, void* sorted, void* tiles, csf_stream_t st) {
     return tile_sources<double>(xycs, n, perm, sorted, tiles, (cudaStream_t)st);
 }
-int csf_pair_forces_tiled_f32(const void* sorted, const void* tiles, int64_t n_src, const void* tgt, int64_t n_tgt,
-                              const CsfFieldParams* fp, float* frep, int accumulate, void* ws, size_t wsb,
-                              unsigned long long* stats, csf_stream_t st) {
-    return pair_tiled<float>(sorted, tiles, n_src, tgt, n_tgt, fp, frep, accumulate, ws, wsb, stats, (cudaStream_t)st);
+int csf_pair_forces_tiled_f32(const void* sorted, const void* tiles, int64_t n_src, const void* tgt,
+                              const int64_t* tgt_perm, int64_t n_tgt, const CsfFieldParams* fp, float* frep,
+                              int accumulate, void* ws, size_t wsb, unsigned long long* stats, csf_stream_t st) {
+    return pair_tiled<float>(sorted, tiles, n_src, tgt, tgt_perm, n_tgt, fp, frep, accumulate, ws, wsb, stats,
+                             (cudaStream_t)st);
 }
-int csf_pair_forces_tiled_f64(const void* sorted, const void* tiles, int64_t n_src, const void* tgt, int64_t n_tgt,
-                              const CsfFieldParams* fp, double* frep, int accumulate, void* ws, size_t wsb,
-                              unsigned long long* stats, csf_stream_t st) {
-    return pair_tiled<double>(sorted, tiles, n_src, tgt, n_tgt, fp, frep, accumulate, ws, wsb, stats, (cudaStream_t)st);
+int csf_pair_forces_tiled_f64(const void* sorted, const void* tiles, int64_t n_src, const void* tgt,
+                              const int64_t* tgt_perm, int64_t n_tgt, const CsfFieldParams* fp, double* frep,
+                              int accumulate, void* ws, size_t wsb, unsigned long long* stats, csf_stream_t st) {
+    return pair_tiled<double>(sorted, tiles, n_src, tgt, tgt_perm, n_tgt, fp, frep, accumulate, ws, wsb, stats,
+                              (cudaStream_t)st);
 }
 
 }  // extern "C"

@@ -376,6 +376,11 @@ class Engine:
                     tiles=torch.zeros((n_tiles, tile_elems), dtype=self.payload.dtype, device=self.device),
                     keys=torch.zeros(c, dtype=torch.int64, device=self.device), perm=None))
                 wsb = max(wsb, int(self.lib.csf_pair_tiled_workspace_bytes(c, self.n_agents, eb)))
+            # visiting order of the local targets (Morton order too: compact target blocks)
+            self._tgt_keys = torch.zeros(self.n_agents, dtype=torch.int64, device=self.device)
+            self._tgt_perm = None
+            self._single_class = (len(self.classes) == 1 and self.classes[0][0] == self.global_offset
+                                  and self.classes[0][1] == self.n_agents)
             self._morton = (-float(extent if extent is not None else 2.0 ** 30 * self.q_scale),
                             2.0 * float(extent if extent is not None else 2.0 ** 30 * self.q_scale) / 65536.0)
         self.ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=self.device)
@@ -425,9 +430,16 @@ class Engine:
             else:
                 resort = self.tiled and (self._pair_calls % max(self.resort_every, 1) == 0)
                 self._pair_calls += 1
+                tgt = C.c_void_p(self.payload.data_ptr() + self.global_offset * self.elem_bytes)
+                if resort or (self.tiled and self._tgt_perm is None):
+                    if not self._single_class:   # (one class covering exactly the targets: reuse the source order)
+                        _lib.check(self._fn("csf_morton_keys")(tgt, self.n_agents, self._morton[0], self._morton[0],
+                                                               self._morton[1], _ptr(self._tgt_keys), st),
+                                   "csf_morton_keys")
+                        self._tgt_perm = torch.argsort(self._tgt_keys)
+                        self.gpu_launches += 1
                 for ci, (s, c, _, fp) in enumerate(self.classes):
                     src = C.c_void_p(self.payload.data_ptr() + s * self.elem_bytes)
-                    tgt = C.c_void_p(self.payload.data_ptr() + self.global_offset * self.elem_bytes)
                     if fp.field_kind == 1:
                         g, ecc = self._ecc[s]
                         _lib.check(self._fn("csf_bicycle_eccentricity")(_ptr(g.v), g.n, fp.v_max, _ptr(ecc), st),
@@ -446,13 +458,15 @@ class Engine:
                                        "csf_morton_keys")
                             tl["perm"] = torch.argsort(tl["keys"])
                             self.gpu_launches += 1
+                            if self._single_class:
+                                self._tgt_perm = tl["perm"]
                         _lib.check(self._fn("csf_tile_sources")(src, c, _ptr(tl["perm"]), _ptr(tl["sorted"]),
                                                                 _ptr(tl["tiles"]), st), "csf_tile_sources")
                         _lib.check(self._fn("csf_pair_forces_tiled")(
-                            _ptr(tl["sorted"]), _ptr(tl["tiles"]), c, tgt, self.n_agents, C.byref(fp),
-                            _ptr(self.frep), 1 if ci > 0 else 0, _ptr(self.ws), self.ws.numel(),
+                            _ptr(tl["sorted"]), _ptr(tl["tiles"]), c, tgt, _ptr(self._tgt_perm), self.n_agents,
+                            C.byref(fp), _ptr(self.frep), 1 if ci > 0 else 0, _ptr(self.ws), self.ws.numel(),
                             _ptr(self.pair_stats), st), "csf_pair_forces_tiled")
-                        self.gpu_launches += 3
+                        self.gpu_launches += 5   # tile build, chunk bounds, block bounds, pair, reduce
                         continue
                     _lib.check(self._fn("csf_pair_forces")(src, c, tgt, self.n_agents,
                                                            C.byref(fp), _ptr(self.frep), 1 if ci > 0 else 0,

@@ -58,6 +58,7 @@ typedef struct CsfFieldParams {
     int32_t p2r;     /* priority_rule == "p2r" (intersection.py:738-741) */
     int32_t field_kind; /* 0: TwoDBicycle field (vehicle.py:1560-1648); 1: Bicycle v0.1 (:1107-1147) */
     double p_0, p_decay, v_max; /* field_kind 1 only (BicycleParameters p_0, p_decay, v_max_riding[1]) */
+    double cutoff_log2; /* tiled f32 kernel: contributions below 2^-cutoff_log2 * f_0 may be dropped (0 = default 40) */
 } CsfFieldParams;
 
 /* Crowd-wide parameters of the per-agent kernels (all models share one struct). */
@@ -169,21 +170,26 @@ int csf_pair_forces_bicycle_f64(const void* src_xycs, const void* src_e, int64_t
 int csf_bicycle_eccentricity_f32(const float* v, int64_t n, double v_max, float* e, csf_stream_t stream);
 int csf_bicycle_eccentricity_f64(const double* v, int64_t n, double v_max, double* e, csf_stream_t stream);
 
-/* ---- K1, tiled variant with exact field-of-view culling ----------------------------------
- * Same result as csf_pair_forces_* up to the order of summation (the f32 build additionally
- * drops tiles whose every contribution is below 2^-40 f_0).  Sources are passed as a spatially
- * sorted, tile-padded copy with one bounding record per tile of 64:
+/* ---- K1, tiled variant with hierarchical culling (production path for large crowds) ------
+ * Same result as csf_pair_forces_* up to the order of summation; the f32 build additionally
+ * drops sources further than csf_field_cutoff_distance(fp) from the target, where every
+ * contribution is below 2^-cutoff_log2 f_0 (|F| = f_0 exp(-rho q/sigma), vehicle.py:1613-1648);
+ * the f64 build never truncates.  Sources are passed as a spatially sorted, tile-padded copy
+ * with one bounding record per tile of 64 and per chunk of 16 tiles:
  *   csf_morton_keys_*   : int64 Morton key per payload element (x0,y0,cell only used by _f64);
  *                         the caller sorts the keys (any sort) to obtain `perm`
- *   csf_tile_sources_*  : sorted[i] = xycs[perm[i]] (perm NULL = identity), padded to
- *                         csf_tiled_padded_sources(n) elements; tiles: csf_tiled_num_tiles(n)
- *                         records of csf_tiled_tile_bytes(elem) bytes
- *   csf_pair_forces_tiled_* : the pair force; `stats` (may be NULL) accumulates the number of
- *                         pair evaluations actually executed (for the roofline). */
+ *   csf_tile_sources_*  : sorted <- xycs[perm[.]] (perm NULL = identity) in the kernel's tile
+ *                         layout, csf_tiled_padded_sources(n) elements; tiles:
+ *                         csf_tiled_num_tiles(n) records of csf_tiled_tile_bytes(elem) bytes
+ *   csf_pair_forces_tiled_* : the pair force.  `tgt_perm` (may be NULL) = visiting order of the
+ *                         targets (a spatial order makes the block-level culling effective;
+ *                         frep is always written in target order); `stats` (may be NULL)
+ *                         accumulates the number of pair evaluations actually executed. */
 int64_t csf_tiled_padded_sources(int64_t n_src);
 int64_t csf_tiled_num_tiles(int64_t n_src);
 int csf_tiled_tile_bytes(int elem_bytes);
 size_t csf_pair_tiled_workspace_bytes(int64_t n_src, int64_t n_tgt, int elem_bytes);
+double csf_field_cutoff_distance(const CsfFieldParams* fp); /* metres; INFINITY if unbounded */
 int csf_morton_keys_f32(const void* xycs, int64_t n, double x0, double y0, double cell, int64_t* keys,
                         csf_stream_t stream);
 int csf_morton_keys_f64(const void* xycs, int64_t n, double x0, double y0, double cell, int64_t* keys,
@@ -193,13 +199,13 @@ int csf_tile_sources_f32(const void* xycs, int64_t n, const int64_t* perm, void*
 int csf_tile_sources_f64(const void* xycs, int64_t n, const int64_t* perm, void* sorted, void* tiles,
                          csf_stream_t stream);
 int csf_pair_forces_tiled_f32(const void* sorted, const void* tiles, int64_t n_src, const void* tgt_xycs,
-                              int64_t n_tgt, const CsfFieldParams* fp, float* frep_xy, int accumulate,
-                              void* workspace, size_t workspace_bytes, unsigned long long* stats,
-                              csf_stream_t stream);
+                              const int64_t* tgt_perm, int64_t n_tgt, const CsfFieldParams* fp,
+                              float* frep_xy, int accumulate, void* workspace, size_t workspace_bytes,
+                              unsigned long long* stats, csf_stream_t stream);
 int csf_pair_forces_tiled_f64(const void* sorted, const void* tiles, int64_t n_src, const void* tgt_xycs,
-                              int64_t n_tgt, const CsfFieldParams* fp, double* frep_xy, int accumulate,
-                              void* workspace, size_t workspace_bytes, unsigned long long* stats,
-                              csf_stream_t stream);
+                              const int64_t* tgt_perm, int64_t n_tgt, const CsfFieldParams* fp,
+                              double* frep_xy, int accumulate, void* workspace, size_t workspace_bytes,
+                              unsigned long long* stats, csf_stream_t stream);
 
 /* ---- road-edge force ------------------------------------------------------------
  * Replaces RoadEdge.calcRepulsiveForce summed over edges (intersection.py:226-242,

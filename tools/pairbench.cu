@@ -18,14 +18,15 @@ int main(int argc, char** argv) {
     Xycs<float>* d; float* f; void* ws;
     cudaMalloc(&d, n * sizeof(Xycs<float>)); cudaMalloc(&f, n * 8);
     cudaMemcpy(d, h.data(), n * sizeof(Xycs<float>), cudaMemcpyHostToDevice);
-    CsfFieldParams fp = {7.0, 0.995, 0.7, 0.5, 5.0, 0.3, 4.9, 2.0943951023931953, q, 0, 0, 0, 0, 0};
+    CsfFieldParams fp = {7.0, 0.995, 0.7, 0.5, 5.0, 0.3, 4.9, 2.0943951023931953, q, 0, 0, 0, 0, 0, 0};
     size_t wsb = csf_pair_workspace_bytes(n, n, 4);
     cudaMalloc(&ws, wsb);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 3; ++i) csf_pair_forces_f32(d, n, d, n, &fp, f, 0, ws, wsb, 0);
+    const bool nodense = argc > 4;   // 4th argument: skip the dense kernel (large n)
+    for (int i = 0; i < (nodense ? 0 : 3); ++i) csf_pair_forces_f32(d, n, d, n, &fp, f, 0, ws, wsb, 0);
     cudaDeviceSynchronize();
     float best = 1e30f, tot = 0;
-    for (int i = 0; i < reps; ++i) {
+    for (int i = 0; i < (nodense ? 0 : reps); ++i) {
         cudaEventRecord(e0); csf_pair_forces_f32(d, n, d, n, &fp, f, 0, ws, wsb, 0); cudaEventRecord(e1);
         cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); best = fminf(best, ms); tot += ms;
     }
@@ -43,14 +44,14 @@ int main(int argc, char** argv) {
         size_t wsb2 = csf_pair_tiled_workspace_bytes(n, n, 4); cudaMalloc(&ws2, wsb2);
         float* f2; cudaMalloc(&f2, n * 8);
         csf_tile_sources_f32(d, n, dperm, sorted, tiles, 0);
-        csf_pair_forces_tiled_f32(sorted, tiles, n, d, n, &fp, f2, 0, ws2, wsb2, stats, 0);
+        csf_pair_forces_tiled_f32(sorted, tiles, n, d, dperm, n, &fp, f2, 0, ws2, wsb2, stats, 0);
         cudaDeviceSynchronize();
         unsigned long long ne = 0; cudaMemcpy(&ne, stats, 8, cudaMemcpyDeviceToHost);
         float bt = 1e30f, tt = 0, ttile = 0;
         for (int i = 0; i < reps; ++i) {
             cudaEventRecord(e0); csf_tile_sources_f32(d, n, dperm, sorted, tiles, 0); cudaEventRecord(e1);
             cudaEventSynchronize(e1); float ms0; cudaEventElapsedTime(&ms0, e0, e1); ttile += ms0;
-            cudaEventRecord(e0); csf_pair_forces_tiled_f32(sorted, tiles, n, d, n, &fp, f2, 0, ws2, wsb2, nullptr, 0);
+            cudaEventRecord(e0); csf_pair_forces_tiled_f32(sorted, tiles, n, d, dperm, n, &fp, f2, 0, ws2, wsb2, nullptr, 0);
             cudaEventRecord(e1); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1);
             bt = fminf(bt, ms); tt += ms;
         }
