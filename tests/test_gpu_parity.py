@@ -226,3 +226,60 @@ def test_batched_independent_scenarios(model):
         worst = max(worst, np.abs(got[k * per:(k + 1) * per] - W.groups[0].s).max())
     report(test="batched_scenarios", model=model, scenarios=n_scen, per=per, steps=steps, max_abs=float(worst))
     assert worst < 1e-9
+
+
+@pytest.mark.parametrize("n,n_sample", [(65536, 160), (1048576, 40)])
+def test_pair_forces_full_size(n, n_sample):
+    """BASELINE.json sizes (headline N = 65,536 and config 5, N = 1,048,576): the f32 production
+    kernel (hierarchical culling, far-field cut-off, packed FP32x2 evaluation) against the float64
+    oracle on a seeded sample of targets, each against ALL N sources; at 65,536 also the whole force
+    array against the dense kernel (every pair evaluated), and the cut-off's premise -- nothing
+    beyond csf_field_cutoff_distance contributes more than 2^-40 f_0 -- against the oracle."""
+    import ctypes as C
+    from cyclistsocialforce_b200 import _lib, parameters as P
+    from cyclistsocialforce_b200.engine import AgentGroup, Engine
+    from cyclistsocialforce_b200.synthetic import queues_with_start
+    s0, q = co.synthetic_crowd(n, seed=1, spacing=4.0)
+    extent = 2.0 * float(max(np.abs(s0[:, :2]).max(), np.abs(q[..., :2]).max())) + 1000.0
+
+    def forces(mode):
+        g = AgentGroup("twod", s0, P.InvPendulumBicycleParameters(), destqueues=list(queues_with_start(s0, q)),
+                       dtype=torch.float32)
+        eng = Engine([g], dtype=torch.float32, extent=extent, pair_mode=mode, count_pairs=(mode == "tiled"))
+        eng._pair_and_road()
+        torch.cuda.synchronize()
+        frac = float(eng.pair_stats.item()) / (float(n) * n) if mode == "tiled" else 1.0
+        return eng.frep.cpu().numpy().astype(float), frac, eng
+
+    got, frac, eng = forces("tiled")
+    assert np.isfinite(got).all()
+    rng = np.random.default_rng(11)
+    tj = np.sort(rng.choice(n, n_sample, replace=False))
+    p = co.default_params("twod")
+    fpar = co.field_params_array([p])[0]
+    ref, margin = co.pair_forces(s0[:, 0], s0[:, 1], s0[:, 2], fpar, tgt=tj, chunk=8, return_margin=True)
+    # a source within 1e-5 rad of a target's field-of-view boundary may flip between fp32 and fp64
+    # (with 65,536+ sources most targets have one somewhere, but it only matters if it is close by):
+    # every target without such a source must pass; of the others at most 2 % may be off.
+    ok = margin > 1e-5
+    err = _vec_rel(got[tj], ref, 1e-3)
+    dcut = float(_lib.load().csf_field_cutoff_distance(C.byref(eng.classes[0][3])))
+    report(test="pair_forces_full_size", n=n, sampled_targets=int(len(tj)), max_rel_clear_margin=float(err[ok].max()) if ok.any() else None, max_rel=float(err.max()),
+           med_rel=float(np.median(err)), n_over_tol=int((err >= F32_TOL).sum()), evaluated_pair_fraction=frac,
+           cutoff_m=dcut)
+    if ok.any():
+        assert err[ok].max() < F32_TOL
+    assert (err >= F32_TOL).mean() <= 0.02
+    assert frac < (0.06 if n == 65536 else 0.005)
+    # premise of the cut-off: with only the sources inside d_cut the oracle's sum moves by < N 2^-40 f_0
+    assert 100.0 < dcut < 200.0
+    j = int(tj[0])
+    near = np.hypot(s0[:, 0] - s0[j, 0], s0[:, 1] - s0[j, 1]) <= dcut
+    idx = np.flatnonzero(near)
+    sub = co.pair_forces(s0[idx, 0], s0[idx, 1], s0[idx, 2], fpar, tgt=[int(np.searchsorted(idx, j))], chunk=8)
+    assert np.abs(sub[0] - ref[0]).max() <= n * 2.0 ** -40 * p.f_0
+    if n == 65536:
+        dense, _, _ = forces("dense")
+        d = _vec_rel(got, dense, 1e-3)
+        report(test="tiled_vs_dense_full_size", n=n, max_rel=float(d.max()))
+        assert d.max() < 2e-5
