@@ -323,10 +323,11 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
     constexpr size_t kStageBytes = (size_t)kCS * sizeof(Xycs<T>) + (size_t)kCT * sizeof(Tile<T>);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * kStageBytes);
     uint64_t* empty = full + kStages;
-    int4* hdr = reinterpret_cast<int4*>(empty + kStages);                           // {item, chunk, list length, next}
+    uint64_t* cbar = empty + kStages;                                               // consumers' own barrier
+    int4* hdr = reinterpret_cast<int4*>(cbar + 2);                                  // {item, chunk, list length, next}
     Xycs<T>* btgt = reinterpret_cast<Xycs<T>*>(hdr + kStages);                      // [kTB] targets of the block
-    T* bacc = reinterpret_cast<T*>(btgt + kTB);                                     // [kTB][2] their sums
-    uint32_t* wlist = reinterpret_cast<uint32_t*>(bacc + kTB * 2);                  // [kStages][kTB] (q << 16) | tile mask
+    T* bacc = reinterpret_cast<T*>(btgt + kTB);                                     // [2][kTB][2] sums (chunk parity)
+    uint32_t* wlist = reinterpret_cast<uint32_t*>(bacc + 2 * kTB * 2);              // [kStages][kTB] (q << 16) | tile mask
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -334,6 +335,7 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kTW);
         }
+        mbar_init(cbar, kTW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -402,19 +404,105 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
     // ===== consumer warps =====
     // Per chunk: (1) cull -- every warp tests its own tpw targets against the chunk's 16 tiles, two
     // targets per pass (lanes 0-15 / 16-31), and appends the non-empty (target, tile mask) entries to the
-    // stage's work list; (2) barrier among the consumers; (3) evaluate -- warps take entries from the
-    // list one at a time (shared counter), so a chunk's work is balanced over the CTA whatever the
-    // targets' headings.  The barrier also orders the updates of bacc[] chunk by chunk: one warp per
-    // (target, chunk), chunks in sequence -> deterministic sums without atomics on floats.
-    uint32_t it = 0;
+    // stage's work list; (2) evaluate -- warps take entries from the list one at a time (shared
+    // counter), so a chunk's work is balanced over the CTA whatever the targets' headings.
+    // The two phases are software pipelined: a warp culls chunk k+1 and *arrives* on the consumers'
+    // barrier, evaluates chunk k, and only then *waits* for the barrier -- by then every warp has long
+    // finished its cull, so nobody idles at the phase boundary.  Chunks k and k+1 can therefore be in
+    // evaluation at the same time (never k and k+2): their sums go to two accumulator sets selected by
+    // the chunk's parity.  One warp per (target, chunk), chunks of one parity in sequence ->
+    // deterministic sums without atomics on floats.
+    uint32_t it = 0, cpar = 0;
     unsigned long long n_eval = 0;
     int cur = -1, cg = 0, nq = 0;
     const int q0 = warp * tpw;           // this warp's targets in the block: [q0, q0 + nq)
     long long myj = -1;
+    auto consumers_arrive = [&]() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(cbar);
+    };
+    auto consumers_wait = [&]() {
+        mbar_wait(cbar, cpar);
+        cpar ^= 1;
+    };
+    auto cull = [&](int stage, int chunk) {
+        const int nt = (int)min((int64_t)kCT, n_tiles - (int64_t)chunk * kCT);
+        const unsigned char* base = smem_raw + stage * kStageBytes;
+        const Tile<T>* trec = reinterpret_cast<const Tile<T>*>(base + (size_t)kCS * sizeof(Xycs<T>));
+        uint32_t* list = wlist + stage * kTB;
+        int* lcount = &hdr[stage].z;
+        const int tl = lane & (kCT - 1), half = lane >> 4;
+        Tile<T> mytile;
+        if (tl < nt) mytile = trec[tl];
+        for (int i0 = 0; i0 < nq; i0 += 2) {          // warp-uniform trip count (ballot inside)
+            const int i = i0 + half;
+            const bool valid = (i < nq) && (tl < nt);
+            const Xycs<T> te = btgt[q0 + (i < nq ? i : 0)];
+            const Tgt<T> tg = *reinterpret_cast<const Tgt<T>*>(&te);
+            const bool v = valid && tile_visible<T, P2R>(mytile, tg, cc);
+            const uint32_t m2 = __ballot_sync(0xffffffffu, v);
+            const uint32_t m = half ? (m2 >> 16) : (m2 & 0xffffu);
+            if (tl == 0 && m) {
+                list[atomicAdd(lcount, 1)] = ((uint32_t)(q0 + i) << 16) | m;
+                if (stats) n_eval += (unsigned long long)__popc(m) * kTileS;
+            }
+        }
+    };
+    auto evaluate = [&](int stage, int par) {
+        const unsigned char* base = smem_raw + stage * kStageBytes;
+        const uint32_t* list = wlist + stage * kTB;
+        const int n_list = hdr[stage].z;
+        int* lnext = &hdr[stage].w;
+        T* acc = bacc + par * kTB * 2;
+        for (;;) {
+            int e = 0;
+            if (lane == 0) e = atomicAdd(lnext, 1);
+            e = __shfl_sync(0xffffffffu, e, 0);
+            if (e >= n_list) break;
+            const uint32_t ent = list[e];
+            const int q = (int)(ent >> 16);
+            uint32_t mask = ent & 0xffffu;
+            const Xycs<T> te = btgt[q];
+            const Tgt<T> tg = *reinterpret_cast<const Tgt<T>*>(&te);
+            typename TileAccSel<T, P2R>::type acc0, acc1;
+            // two surviving tiles per iteration: four independent pair evaluations in flight
+            while (mask & (mask - 1)) {
+                const int t0 = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int t1 = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const unsigned char* p0 = base + (size_t)t0 * TileBytes<T>::v;
+                const unsigned char* p1 = base + (size_t)t1 * TileBytes<T>::v;
+                const SrcA<T> A0 = reinterpret_cast<const SrcA<T>*>(p0)[lane];
+                const SrcB<T> B0 = reinterpret_cast<const SrcB<T>*>(p0 + 32 * sizeof(SrcA<T>))[lane];
+                const SrcA<T> A1 = reinterpret_cast<const SrcA<T>*>(p1)[lane];
+                const SrcB<T> B1 = reinterpret_cast<const SrcB<T>*>(p1 + 32 * sizeof(SrcA<T>))[lane];
+                acc0.eval(A0, B0, tg, k);
+                acc1.eval(A1, B1, tg, k);
+            }
+            if (mask) {
+                const int t0 = __ffs(mask) - 1;
+                const unsigned char* p0 = base + (size_t)t0 * TileBytes<T>::v;
+                const SrcA<T> A0 = reinterpret_cast<const SrcA<T>*>(p0)[lane];
+                const SrcB<T> B0 = reinterpret_cast<const SrcB<T>*>(p0 + 32 * sizeof(SrcA<T>))[lane];
+                acc0.eval(A0, B0, tg, k);
+            }
+            acc0.merge(acc1);
+            T ax, ay;
+            acc0.total(ax, ay);
+            // both sums in one butterfly: lanes 0-15 reduce x, lanes 16-31 reduce y
+            const bool upper = lane >= 16;
+            T mine = upper ? ay : ax;
+            const T other = upper ? ax : ay;
+            mine += __shfl_xor_sync(0xffffffffu, other, 16);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+            if ((lane & 15) == 0) acc[q * 2 + (lane >> 4)] += mine;
+        }
+    };
     for (;;) {
         const int stage = it % kStages;
-        const uint32_t phase = (it / kStages) & 1;
-        mbar_wait(&full[stage], phase);
+        mbar_wait(&full[stage], (it / kStages) & 1);
         const int item = hdr[stage].x, chunk = hdr[stage].y;
         if (chunk == -2) break;
         if (item != cur) {
@@ -429,92 +517,47 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
             if (lane < nq) {
                 myj = tgt_perm ? tgt_perm[t_first + lane] : (t_first + lane);
                 btgt[q0 + lane] = tgt[myj];
-                bacc[(q0 + lane) * 2] = (T)0;
-                bacc[(q0 + lane) * 2 + 1] = (T)0;
+            }
+            if (lane < 2 * nq) {
+                bacc[q0 * 2 + lane] = (T)0;
+                bacc[kTB * 2 + q0 * 2 + lane] = (T)0;
             }
             __syncwarp();
         }
         if (chunk == -1) {
-            // close the item: every warp has finished adding to bacc[]; write this warp's targets
-            consumer_barrier();
+            // close the item: once every warp has finished adding, write this warp's targets
+            consumers_arrive();
+            consumers_wait();
             const long long jj = __shfl_sync(0xffffffffu, myj, (lane >> 1) & (kMaxTPW - 1));
-            if ((lane >> 1) < nq) partial[((size_t)cg * n_tgt + (size_t)jj) * 2 + (lane & 1)] = bacc[q0 * 2 + lane];
-        } else {
-            const int nt = (int)min((int64_t)kCT, n_tiles - (int64_t)chunk * kCT);
-            const unsigned char* base = smem_raw + stage * kStageBytes;
-            const Tile<T>* trec = reinterpret_cast<const Tile<T>*>(base + (size_t)kCS * sizeof(Xycs<T>));
-            uint32_t* list = wlist + stage * kTB;
-            int* lcount = &hdr[stage].z;
-            int* lnext = &hdr[stage].w;
-            // (1) cull
-            {
-                const int tl = lane & (kCT - 1), half = lane >> 4;
-                Tile<T> mytile;
-                if (tl < nt) mytile = trec[tl];
-                for (int i0 = 0; i0 < nq; i0 += 2) {          // warp-uniform trip count (ballot inside)
-                    const int i = i0 + half;
-                    const bool valid = (i < nq) && (tl < nt);
-                    const Xycs<T> te = btgt[q0 + (i < nq ? i : 0)];
-                    const Tgt<T> tg = *reinterpret_cast<const Tgt<T>*>(&te);
-                    const bool v = valid && tile_visible<T, P2R>(mytile, tg, cc);
-                    const uint32_t m2 = __ballot_sync(0xffffffffu, v);
-                    const uint32_t m = half ? (m2 >> 16) : (m2 & 0xffffu);
-                    if (tl == 0 && m) {
-                        list[atomicAdd(lcount, 1)] = ((uint32_t)(q0 + i) << 16) | m;
-                        if (stats) n_eval += (unsigned long long)__popc(m) * kTileS;
-                    }
-                }
-            }
-            consumer_barrier();
-            // (2) evaluate
-            const int n_list = *lcount;
-            for (;;) {
-                int e = 0;
-                if (lane == 0) e = atomicAdd(lnext, 1);
-                e = __shfl_sync(0xffffffffu, e, 0);
-                if (e >= n_list) break;
-                const uint32_t ent = list[e];
-                const int q = (int)(ent >> 16);
-                uint32_t mask = ent & 0xffffu;
-                const Xycs<T> te = btgt[q];
-                const Tgt<T> tg = *reinterpret_cast<const Tgt<T>*>(&te);
-                typename TileAccSel<T, P2R>::type acc0, acc1;
-                // two surviving tiles per iteration: four independent pair evaluations in flight
-                while (mask & (mask - 1)) {
-                    const int t0 = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const int t1 = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const unsigned char* p0 = base + (size_t)t0 * TileBytes<T>::v;
-                    const unsigned char* p1 = base + (size_t)t1 * TileBytes<T>::v;
-                    const SrcA<T> A0 = reinterpret_cast<const SrcA<T>*>(p0)[lane];
-                    const SrcB<T> B0 = reinterpret_cast<const SrcB<T>*>(p0 + 32 * sizeof(SrcA<T>))[lane];
-                    const SrcA<T> A1 = reinterpret_cast<const SrcA<T>*>(p1)[lane];
-                    const SrcB<T> B1 = reinterpret_cast<const SrcB<T>*>(p1 + 32 * sizeof(SrcA<T>))[lane];
-                    acc0.eval(A0, B0, tg, k);
-                    acc1.eval(A1, B1, tg, k);
-                }
-                if (mask) {
-                    const int t0 = __ffs(mask) - 1;
-                    const unsigned char* p0 = base + (size_t)t0 * TileBytes<T>::v;
-                    const SrcA<T> A0 = reinterpret_cast<const SrcA<T>*>(p0)[lane];
-                    const SrcB<T> B0 = reinterpret_cast<const SrcB<T>*>(p0 + 32 * sizeof(SrcA<T>))[lane];
-                    acc0.eval(A0, B0, tg, k);
-                }
-                acc0.merge(acc1);
-                T ax, ay;
-                acc0.total(ax, ay);
-                ax = warp_sum(ax);
-                ay = warp_sum(ay);
-                if (lane == 0) {
-                    bacc[q * 2] += ax;
-                    bacc[q * 2 + 1] += ay;
-                }
-            }
+            if ((lane >> 1) < nq)
+                partial[((size_t)cg * n_tgt + (size_t)jj) * 2 + (lane & 1)] =
+                    bacc[q0 * 2 + lane] + bacc[kTB * 2 + q0 * 2 + lane];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            ++it;
+            continue;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
-        ++it;
+        // first chunk of the item: cull, then a full barrier
+        cull(stage, chunk);
+        consumers_arrive();
+        consumers_wait();
+        for (int par = 0;; par ^= 1) {
+            // the work list of stage (it % kStages) is complete; look at the next stream element
+            const int s0 = it % kStages, s1 = (it + 1) % kStages;
+            mbar_wait(&full[s1], ((it + 1) / kStages) & 1);
+            const int c1 = hdr[s1].y;
+            const bool more = c1 >= 0;               // another chunk of this item (a new item starts after -1)
+            if (more) {
+                cull(s1, c1);
+                consumers_arrive();
+            }
+            evaluate(s0, par);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s0]);
+            ++it;
+            if (!more) break;
+            consumers_wait();
+        }
     }
     if (stats && n_eval) atomicAdd(stats, n_eval);
 }
@@ -533,8 +576,8 @@ __global__ void reduce_groups_kernel(const T* __restrict__ partial, int n_groups
 template <typename T> size_t tiled_smem_bytes() {
     constexpr int kStages = Stages<T>::n;
     return kStages * ((size_t)kCS * sizeof(Xycs<T>) + (size_t)kCT * sizeof(Tile<T>)) +
-           2 * kStages * sizeof(uint64_t) + kStages * sizeof(int4) + (size_t)kTB * sizeof(Xycs<T>) +
-           (size_t)kTB * 2 * sizeof(T) + (size_t)kStages * kTB * sizeof(uint32_t);
+           (2 * kStages + 2) * sizeof(uint64_t) + kStages * sizeof(int4) + (size_t)kTB * sizeof(Xycs<T>) +
+           (size_t)2 * kTB * 2 * sizeof(T) + (size_t)kStages * kTB * sizeof(uint32_t);
 }
 
 int g_tiled_ctas[2] = {0, 0};
