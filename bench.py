@@ -34,8 +34,8 @@ WORKLOAD = f"{N_AGENTS}-cyclist TwoDBicycle open-plane crowd (SURVEY 8d recipe, 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -125,7 +125,7 @@ def main():
     from cyclistsocialforce_b200 import _lib, parameters as P
     from cyclistsocialforce_b200.distributed import PayloadExchange, shard_bounds
     from cyclistsocialforce_b200.engine import AgentGroup, Engine
-    from cyclistsocialforce_b200.synthetic import queues_with_start, synthetic_crowd
+    from cyclistsocialforce_b200.synthetic import queues_with_start, spatial_order, synthetic_crowd
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
@@ -137,6 +137,10 @@ def main():
 
     # ---- the crowd, sharded by agent range -------------------------------------------------
     s0, q = synthetic_crowd(N_AGENTS, seed=SEED)
+    # spatial domain decomposition: agents are numbered along a Hilbert curve through their initial
+    # positions, so that the contiguous agent range of a rank is a compact region of the plane
+    order = spatial_order(s0[:, 0], s0[:, 1])
+    s0, q = s0[order], q[order]
     queues = queues_with_start(s0, q)
     # CSF_BENCH_EMULATE_WORLD=8: time ONE rank's shard of an 8-way split on a single GPU (tuning aid;
     # the payload of the other shards stays frozen, no exchange) -- never used for reported numbers
@@ -153,8 +157,9 @@ def main():
         frozen_payload = e_full.payload.clone()
         del e_full, full
     pair_mode = os.environ.get("CSF_PAIR_MODE", "tiled")
+    use_graph = os.environ.get("CSF_BENCH_GRAPH", "1") != "0"
     eng = Engine([group], dtype=torch.float32, device=dev, extent=extent, n_global=N_AGENTS, global_offset=lo,
-                 exchange=exch, pair_mode=pair_mode, count_pairs=True)
+                 exchange=exch, pair_mode=pair_mode, count_pairs=True, graph=False)
     exch(eng.payload)
     if emu:
         eng.payload.copy_(frozen_payload)
@@ -202,34 +207,51 @@ def main():
     eng.pair_stats_ptr_backup = eng.pair_stats
     eng.pair_stats = None                      # no counting inside the timed region
 
+    eng.use_graph = use_graph                  # step() = CUDA-graph replay of the step's kernels
+    for _ in range(2):
+        eng.step()                             # (captures the graph)
+    sync()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
     launches0 = eng.gpu_launches
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     sync()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)                      # L2 flush, outside the per-step events
-        a, b, c = ev[k]
+        a, c = ev[k]
         a.record()
-        have_rep = eng._pair_and_road()            # K1 (+ partial-sum reduce)
-        b.record()
-        eng._agent_step(have_rep)                  # K2+K3 fused, + payload all-gather
+        eng.step()                                 # K1 (+ tile build, partial-sum reduce), K2+K3 fused, all-gather
         c.record()
     sync()
     barrier()
     launches = eng.gpu_launches - launches0
     clocks = sampler.stop()
-    step_ms = [a.elapsed_time(c) for a, b, c in ev]
-    pair_ms = [a.elapsed_time(b) for a, b, c in ev]
-    agent_ms = [b.elapsed_time(c) for a, b, c in ev]
+    step_ms = [a.elapsed_time(c) for a, c in ev]
     total_ms = sum(step_ms)
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
+    # per-kernel durations: events cannot be placed inside a graph replay, so the split of a step
+    # into K1 / K2+K3 is taken in a second pass of the same K steps launched kernel by kernel
+    eng.use_graph = False
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+            torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        a, b, c = ev2[k]
+        a.record()
+        have_rep = eng._pair_and_road()
+        b.record()
+        eng._agent_step(have_rep)
+        c.record()
+    sync()
+    barrier()
+    pair_ms = [a.elapsed_time(b) for a, b, c in ev2]
+    agent_ms = [b.elapsed_time(c) for a, b, c in ev2]
+    ungraphed_ms = statistics.mean(a.elapsed_time(c) for a, b, c in ev2)
     eng.check_status()
     value = N_AGENTS * args.steps / (total_ms * 1e-3)
     ms_per_step = total_ms / args.steps
@@ -240,6 +262,7 @@ def main():
     host_force = torch.empty((n_local, 2), dtype=torch.float32).pin_memory()
     h2d = sum(t.numel() * t.element_size() for t in host_in.values())
     d2h = h2d + host_force.numel() * host_force.element_size()
+    eng.use_graph = use_graph
     for _ in range(2):
         eng.step_host(host_in, host_out, host_force)
     barrier()
@@ -282,7 +305,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_agents": N_AGENTS, "parallelism": f"agent-range x{world}" + (f" (EMULATED 1/{emu} shard, not a result)" if emu else ""), "pair_kernel": "tiled+culled" if eng.tiled else "dense",
+            "config": {"workload": WORKLOAD, "n_agents": N_AGENTS, "step": "CUDA-graph replay" if use_graph else "kernel-by-kernel launches", "partition": "contiguous agent ranges of a Hilbert order of the initial positions (spatial decomposition)", "parallelism": f"agent-range x{world}" + (f" (EMULATED 1/{emu} shard, not a result)" if emu else ""), "pair_kernel": "tiled+culled" if eng.tiled else "dense",
                        "l2": "flushed between timed steps (256 MiB write)", "q_scale_m": eng.q_scale,
                        "pair_interactions_per_s": float(N_AGENTS) * (N_AGENTS - 1) * args.steps / (total_ms * 1e-3)},
             "clocks": clocks,
@@ -299,7 +322,8 @@ def main():
                          "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops,
                          "traffic": traffic, "peak_source": "csf_ffma_peak micro-benchmark in this run",
                          "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs_per_launch,
-                         "kernel_ms": pair_s * 1e3, "share_of_step": pair_s * 1e3 / statistics.mean(step_ms)},
+                         "kernel_ms": pair_s * 1e3, "share_of_step": pair_s * 1e3 / ungraphed_ms,
+                         "timing": "second pass of the same K steps, launched kernel by kernel (ms_per_step of that pass: %.4f)" % ungraphed_ms},
             "roofline_agent_kernel": {"bound": "hbm", "kernel": "agent_kernel<float,TWOD,STEP>",
                                       "achieved": n_local * BYTES_PER_AGENT_STEP / agent_s / 1e9, "peak": hbm_peak,
                                       "unit": "GB/s", "frac": n_local * BYTES_PER_AGENT_STEP / agent_s / 1e9 / hbm_peak,

@@ -285,11 +285,13 @@ class Engine:
     def __init__(self, groups, obstacles=None, priority_rule="unregulated", road_edges=(),
                  dtype=torch.float32, device="cuda", q_scale=None, extent=None, scenario_size=None,
                  n_global=None, global_offset=0, exchange=None, pair_mode="auto", resort_every=32,
-                 count_pairs=False):
+                 count_pairs=False, graph=False):
         """``n_global`` / ``global_offset`` / ``exchange``: agent-range sharding of one crowd over
         several GPUs -- this engine owns agents [global_offset, global_offset + n) of an
         ``n_global``-agent crowd with homogeneous field parameters; ``exchange(payload)`` is
-        called after every step to all-gather the pair payload (see distributed.py)."""
+        called after every step to all-gather the pair payload (see distributed.py).
+        ``graph=True``: ``step()`` replays a CUDA graph of the step's kernel sequence (captured at the
+        first call; the periodic re-sort of the spatial order and the exchange stay outside it)."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.CsfError("no CUDA device: the csf_b200 engine has no CPU fallback")
@@ -307,6 +309,8 @@ class Engine:
         assert pair_mode in ("auto", "dense", "tiled")
         self.pair_mode = pair_mode
         self.resort_every = int(resort_every)
+        self.use_graph = bool(graph)
+        self._graph = None
         self.global_offset = int(global_offset)
         off = self.global_offset
         for g in self.groups + self.obstacles:
@@ -374,11 +378,13 @@ class Engine:
                 self._tiles.append(dict(
                     sorted=torch.zeros((n_pad, 4), dtype=self.payload.dtype, device=self.device),
                     tiles=torch.zeros((n_tiles, tile_elems), dtype=self.payload.dtype, device=self.device),
-                    keys=torch.zeros(c, dtype=torch.int64, device=self.device), perm=None))
+                    keys=torch.zeros(c, dtype=torch.int64, device=self.device),
+                    perm=torch.zeros(c, dtype=torch.int64, device=self.device)))
                 wsb = max(wsb, int(self.lib.csf_pair_tiled_workspace_bytes(c, self.n_agents, eb)))
             # visiting order of the local targets (Morton order too: compact target blocks)
             self._tgt_keys = torch.zeros(self.n_agents, dtype=torch.int64, device=self.device)
             self._tgt_perm = None
+            self._order_valid = False
             self._single_class = (len(self.classes) == 1 and self.classes[0][0] == self.global_offset
                                   and self.classes[0][1] == self.n_agents)
             self._morton = (-float(extent if extent is not None else 2.0 ** 30 * self.q_scale),
@@ -417,6 +423,34 @@ class Engine:
                        "csf_pack_xypsi")
             self.gpu_launches += 1
 
+    _capturing = False
+
+    def _refresh_order(self):
+        """Spatial (Hilbert) visiting order of the sources of every class and of the local targets:
+        keys on the device (csf_morton_keys_*), sort by torch (plumbing), written into buffers whose
+        addresses never change (a captured CUDA graph keeps pointing at them)."""
+        st = self._stream()
+        for ci, (s, c, _, fp) in enumerate(self.classes):
+            if fp.field_kind == 1:
+                continue
+            tl = self._tiles[ci]
+            src = C.c_void_p(self.payload.data_ptr() + s * self.elem_bytes)
+            _lib.check(self._fn("csf_morton_keys")(src, c, self._morton[0], self._morton[0], self._morton[1],
+                                                   _ptr(tl["keys"]), st), "csf_morton_keys")
+            tl["perm"].copy_(torch.argsort(tl["keys"]))
+            self.gpu_launches += 1
+        if self._single_class:      # one class covering exactly the targets: same order
+            self._tgt_perm = self._tiles[0]["perm"]
+        else:
+            tgt = C.c_void_p(self.payload.data_ptr() + self.global_offset * self.elem_bytes)
+            _lib.check(self._fn("csf_morton_keys")(tgt, self.n_agents, self._morton[0], self._morton[0],
+                                                   self._morton[1], _ptr(self._tgt_keys), st), "csf_morton_keys")
+            if self._tgt_perm is None:
+                self._tgt_perm = torch.zeros(self.n_agents, dtype=torch.int64, device=self.device)
+            self._tgt_perm.copy_(torch.argsort(self._tgt_keys))
+            self.gpu_launches += 1
+        self._order_valid = True
+
     def _pair_and_road(self):
         st = self._stream()
         have_rep = self.n_total > 1
@@ -428,16 +462,11 @@ class Engine:
                                                                _ptr(self.frep), st), "csf_pair_forces_grouped")
                 self.gpu_launches += 1
             else:
-                resort = self.tiled and (self._pair_calls % max(self.resort_every, 1) == 0)
+                if self.tiled and not self._capturing and (
+                        not self._order_valid or self._pair_calls % max(self.resort_every, 1) == 0):
+                    self._refresh_order()
                 self._pair_calls += 1
                 tgt = C.c_void_p(self.payload.data_ptr() + self.global_offset * self.elem_bytes)
-                if resort or (self.tiled and self._tgt_perm is None):
-                    if not self._single_class:   # (one class covering exactly the targets: reuse the source order)
-                        _lib.check(self._fn("csf_morton_keys")(tgt, self.n_agents, self._morton[0], self._morton[0],
-                                                               self._morton[1], _ptr(self._tgt_keys), st),
-                                   "csf_morton_keys")
-                        self._tgt_perm = torch.argsort(self._tgt_keys)
-                        self.gpu_launches += 1
                 for ci, (s, c, _, fp) in enumerate(self.classes):
                     src = C.c_void_p(self.payload.data_ptr() + s * self.elem_bytes)
                     if fp.field_kind == 1:
@@ -452,14 +481,6 @@ class Engine:
                         continue
                     if self.tiled:
                         tl = self._tiles[ci]
-                        if resort or tl["perm"] is None:
-                            _lib.check(self._fn("csf_morton_keys")(src, c, self._morton[0], self._morton[0],
-                                                                   self._morton[1], _ptr(tl["keys"]), st),
-                                       "csf_morton_keys")
-                            tl["perm"] = torch.argsort(tl["keys"])
-                            self.gpu_launches += 1
-                            if self._single_class:
-                                self._tgt_perm = tl["perm"]
                         _lib.check(self._fn("csf_tile_sources")(src, c, _ptr(tl["perm"]), _ptr(tl["sorted"]),
                                                                 _ptr(tl["tiles"]), st), "csf_tile_sources")
                         _lib.check(self._fn("csf_pair_forces_tiled")(
@@ -509,7 +530,7 @@ class Engine:
                 self._off(self.force, g), _ptr(self.payload), st), "csf_agent_advance")
             self.gpu_launches += 1
 
-    def _agent_step(self, have_rep):
+    def _agent_step(self, have_rep, exchange=True):
         st = self._stream()
         for g in self.groups:
             _lib.check(self._fn("csf_agent_step")(
@@ -517,14 +538,44 @@ class Engine:
                 self._off(self.frep, g) if have_rep else C.c_void_p(0), self._off(self.froad, g),
                 self._off(self.force, g), _ptr(self.payload), st), "csf_agent_step")
             self.gpu_launches += 1
-        if self.exchange is not None:
+        if exchange and self.exchange is not None:
             self.exchange(self.payload)
 
     def step(self):
         """SocialForceIntersection.step (intersection.py:866-896), fused per-agent kernel."""
         if self.n_agents == 0:
             return
+        if self.use_graph:
+            return self._step_graph()
         self._agent_step(self._pair_and_road())
+
+    def _step_graph(self):
+        """The same kernel sequence replayed from a CUDA graph (launch-bound small crowds / shards)."""
+        if self.tiled and (not self._order_valid or self._pair_calls % max(self.resort_every, 1) == 0):
+            self._refresh_order()
+        if self._graph is None:
+            launches0 = self.gpu_launches
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            g = torch.cuda.CUDAGraph()
+            self._capturing = True
+            try:
+                with torch.cuda.stream(side):
+                    calls = self._pair_calls
+                    with torch.cuda.graph(g, stream=side):
+                        self._agent_step(self._pair_and_road(), exchange=False)
+                    self._pair_calls = calls
+            finally:
+                self._capturing = False
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self._graph_launches = self.gpu_launches - launches0
+            self.gpu_launches = launches0
+            self._graph = g
+        self._graph.replay()
+        self._pair_calls += 1
+        self.gpu_launches += self._graph_launches
+        if self.exchange is not None:
+            self.exchange(self.payload)
 
     def step_host(self, host_in, host_out, host_force=None):
         """One step driven from HOST buffers (pinned): upload the CSF state (x, y, psi, v, delta ...)

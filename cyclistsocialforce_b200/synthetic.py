@@ -29,3 +29,29 @@ def queues_with_start(s0, q):
     start = np.zeros((n, 1, 3))
     start[:, 0, 0], start[:, 0, 1] = s0[:, 0], s0[:, 1]
     return np.concatenate([start, q], axis=1)
+
+
+def spatial_order(x, y, bits=16):
+    """Permutation that sorts positions along a Hilbert curve (same curve as the kernels' keys).
+    Sharding a crowd by contiguous ranges of this order is a spatial domain decomposition: every
+    rank's agents are compact, so its target blocks cull most source chunks."""
+    x = np.asarray(x, float)
+    y = np.asarray(y, float)
+    lo = min(x.min(), y.min())
+    span = max(x.max(), y.max()) - lo
+    n = 1 << bits
+    xi = np.minimum(((x - lo) / max(span, 1e-300) * (n - 1)).astype(np.int64), n - 1)
+    yi = np.minimum(((y - lo) / max(span, 1e-300) * (n - 1)).astype(np.int64), n - 1)
+    d = np.zeros_like(xi)
+    s = n >> 1
+    while s > 0:
+        rx = ((xi & s) > 0).astype(np.int64)
+        ry = ((yi & s) > 0).astype(np.int64)
+        d += s * s * ((3 * rx) ^ ry)
+        flip = (ry == 0) & (rx == 1)
+        xi = np.where(flip, n - 1 - xi, xi)
+        yi = np.where(flip, n - 1 - yi, yi)
+        swap = ry == 0
+        xi, yi = np.where(swap, yi, xi), np.where(swap, xi, yi)
+        s >>= 1
+    return np.argsort(d, kind="stable")

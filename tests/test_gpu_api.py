@@ -232,3 +232,24 @@ def test_f32_per_step_error_against_f64_build():
         worst_s = max(worst_s, np.sort(es)[-3])
         assert (ef > 1e-4).sum() <= 2 and (es > 1e-4).sum() <= 2, (step, np.sort(ef)[-6:], np.sort(es)[-6:])
     report(test="f32_per_step_vs_f64", n=n, steps=30, force_rel_3rd_worst=float(worst_f), state_rel_3rd_worst=float(worst_s))
+
+
+def test_graph_step_equals_kernel_by_kernel_step():
+    """Engine(graph=True) replays a CUDA graph of the step; the periodic re-sort of the spatial order
+    stays outside the graph.  Same kernels, same order -> bitwise the same crowd, across re-sorts."""
+    from cyclistsocialforce_b200 import parameters as P
+    from cyclistsocialforce_b200.engine import AgentGroup, Engine
+    from cyclistsocialforce_b200.synthetic import queues_with_start
+    n = 6000
+    s0, q = co.synthetic_crowd(n, seed=4, spacing=3.0)
+    out = {}
+    for graph in (False, True):
+        g = AgentGroup("twod", s0, P.InvPendulumBicycleParameters(), destqueues=list(queues_with_start(s0, q)),
+                       dtype=torch.float32)
+        eng = Engine([g], dtype=torch.float32, pair_mode="tiled", resort_every=16, graph=graph)
+        for _ in range(40):
+            eng.step()
+        eng.check_status()
+        out[graph] = (g.states_numpy(), eng.force.cpu().numpy())
+    assert np.array_equal(out[False][0], out[True][0])
+    assert np.array_equal(out[False][1], out[True][1])

@@ -43,6 +43,22 @@ int main(int argc, char** argv) {
         cudaMalloc(&stats, 8); cudaMemset(stats, 0, 8);
         size_t wsb2 = csf_pair_tiled_workspace_bytes(n, n, 4); cudaMalloc(&ws2, wsb2);
         float* f2; cudaMalloc(&f2, n * 8);
+        if (argc > 5) {   // 5th argument: divisor -- time one shard (the first n/div targets of the spatial order)
+            const int64_t nt = n / atoi(argv[5]);
+            for (int i = 0; i < 3; ++i) {
+                csf_tile_sources_f32(d, n, dperm, sorted, tiles, 0);
+                csf_pair_forces_tiled_f32(sorted, tiles, n, d, dperm, nt, &fp, f2, 0, ws2, wsb2, nullptr, 0);
+            }
+            cudaDeviceSynchronize();
+            float bt = 1e30f;
+            for (int i = 0; i < reps; ++i) {
+                cudaEventRecord(e0); csf_pair_forces_tiled_f32(sorted, tiles, n, d, dperm, nt, &fp, f2, 0, ws2, wsb2, nullptr, 0);
+                cudaEventRecord(e1); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); bt = fminf(bt, ms);
+            }
+            printf("SHARD n_src=%lld n_tgt=%lld best %.4f ms (x%d = %.4f ms) err=%s\n", (long long)n, (long long)nt, bt,
+                   atoi(argv[5]), bt * atoi(argv[5]), cudaGetErrorString(cudaGetLastError()));
+            return 0;
+        }
         csf_tile_sources_f32(d, n, dperm, sorted, tiles, 0);
         csf_pair_forces_tiled_f32(sorted, tiles, n, d, dperm, n, &fp, f2, 0, ws2, wsb2, stats, 0);
         cudaDeviceSynchronize();
