@@ -99,6 +99,19 @@ def cpu_oracle_run(steps, warmup, sample_agents=None):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (the NCCL version banner) are
+    # sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    try:
+        return run(args, real_stdout)
+    finally:
+        sys.stdout.flush()
+        real_stdout.flush()
+
+
+def run(args, out):
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -117,13 +130,13 @@ def main():
             "e2e": {"value": r["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
         return 0
 
     import torch
     import torch.distributed as dist
     from cyclistsocialforce_b200 import _lib, parameters as P
-    from cyclistsocialforce_b200.distributed import PayloadExchange, shard_bounds
+    from cyclistsocialforce_b200.distributed import PayloadExchange, PeerExchange, shard_bounds
     from cyclistsocialforce_b200.engine import AgentGroup, Engine
     from cyclistsocialforce_b200.synthetic import queues_with_start, spatial_order, synthetic_crowd
 
@@ -149,7 +162,9 @@ def main():
     extent = 2.0 * float(max(np.abs(s0[:, :2]).max(), np.abs(q[..., :2]).max())) + 1000.0
     group = AgentGroup("twod", s0[lo:hi], P.InvPendulumBicycleParameters(), destqueues=list(queues[lo:hi]),
                        dtype=torch.float32, device=dev)
-    exch = PayloadExchange(N_AGENTS, rank, world)
+    exchange_kind = os.environ.get("CSF_BENCH_EXCHANGE", "peer") if (world > 1 and not emu) else "none"
+    exch = (PeerExchange(N_AGENTS, rank, world, torch.float32, dev) if exchange_kind == "peer"
+            else PayloadExchange(N_AGENTS, rank, world))
     if emu:
         full = AgentGroup("twod", s0, P.InvPendulumBicycleParameters(), destqueues=list(queues),
                           dtype=torch.float32, device=dev)
@@ -305,7 +320,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_agents": N_AGENTS, "step": "CUDA-graph replay" if use_graph else "kernel-by-kernel launches", "partition": "contiguous agent ranges of a Hilbert order of the initial positions (spatial decomposition)", "parallelism": f"agent-range x{world}" + (f" (EMULATED 1/{emu} shard, not a result)" if emu else ""), "pair_kernel": "tiled+culled" if eng.tiled else "dense",
+            "config": {"workload": WORKLOAD, "n_agents": N_AGENTS, "step": "CUDA-graph replay" if use_graph else "kernel-by-kernel launches", "partition": "contiguous agent ranges of a Hilbert order of the initial positions (spatial decomposition)", "exchange": {"peer": "NVLink peer-memory stores + flags inside the step graph (csf_peer_*)", "nccl": "NCCL all_gather_into_tensor", "none": "none (1 GPU)"}[exchange_kind], "parallelism": f"agent-range x{world}" + (f" (EMULATED 1/{emu} shard, not a result)" if emu else ""), "pair_kernel": "tiled+culled" if eng.tiled else "dense",
                        "l2": "flushed between timed steps (256 MiB write)", "q_scale_m": eng.q_scale,
                        "pair_interactions_per_s": float(N_AGENTS) * (N_AGENTS - 1) * args.steps / (total_ms * 1e-3)},
             "clocks": clocks,
@@ -334,7 +349,7 @@ def main():
             r = cpu_oracle_run(steps=2, warmup=1)
             line["cpu_baseline"] = {"value": r["value"], "unit": "agent-steps/s", "cores": r["cores"],
                                     "kind": r["kind"], "sample": r["sample"]}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

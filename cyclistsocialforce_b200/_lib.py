@@ -25,6 +25,19 @@ class CsfFieldParams(C.Structure):
     ]
 
 
+CSF_MAX_PEERS = 16
+
+
+class CsfPeerComm(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32), ("rank", C.c_int32),
+        ("payload", C.c_void_p * CSF_MAX_PEERS),
+        ("data_flags", C.c_void_p * CSF_MAX_PEERS),
+        ("read_flags", C.c_void_p * CSF_MAX_PEERS),
+        ("seq", C.c_void_p),
+    ]
+
+
 class CsfAgentParams(C.Structure):
     _fields_ = [
         ("t_s", C.c_double),
@@ -105,6 +118,14 @@ SIGNATURES = {
     "csf_pack_xypsi_f32": (C.c_int, [_vp, _vp, _vp, _i64, _dbl, _vp, _vp]),
     "csf_pack_xypsi_f64": (C.c_int, [_vp, _vp, _vp, _i64, _dbl, _vp, _vp]),
     "csf_ffma_peak": (C.c_int, [_i64, _vp, C.POINTER(C.c_double), _vp]),
+    "csf_peer_handle_bytes": (C.c_int, []),
+    "csf_peer_alloc": (C.c_int, [_sz, C.POINTER(C.c_void_p), _vp]),
+    "csf_peer_open": (C.c_int, [_vp, C.POINTER(C.c_void_p)]),
+    "csf_peer_close": (C.c_int, [_vp]),
+    "csf_peer_free": (C.c_int, [_vp]),
+    "csf_peer_wait_data": (C.c_int, [C.POINTER(CsfPeerComm), _vp]),
+    "csf_peer_signal_read": (C.c_int, [C.POINTER(CsfPeerComm), _vp]),
+    "csf_peer_push": (C.c_int, [C.POINTER(CsfPeerComm), _i64, _i64, C.c_int, _vp]),
 }
 
 _lib = None

@@ -55,6 +55,118 @@ class PayloadExchange:
                     payload[lo:hi] = self._slab[r, :hi - lo]
 
 
+class _RawDeviceArray:
+    """``__cuda_array_interface__`` wrapper: lets torch view memory this package allocated itself."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False),
+                                             version=2)
+
+
+class PeerExchange:
+    """The same exchange over NVLink peer memory, no collective call on the step path
+    (csrc/csf_peer.cu): every rank owns one IPC-shared buffer [payload | data flags | read flags |
+    sequence words]; after K2/K3 a rank stores its new payload range straight into every peer's
+    buffer and raises a flag there; the next step's first kernel waits for all flags.  The three
+    kernels (wait / signal-read / push) have fixed arguments, so they are captured into the step's
+    CUDA graph.  One node only (CUDA IPC); ``torch.distributed`` is used once, to swap the handles."""
+
+    capturable = True
+
+    def __init__(self, n_global, rank, world, dtype, device, group=None):
+        import ctypes as C
+        from . import _lib
+        self.lib = _lib.load()
+        self._lib_mod = _lib
+        if world > _lib.CSF_MAX_PEERS:
+            raise ValueError(f"PeerExchange supports at most {_lib.CSF_MAX_PEERS} ranks")
+        self.bounds = shard_bounds(n_global, world)
+        self.rank, self.world, self.group = rank, world, group
+        self.lo, self.hi = self.bounds[rank]
+        self.device = torch.device(device)
+        self.f32 = dtype == torch.float32
+        self.elem_bytes = 16 if self.f32 else 32
+        self.calls = 0
+        pay = (n_global * self.elem_bytes + 255) // 256 * 256
+        self.off_data, self.off_read, self.off_seq = pay, pay + 256, pay + 512
+        self.bytes = pay + 1024
+        base = C.c_void_p()
+        hb = self.lib.csf_peer_handle_bytes()
+        handle = (C.c_ubyte * hb)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.csf_peer_alloc(self.bytes, C.byref(base), handle), "csf_peer_alloc")
+        self.base = int(base.value)
+        self.peers = [None] * world
+        self.peers[rank] = self.base
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            with torch.cuda.device(self.device):
+                for p in range(world):
+                    if p == rank:
+                        continue
+                    ptr = C.c_void_p()
+                    buf = (C.c_ubyte * hb).from_buffer_copy(handles[p])
+                    _lib.check(self.lib.csf_peer_open(buf, C.byref(ptr)), "csf_peer_open")
+                    self.peers[p] = int(ptr.value)
+            dist.barrier(group=group)
+        comm = _lib.CsfPeerComm()
+        comm.world, comm.rank = world, rank
+        for p in range(world):
+            comm.payload[p] = self.peers[p]
+            comm.data_flags[p] = self.peers[p] + self.off_data
+            comm.read_flags[p] = self.peers[p] + self.off_read
+        comm.seq = self.base + self.off_seq
+        self.comm = comm
+        self._C = C
+        shape, typestr = ((n_global, 4), "<i4") if self.f32 else ((n_global, 4), "<f8")
+        self._raw = _RawDeviceArray(self.base, shape, typestr)
+        self.payload = torch.as_tensor(self._raw, device=self.device)
+        self._seq = torch.as_tensor(_RawDeviceArray(self.base + self.off_seq, (4,), "<i4"), device=self.device)
+
+    def payload_tensor(self):
+        """The (n_global, 4) payload array inside the shared buffer: the Engine uses it as its payload."""
+        return self.payload
+
+    def _st(self):
+        return self._C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def begin_step(self):
+        self._lib_mod.check(self.lib.csf_peer_wait_data(self._C.byref(self.comm), self._st()), "csf_peer_wait_data")
+
+    def after_pair(self):
+        self._lib_mod.check(self.lib.csf_peer_signal_read(self._C.byref(self.comm), self._st()),
+                            "csf_peer_signal_read")
+
+    def __call__(self, payload):
+        if self.world == 1:
+            return
+        assert payload.data_ptr() == self.base, "PeerExchange: the engine must use payload_tensor() as its payload"
+        self.calls += 1
+        self._lib_mod.check(self.lib.csf_peer_push(self._C.byref(self.comm), self.lo, self.hi - self.lo,
+                                                   self.elem_bytes, self._st()), "csf_peer_push")
+
+    def check_status(self):
+        st = int(self._seq[3].item())
+        if st:
+            raise RuntimeError(f"PeerExchange: a wait on a peer flag timed out (status {st})")
+
+    def close(self):
+        if self.base is None:
+            return
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        for p, ptr in enumerate(self.peers):
+            if p != self.rank and ptr:
+                self.lib.csf_peer_close(self._C.c_void_p(ptr))
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        self.payload = self._seq = self._raw = None
+        self.lib.csf_peer_free(self._C.c_void_p(self.base))
+        self.base = None
+
+
 def gather_rows_host(local_rows: np.ndarray, n_global: int, rank: int, world: int, group=None):
     """Host-side helper for tests: concatenate per-rank numpy rows on every rank."""
     if world == 1:

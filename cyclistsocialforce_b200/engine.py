@@ -334,7 +334,12 @@ class Engine:
         self.q_scale = float(q_scale)
         self.elem_bytes = 16 if self.f32 else 32
         n = max(self.n_total, 1)
-        self.payload = torch.zeros((n, 4), dtype=torch.int32 if self.f32 else torch.float64, device=self.device)
+        if exchange is not None and hasattr(exchange, "payload_tensor"):
+            self.payload = exchange.payload_tensor()      # lives in the peer-shared buffer (PeerExchange)
+            assert self.payload.shape[0] == n and self.payload.dtype == (torch.int32 if self.f32 else torch.float64)
+        else:
+            self.payload = torch.zeros((n, 4), dtype=torch.int32 if self.f32 else torch.float64,
+                                       device=self.device)
         self.frep = torch.zeros((max(self.n_agents, 1), 2), dtype=dtype, device=self.device)
         self.force = torch.zeros_like(self.frep)
         self.fdest = torch.zeros_like(self.frep)
@@ -453,6 +458,15 @@ class Engine:
 
     def _pair_and_road(self):
         st = self._stream()
+        if self.exchange is not None and hasattr(self.exchange, "begin_step"):
+            self.exchange.begin_step()                    # wait for every peer's payload push
+        have_rep = self._pair(st)
+        if self.exchange is not None and hasattr(self.exchange, "after_pair"):
+            self.exchange.after_pair()                    # the payload has been read: peers may overwrite it
+        self._road(st)
+        return have_rep
+
+    def _pair(self, st):
         have_rep = self.n_total > 1
         if have_rep:
             if self.scenario_size is not None:
@@ -493,6 +507,9 @@ class Engine:
                                                            C.byref(fp), _ptr(self.frep), 1 if ci > 0 else 0,
                                                            _ptr(self.ws), self.ws.numel(), st), "csf_pair_forces")
                     self.gpu_launches += 2
+        return have_rep
+
+    def _road(self, st):
         if self.road:
             for g in self.groups:
                 out = self._off(self.froad, g)
@@ -501,7 +518,6 @@ class Engine:
                                                            F_0, sigma, out, 1 if ei > 0 else 0, st),
                                "csf_road_forces")
                     self.gpu_launches += 1
-        return have_rep
 
     def _off(self, t, g):
         if t is None:
@@ -553,6 +569,7 @@ class Engine:
         """The same kernel sequence replayed from a CUDA graph (launch-bound small crowds / shards)."""
         if self.tiled and (not self._order_valid or self._pair_calls % max(self.resort_every, 1) == 0):
             self._refresh_order()
+        self._exchange_in_graph = bool(getattr(self.exchange, "capturable", False))
         if self._graph is None:
             launches0 = self.gpu_launches
             side = torch.cuda.Stream(device=self.device)
@@ -563,7 +580,7 @@ class Engine:
                 with torch.cuda.stream(side):
                     calls = self._pair_calls
                     with torch.cuda.graph(g, stream=side):
-                        self._agent_step(self._pair_and_road(), exchange=False)
+                        self._agent_step(self._pair_and_road(), exchange=self._exchange_in_graph)
                     self._pair_calls = calls
             finally:
                 self._capturing = False
@@ -574,7 +591,7 @@ class Engine:
         self._graph.replay()
         self._pair_calls += 1
         self.gpu_launches += self._graph_launches
-        if self.exchange is not None:
+        if self.exchange is not None and not self._exchange_in_graph:
             self.exchange(self.payload)
 
     def step_host(self, host_in, host_out, host_force=None):
@@ -595,6 +612,8 @@ class Engine:
         torch.cuda.current_stream(self.device).synchronize()
 
     def check_status(self):
+        if self.exchange is not None and hasattr(self.exchange, "check_status"):
+            self.exchange.check_status()
         return [g.check_status() for g in self.groups]
 
     # ---- per-vehicle operations (the reference's per-vehicle hooks) -------------------------------

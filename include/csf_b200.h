@@ -255,6 +255,36 @@ int csf_pack_xypsi_f32(const double* x, const double* y, const double* psi, int6
 int csf_pack_xypsi_f64(const double* x, const double* y, const double* psi, int64_t n, double q_scale,
                        void* xycs, csf_stream_t stream);
 
+/* ---- multi-GPU: payload exchange over NVLink peer memory --------------------------------
+ * One crowd sharded by agent range over the GPUs of a node: the one exchange step
+ * per simulation step -- every rank's new payload entries to every other rank -- done with
+ * direct peer stores and flag words instead of a collective library call.  Each rank allocates
+ * one buffer with csf_peer_alloc (cudaMalloc + IPC handle), ranks swap the handles through any
+ * host channel and map them with csf_peer_open, and fill a CsfPeerComm with the device addresses
+ * (layout of the buffer is the caller's: payload array, then `world` data flags, `world` read
+ * flags and 4 sequence words, all zero-initialised).  Per step, in stream order:
+ *   csf_peer_wait_data  -> (readers of the payload: tile build, K1) -> csf_peer_signal_read
+ *   -> (K2/K3 writes the own range locally) -> csf_peer_push(first_elem, n_elem)
+ * Every rank must issue the same sequence.  All three are plain kernel launches with fixed
+ * arguments (CUDA-graph capturable).  seq[3] != 0 afterwards = a wait timed out (~4 s). */
+#define CSF_MAX_PEERS 16
+typedef struct CsfPeerComm {
+    int32_t world, rank;
+    void* payload[CSF_MAX_PEERS];        /* payload array of every rank (own entry: local pointer) */
+    uint32_t* data_flags[CSF_MAX_PEERS]; /* [world] words in rank p's buffer; rank r writes word r */
+    uint32_t* read_flags[CSF_MAX_PEERS];
+    uint32_t* seq;                       /* local: push count, read count, block counter, status */
+} CsfPeerComm;
+int csf_peer_handle_bytes(void);
+int csf_peer_alloc(size_t bytes, void** devptr, void* ipc_handle_out);
+int csf_peer_open(const void* ipc_handle, void** devptr);
+int csf_peer_close(void* devptr);
+int csf_peer_free(void* devptr);
+int csf_peer_wait_data(const CsfPeerComm* comm, csf_stream_t stream);
+int csf_peer_signal_read(const CsfPeerComm* comm, csf_stream_t stream);
+int csf_peer_push(const CsfPeerComm* comm, int64_t first_elem, int64_t n_elem, int elem_bytes,
+                  csf_stream_t stream);
+
 /* ---- measurement helper: sustained FP32 FFMA throughput of this device ------------
  * Runs `iters` dependent-chain FFMA rounds on every SM; returns flops executed
  * (2 per FFMA) through *flops; the caller times it with CUDA events. */

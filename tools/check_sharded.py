@@ -14,7 +14,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cyclistsocialforce_b200 import parameters as P  # noqa: E402
-from cyclistsocialforce_b200.distributed import PayloadExchange, gather_rows_host, shard_bounds  # noqa: E402
+from cyclistsocialforce_b200.distributed import PayloadExchange, PeerExchange, gather_rows_host, shard_bounds  # noqa: E402
 from cyclistsocialforce_b200.engine import AgentGroup, Engine  # noqa: E402
 from cyclistsocialforce_b200.synthetic import queues_with_start, synthetic_crowd  # noqa: E402
 
@@ -25,15 +25,17 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     dev = torch.device("cuda", lr)
     ok = True
-    for n, dtype, steps in ((4099, torch.float64, 12), (8192, torch.float32, 12)):
+    peer = "--peer" in sys.argv          # NVLink peer-memory exchange (+ CUDA-graph step) instead of NCCL
+    for n, dtype, steps in ((4099, torch.float64, 12), (8192, torch.float32, 40)):
         s0, q = synthetic_crowd(n, seed=17, spacing=3.0)
         queues = queues_with_start(s0, q)
         extent = 2.0 * float(max(np.abs(s0[:, :2]).max(), np.abs(q[..., :2]).max())) + 1000.0
         lo, hi = shard_bounds(n, world)[rank]
         g = AgentGroup("twod", s0[lo:hi], P.InvPendulumBicycleParameters(), destqueues=list(queues[lo:hi]),
                        dtype=dtype, device=dev)
-        ex = PayloadExchange(n, rank, world)
-        eng = Engine([g], dtype=dtype, device=dev, extent=extent, n_global=n, global_offset=lo, exchange=ex)
+        ex = PeerExchange(n, rank, world, dtype, dev) if peer else PayloadExchange(n, rank, world)
+        eng = Engine([g], dtype=dtype, device=dev, extent=extent, n_global=n, global_offset=lo, exchange=ex,
+                     graph=peer, resort_every=16)
         ex(eng.payload)
         for _ in range(steps):
             eng.step()
@@ -42,15 +44,18 @@ def main():
         if rank == 0:
             g1 = AgentGroup("twod", s0, P.InvPendulumBicycleParameters(), destqueues=list(queues), dtype=dtype,
                             device=dev)
-            e1 = Engine([g1], dtype=dtype, device=dev, extent=extent)
+            e1 = Engine([g1], dtype=dtype, device=dev, extent=extent, resort_every=16)
             for _ in range(steps):
                 e1.step()
             ref = g1.states_numpy()
             err = float(np.abs(got - ref).max())
             tol = 1e-10 if dtype == torch.float64 else 2e-4
-            print(f"sharded x{world} vs single GPU: n={n} {dtype} {steps} steps max|diff|={err:.3e} "
+            print(f"sharded x{world} ({'peer memory + graph' if peer else 'NCCL all-gather'}) vs single GPU: n={n} {dtype} {steps} steps max|diff|={err:.3e} "
                   f"(tol {tol:g}) exchanges={ex.calls}", flush=True)
             ok = ok and err < tol
+        if peer:
+            del eng
+            ex.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
