@@ -136,7 +136,8 @@ def run(args, out):
     import torch
     import torch.distributed as dist
     from cyclistsocialforce_b200 import _lib, parameters as P
-    from cyclistsocialforce_b200.distributed import PayloadExchange, PeerExchange, shard_bounds
+    from cyclistsocialforce_b200.distributed import (PayloadExchange, PeerExchange, balanced_bounds, neighbour_work,
+                                                     shard_bounds)
     from cyclistsocialforce_b200.engine import AgentGroup, Engine
     from cyclistsocialforce_b200.synthetic import queues_with_start, spatial_order, synthetic_crowd
 
@@ -158,13 +159,20 @@ def run(args, out):
     # CSF_BENCH_EMULATE_WORLD=8: time ONE rank's shard of an 8-way split on a single GPU (tuning aid;
     # the payload of the other shards stays frozen, no exchange) -- never used for reported numbers
     emu = int(os.environ.get("CSF_BENCH_EMULATE_WORLD", 0))
-    lo, hi = shard_bounds(N_AGENTS, emu)[0] if emu else shard_bounds(N_AGENTS, world)[rank]
+    # ranks get contiguous ranges of equal estimated pair work (agents at the rim of the crowd have
+    # fewer neighbours): every rank computes the same bounds from the same initial positions
+    nparts = emu if emu else world
+    balance = os.environ.get("CSF_BENCH_BALANCE", "1") != "0"
+    bounds = (balanced_bounds(neighbour_work(s0[:, 0], s0[:, 1], 160.0), nparts) if (balance and nparts > 1)
+              else shard_bounds(N_AGENTS, nparts))
+    lo, hi = bounds[0] if emu else bounds[rank]
     extent = 2.0 * float(max(np.abs(s0[:, :2]).max(), np.abs(q[..., :2]).max())) + 1000.0
     group = AgentGroup("twod", s0[lo:hi], P.InvPendulumBicycleParameters(), destqueues=list(queues[lo:hi]),
                        dtype=torch.float32, device=dev)
     exchange_kind = os.environ.get("CSF_BENCH_EXCHANGE", "peer") if (world > 1 and not emu) else "none"
-    exch = (PeerExchange(N_AGENTS, rank, world, torch.float32, dev) if exchange_kind == "peer"
-            else PayloadExchange(N_AGENTS, rank, world))
+    xb = None if emu else bounds
+    exch = (PeerExchange(N_AGENTS, rank, world, torch.float32, dev, bounds=xb) if exchange_kind == "peer"
+            else PayloadExchange(N_AGENTS, rank, world, bounds=xb))
     if emu:
         full = AgentGroup("twod", s0, P.InvPendulumBicycleParameters(), destqueues=list(queues),
                           dtype=torch.float32, device=dev)
@@ -320,7 +328,7 @@ def run(args, out):
             "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_agents": N_AGENTS, "step": "CUDA-graph replay" if use_graph else "kernel-by-kernel launches", "partition": "contiguous agent ranges of a Hilbert order of the initial positions (spatial decomposition)", "exchange": {"peer": "NVLink peer-memory stores + flags inside the step graph (csf_peer_*)", "nccl": "NCCL all_gather_into_tensor", "none": "none (1 GPU)"}[exchange_kind], "parallelism": f"agent-range x{world}" + (f" (EMULATED 1/{emu} shard, not a result)" if emu else ""), "pair_kernel": "tiled+culled" if eng.tiled else "dense",
+            "config": {"workload": WORKLOAD, "n_agents": N_AGENTS, "step": "CUDA-graph replay" if use_graph else "kernel-by-kernel launches", "partition": "contiguous agent ranges of a Hilbert order of the initial positions (spatial decomposition)" + (", ranges balanced by estimated neighbour count" if (balance and nparts > 1) else ""), "exchange": {"peer": "NVLink peer-memory stores + flags inside the step graph (csf_peer_*)", "nccl": "NCCL all_gather_into_tensor", "none": "none (1 GPU)"}[exchange_kind], "parallelism": f"agent-range x{world}" + (f" (EMULATED 1/{emu} shard, not a result)" if emu else ""), "pair_kernel": "tiled+culled" if eng.tiled else "dense",
                        "l2": "flushed between timed steps (256 MiB write)", "q_scale_m": eng.q_scale,
                        "pair_interactions_per_s": float(N_AGENTS) * (N_AGENTS - 1) * args.steps / (total_ms * 1e-3)},
             "clocks": clocks,

@@ -160,58 +160,54 @@ template <> struct BBox<double> {
     }
 };
 
-// One warp per tile: gather the tile's 64 sources through `perm` (nullptr: identity), write them in
-// the SrcA/SrcB layout and the tile's bounding circle.  Entries past n are padded with a far-away
-// sentinel that contributes exactly 0 and is not part of any bounding circle.
+// One CTA per chunk, one warp per tile: gather the tile's 64 sources through `perm` (nullptr:
+// identity), write them in the SrcA/SrcB layout with the tile's bounding circle, then combine the 16
+// tile boxes into the chunk's bounding circle.  Entries past n are padded with a far-away sentinel
+// that contributes exactly 0 and is not part of any bounding circle.
 template <typename T>
-__global__ void tile_sources_kernel(const Xycs<T>* __restrict__ xycs, int64_t n, const int64_t* __restrict__ perm,
-                                    unsigned char* __restrict__ sorted, Tile<T>* __restrict__ tiles, int64_t n_tiles) {
-    const int lane = threadIdx.x & 31;
-    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (t >= n_tiles) return;
-    const int64_t i0 = t * kTileS + lane, i1 = i0 + 32;
-    Xycs<T> a, b;
-    const bool va = i0 < n, vb = i1 < n;
-    if (va) a = xycs[perm ? perm[i0] : i0]; else pad_entry(a);
-    if (vb) b = xycs[perm ? perm[i1] : i1]; else pad_entry(b);
-    SrcA<T> A;
-    SrcB<T> B;
-    split(a, b, A, B);
-    unsigned char* base = sorted + (size_t)t * TileBytes<T>::v;
-    reinterpret_cast<SrcA<T>*>(base)[lane] = A;
-    reinterpret_cast<SrcB<T>*>(base + 32 * sizeof(SrcA<T>))[lane] = B;
+__global__ void __launch_bounds__(kCT * 32)
+tile_sources_kernel(const Xycs<T>* __restrict__ xycs, int64_t n, const int64_t* __restrict__ perm,
+                    unsigned char* __restrict__ sorted, Tile<T>* __restrict__ tiles, int64_t n_tiles) {
+    __shared__ __align__(16) unsigned char boxes_raw[kCT * sizeof(BBox<T>)];
+    BBox<T>* boxes = reinterpret_cast<BBox<T>*>(boxes_raw);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t c = blockIdx.x, t = c * kCT + w;
     BBox<T> bb;
-    if (va) bb.add(a);
-    if (vb) bb.add(b);
-    bb.warp_reduce();
-    const int64_t rem = n - t * kTileS;
-    if (lane == 0) tiles[t] = bb.circle(rem < kTileS ? rem : kTileS);
-}
-
-// One warp per chunk: bounding circle of the chunk's sources, read back from the sorted copy.
-template <typename T>
-__global__ void chunk_bounds_kernel(const unsigned char* __restrict__ sorted, int64_t n, int64_t n_tiles,
-                                    Tile<T>* __restrict__ chunks, int64_t n_chunks) {
-    const int lane = threadIdx.x & 31;
-    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c >= n_chunks) return;
-    BBox<T> bb;
-    const int64_t t_end = min(n_tiles, (c + 1) * kCT);
-    for (int64_t t = c * kCT; t < t_end; ++t) {
-        const SrcA<T> A = reinterpret_cast<const SrcA<T>*>(sorted + (size_t)t * TileBytes<T>::v)[lane];
-        const int64_t i0 = t * kTileS + lane;
-        if (i0 < n) bb.add(A.x0, A.y0);
-        if (i0 + 32 < n) bb.add(A.x1, A.y1);
+    if (t < n_tiles) {
+        const int64_t i0 = t * kTileS + lane, i1 = i0 + 32;
+        Xycs<T> a, b;
+        const bool va = i0 < n, vb = i1 < n;
+        if (va) a = xycs[perm ? perm[i0] : i0]; else pad_entry(a);
+        if (vb) b = xycs[perm ? perm[i1] : i1]; else pad_entry(b);
+        SrcA<T> A;
+        SrcB<T> B;
+        split(a, b, A, B);
+        unsigned char* base = sorted + (size_t)t * TileBytes<T>::v;
+        reinterpret_cast<SrcA<T>*>(base)[lane] = A;
+        reinterpret_cast<SrcB<T>*>(base + 32 * sizeof(SrcA<T>))[lane] = B;
+        if (va) bb.add(a);
+        if (vb) bb.add(b);
+        bb.warp_reduce();
+        const int64_t rem = n - t * kTileS;
+        if (lane == 0) tiles[t] = bb.circle(rem < kTileS ? rem : kTileS);
     }
-    bb.warp_reduce();
-    const int64_t cnt = min(n, (c + 1) * (int64_t)kCS) - c * (int64_t)kCS;
-    if (lane == 0) chunks[c] = bb.circle(cnt);
+    if (lane == 0) boxes[w] = bb;
+    __syncthreads();
+    if (w == 0) {
+        BBox<T> cb;
+        if (lane < kCT) cb = boxes[lane];
+        cb.warp_reduce();
+        const int64_t cnt = min(n, (c + 1) * (int64_t)kCS) - c * (int64_t)kCS;
+        if (lane == 0) tiles[n_tiles + c] = cb.circle(cnt);
+    }
 }
 
 // One warp per target block: bounding circle of targets tgt[perm[b*group .. (b+1)*group)).
 template <typename T>
 __global__ void block_bounds_kernel(const Xycs<T>* __restrict__ tgt, const int64_t* __restrict__ perm, int64_t n,
-                                    int group, Tile<T>* __restrict__ blocks, int64_t n_blocks) {
+                                    int group, Tile<T>* __restrict__ blocks, int64_t n_blocks,
+                                    unsigned int* __restrict__ item_counter) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *item_counter = 0;   // the pair kernel's dynamic item counter
     const int lane = threadIdx.x & 31;
     const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (b >= n_blocks) return;
@@ -697,12 +693,9 @@ template <typename T>
 int tile_sources(const void* xycs, int64_t n, const int64_t* perm, void* sorted, void* tiles, cudaStream_t st) {
     if (n <= 0) return 0;
     const int64_t n_tiles = (n + kTileS - 1) / kTileS, n_chunks = (n_tiles + kCT - 1) / kCT;
-    tile_sources_kernel<T><<<(unsigned)((n_tiles * 32 + 127) / 128), 128, 0, st>>>(
+    tile_sources_kernel<T><<<(unsigned)n_chunks, kCT * 32, 0, st>>>(
         (const Xycs<T>*)xycs, n, perm, (unsigned char*)sorted, (Tile<T>*)tiles, n_tiles);
     CSF_CHECK_LAUNCH("tile_sources_kernel");
-    chunk_bounds_kernel<T><<<(unsigned)((n_chunks * 32 + 127) / 128), 128, 0, st>>>(
-        (const unsigned char*)sorted, n, n_tiles, (Tile<T>*)tiles + n_tiles, n_chunks);
-    CSF_CHECK_LAUNCH("chunk_bounds_kernel");
     return 0;
 }
 
@@ -733,9 +726,8 @@ int pair_tiled(const void* sorted, const void* tiles, int64_t n_src, const void*
     unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
     Tile<T>* tblocks = reinterpret_cast<Tile<T>*>((unsigned char*)ws + kWsHeader);
     T* partial = reinterpret_cast<T*>((unsigned char*)ws + off_partial);
-    cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
     block_bounds_kernel<T><<<(unsigned)(((int64_t)pl.n_tblocks * 32 + 127) / 128), 128, 0, st>>>(
-        (const Xycs<T>*)tgt, tgt_perm, n_tgt, kTW * pl.tpw, tblocks, pl.n_tblocks);
+        (const Xycs<T>*)tgt, tgt_perm, n_tgt, kTW * pl.tpw, tblocks, pl.n_tblocks, counter);
     CSF_CHECK_LAUNCH("block_bounds_kernel");
     tiled_ctas<T>();   // sets the dynamic shared-memory attribute
     if (fp->p2r)

@@ -24,11 +24,50 @@ def shard_bounds(n, world):
     return out
 
 
+def balanced_bounds(weights, world):
+    """Contiguous agent ranges of (nearly) equal total weight: [(lo, hi)] per rank.  With the agents
+    numbered along a space-filling curve and ``weights`` = estimated pair work per agent this is a
+    load-balanced spatial decomposition (ranks at the rim of a crowd have fewer neighbours per agent
+    and get more agents)."""
+    w = np.asarray(weights, float)
+    n = w.shape[0]
+    c = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [0]
+    for r in range(1, world):
+        k = int(np.searchsorted(c, c[-1] * r / world))
+        cuts.append(min(max(k, cuts[-1] + 1), n - (world - r)))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def neighbour_work(x, y, radius, cell=None, overhead=0.1):
+    """Estimated pair work per agent: the number of road users within ``radius`` (cell histogram +
+    disc-shaped box filter), plus ``overhead`` x the mean as the per-agent fixed cost."""
+    x = np.asarray(x, float)
+    y = np.asarray(y, float)
+    cell = cell or radius / 5.0
+    ix = np.floor((x - x.min()) / cell).astype(np.int64)
+    iy = np.floor((y - y.min()) / cell).astype(np.int64)
+    nx, ny = int(ix.max()) + 1, int(iy.max()) + 1
+    hist = np.zeros((nx, ny))
+    np.add.at(hist, (ix, iy), 1.0)
+    k = int(np.ceil(radius / cell))
+    acc = np.zeros_like(hist)
+    for dx in range(-k, k + 1):
+        for dy in range(-k, k + 1):
+            if (dx * dx + dy * dy) * cell * cell > (radius + cell) ** 2:
+                continue
+            src = hist[max(0, -dx):nx - max(0, dx), max(0, -dy):ny - max(0, dy)]
+            acc[max(0, dx):nx - max(0, -dx), max(0, dy):ny - max(0, -dy)] += src
+    w = acc[ix, iy]
+    return w + overhead * w.mean()
+
+
 class PayloadExchange:
     """all-gather of the pair payload; handles unequal shard sizes."""
 
-    def __init__(self, n_global, rank, world, group=None):
-        self.bounds = shard_bounds(n_global, world)
+    def __init__(self, n_global, rank, world, group=None, bounds=None):
+        self.bounds = list(bounds) if bounds is not None else shard_bounds(n_global, world)
         self.rank, self.world, self.group = rank, world, group
         self.lo, self.hi = self.bounds[rank]
         self.equal = len({hi - lo for lo, hi in self.bounds}) == 1
@@ -73,14 +112,14 @@ class PeerExchange:
 
     capturable = True
 
-    def __init__(self, n_global, rank, world, dtype, device, group=None):
+    def __init__(self, n_global, rank, world, dtype, device, group=None, bounds=None):
         import ctypes as C
         from . import _lib
         self.lib = _lib.load()
         self._lib_mod = _lib
         if world > _lib.CSF_MAX_PEERS:
             raise ValueError(f"PeerExchange supports at most {_lib.CSF_MAX_PEERS} ranks")
-        self.bounds = shard_bounds(n_global, world)
+        self.bounds = list(bounds) if bounds is not None else shard_bounds(n_global, world)
         self.rank, self.world, self.group = rank, world, group
         self.lo, self.hi = self.bounds[rank]
         self.device = torch.device(device)

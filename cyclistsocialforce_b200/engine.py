@@ -501,7 +501,7 @@ class Engine:
                             _ptr(tl["sorted"]), _ptr(tl["tiles"]), c, tgt, _ptr(self._tgt_perm), self.n_agents,
                             C.byref(fp), _ptr(self.frep), 1 if ci > 0 else 0, _ptr(self.ws), self.ws.numel(),
                             _ptr(self.pair_stats), st), "csf_pair_forces_tiled")
-                        self.gpu_launches += 5   # tile build, chunk bounds, block bounds, pair, reduce
+                        self.gpu_launches += 4   # tile build (+ chunk bounds), block bounds, pair, reduce
                         continue
                     _lib.check(self._fn("csf_pair_forces")(src, c, tgt, self.n_agents,
                                                            C.byref(fp), _ptr(self.frep), 1 if ci > 0 else 0,

@@ -58,3 +58,28 @@ def test_payload_exchange_gloo_world2(n):
     mp.spawn(_worker, args=(world, _free_port(), n, ret), nprocs=world, join=True)
     assert all(ret[r][0] for r in range(world)), dict(ret)
     assert all(ret[r][1] == 2 for r in range(world))
+
+
+def test_balanced_spatial_partition():
+    """Spatial decomposition helpers: Hilbert order of the initial positions, ranges balanced by the
+    estimated neighbour count (host logic of bench.py's multi-GPU partition)."""
+    import numpy as np
+    from cyclistsocialforce_b200.distributed import balanced_bounds, neighbour_work, shard_bounds
+    from cyclistsocialforce_b200.synthetic import spatial_order, synthetic_crowd
+    s0, _ = synthetic_crowd(4096, seed=2, spacing=4.0)
+    order = spatial_order(s0[:, 0], s0[:, 1])
+    assert np.array_equal(np.sort(order), np.arange(4096))
+    xs, ys = s0[order, 0], s0[order, 1]
+    # consecutive agents along the curve are close: a shard is a compact region
+    step = np.hypot(np.diff(xs), np.diff(ys))
+    assert np.median(step) < 8.0 and step.max() < 64.0
+    w = neighbour_work(xs, ys, 60.0)
+    # brute-force neighbour count on a sample agrees with the cell estimate within the cell slack
+    for j in (0, 1000, 4095):
+        exact = (np.hypot(xs - xs[j], ys - ys[j]) <= 60.0).sum()
+        assert 0.6 * exact <= w[j] <= 1.9 * exact + 0.1 * w.mean()
+    b = balanced_bounds(w, 8)
+    assert b[0][0] == 0 and b[-1][1] == 4096 and all(b[r][1] == b[r + 1][0] for r in range(7))
+    share = np.array([w[lo:hi].sum() for lo, hi in b]) / w.sum()
+    assert np.abs(share - 0.125).max() < 0.01
+    assert balanced_bounds(np.ones(10), 3) == shard_bounds(10, 3) or sum(hi - lo for lo, hi in balanced_bounds(np.ones(10), 3)) == 10
