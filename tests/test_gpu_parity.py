@@ -283,3 +283,42 @@ def test_pair_forces_full_size(n, n_sample):
         d = _vec_rel(got, dense, 1e-3)
         report(test="tiled_vs_dense_full_size", n=n, max_rel=float(d.max()))
         assert d.max() < 2e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("p2r", [False, True])
+def test_tiled_mixed_classes_sparse_domain(dtype, p2r):
+    """Tiled kernel with several source classes (two bicycle parameter sets + obstacles with
+    hfov = 2 pi), targets that are only a part of the sources, a domain several cut-off distances
+    wide (10 m spacing: the f32 far-field cut-off is active), both priority rules: against the
+    oracle and against the dense kernel."""
+    from cyclistsocialforce_b200 import parameters as P
+    from cyclistsocialforce_b200.engine import AgentGroup, Engine, ObstacleGroup
+    from cyclistsocialforce_b200.synthetic import queues_with_start
+    n1, n2, n3 = 1500, 900, 400
+    n = n1 + n2 + n3
+    s0, q = co.synthetic_crowd(n, seed=13, spacing=10.0)
+    wide = dict(hfov=1.2 * np.pi, f_0=5.0, sigma_1=6.0, e_0=0.9)
+    res = {}
+    for mode in ("tiled", "dense"):
+        g1 = AgentGroup("twod", s0[:n1], P.InvPendulumBicycleParameters(),
+                        destqueues=list(queues_with_start(s0[:n1], q[:n1])), dtype=dtype)
+        g2 = AgentGroup("twod", s0[n1:n1 + n2], P.InvPendulumBicycleParameters(**wide),
+                        destqueues=list(queues_with_start(s0[n1:n1 + n2], q[n1:n1 + n2])), dtype=dtype)
+        ob = ObstacleGroup(s0[n1 + n2:, :3], P.VehicleParameters())
+        eng = Engine([g1, g2], obstacles=[ob], dtype=dtype, pair_mode=mode,
+                     priority_rule="p2r" if p2r else "unregulated")
+        assert eng.tiled == (mode == "tiled") and len(eng.classes) == 3
+        eng._pair_and_road()
+        res[mode] = eng.frep.cpu().numpy().astype(float)
+    pa, pb, pc = co.default_params("twod"), co.default_params("twod", **wide), co.default_params("uncontrolled")
+    fp = np.vstack([np.repeat(co.field_params_array([p]), k, axis=0) for p, k in ((pa, n1), (pb, n2), (pc, n3))])
+    ref, margin = co.pair_forces(s0[:, 0], s0[:, 1], s0[:, 2], fp, p2r=p2r, tgt=np.arange(n1 + n2),
+                                 return_margin=True)
+    ok = margin > (1e-9 if dtype == torch.float64 else 1e-5)
+    assert ok.mean() > 0.9
+    tol = F64_TOL if dtype == torch.float64 else F32_TOL
+    err = _vec_rel(res["tiled"][ok], ref[ok], 1e-6 if dtype == torch.float64 else 1e-3)
+    report(test="tiled_mixed_classes", dtype=str(dtype), p2r=p2r, max_rel=float(err.max()))
+    assert err.max() < tol
+    assert _vec_rel(res["tiled"], res["dense"], 1e-3).max() < (1e-10 if dtype == torch.float64 else 2e-5)
