@@ -42,7 +42,7 @@ constexpr int kTileS = 64;               // sources per tile (2 per lane)
 constexpr int kCT = 16;                  // tiles per chunk = one shared-memory stage
 constexpr int kCS = kCT * kTileS;        // sources per chunk
 constexpr int kTMaxGroups = 64;
-template <typename T> struct Stages { static constexpr int n = sizeof(T) == 4 ? 4 : 3; };
+template <typename T> struct Stages { static constexpr int n = 3; };
 
 template <typename T> struct Tile;
 template <> struct __align__(16) Tile<float> { int32_t cx, cy; float R; int32_t cnt; };
@@ -57,9 +57,14 @@ template <> struct __align__(16) SrcA<double> { double x0, x1, y0, y1; };
 template <typename T> struct __align__(16) SrcB { T c0, c1, s0, s1; };
 template <typename T> struct TileBytes { static constexpr size_t v = (size_t)kTileS * sizeof(Xycs<T>); };
 
+constexpr int kLobeBins = 64;
 template <typename T> struct CullConst {
     T ca, sa;    // cos / sin of hfov/2
     T dmax;      // cut-off distance d_cut in payload units (huge: never)
+    // reach of a source's field in the direction phi (measured from its heading), as a step function of
+    // cos(phi): lobe[b] >= max distance at which |F| >= 2^-cutoff_log2 f_0 for any phi' with
+    // cos(phi') <= -1 + (b+1) 2/kLobeBins and any heading difference (payload units; huge: never)
+    T lobe[kLobeBins];
 };
 
 __device__ __forceinline__ void split(const Xycs<float>& a, const Xycs<float>& b, SrcA<float>& A, SrcB<float>& B) {
@@ -299,6 +304,42 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
     return v;
 }
 
+__device__ __forceinline__ int32_t pos_x(const Xycs<float>& e) { return e.xq; }
+__device__ __forceinline__ int32_t pos_y(const Xycs<float>& e) { return e.yq; }
+__device__ __forceinline__ double pos_x(const Xycs<double>& e) { return e.x; }
+__device__ __forceinline__ double pos_y(const Xycs<double>& e) { return e.y; }
+
+// ---- lobe filter: can source (x, y, heading c, s) matter for ANY target inside the block circle? ----
+// d = distance source -> block centre, phi0 = its direction seen from the source's heading, delta =
+// half angle under which the source sees the circle.  Every point of the circle lies in a direction
+// |phi| >= |phi0| - delta at a distance >= d - R_b, and the reach is tabulated as a non-decreasing step
+// function of cos(phi): the source cannot matter if d - R_b exceeds the reach at cos(|phi0| - delta).
+__device__ __forceinline__ void block_delta(const Tile<float>& b, int32_t x, int32_t y, float& dx, float& dy) {
+    dx = (float)(b.cx - x);
+    dy = (float)(b.cy - y);
+}
+__device__ __forceinline__ void block_delta(const Tile<double>& b, double x, double y, double& dx, double& dy) {
+    dx = b.cx - x;
+    dy = b.cy - y;
+}
+template <typename T, typename P>
+__device__ __forceinline__ bool lobe_reaches(const Tile<T>& blk, P x, P y, T c, T s, const T* __restrict__ lobe, T tiny) {
+    T dx, dy;
+    block_delta(blk, x, y, dx, dy);
+    const T d2 = fma(dy, dy, fma(dx, dx, tiny));
+    const T rinv = M<T>::rsqrt(d2);
+    const T d = d2 * rinv;
+    const T Rb = (T)blk.R;
+    const T cphi = fma(dy, s, dx * c) * rinv;
+    const T sphi = fabs(fma(dy, c, -(dx * s))) * rinv;
+    const T sdel = fmin(Rb * rinv, (T)1);
+    const T cdel = M<T>::sqrt(fmax(fma(-sdel, sdel, (T)1), (T)0));
+    T cmin = fma(cphi, cdel, sphi * sdel);                 // cos(|phi0| - delta)
+    cmin = (cphi >= cdel) ? (T)1 : cmin;                   // the circle straddles the heading direction
+    const int bin = min(max((int)((cmin + (T)1.00002) * (T)(kLobeBins / 2)), 0), kLobeBins - 1);
+    return d - Rb <= lobe[bin] * (T)1.0001;
+}
+
 // named barrier 1 among the consumer warps only (the producer warp never joins)
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kTW * 32) : "memory"); }
 
@@ -319,11 +360,15 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
     constexpr size_t kStageBytes = (size_t)kCS * sizeof(Xycs<T>) + (size_t)kCT * sizeof(Tile<T>);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * kStageBytes);
     uint64_t* empty = full + kStages;
-    uint64_t* cbar = empty + kStages;                                               // consumers' own barrier
-    int4* hdr = reinterpret_cast<int4*>(cbar + 2);                                  // {item, chunk, list length, next}
-    Xycs<T>* btgt = reinterpret_cast<Xycs<T>*>(hdr + kStages);                      // [kTB] targets of the block
-    T* bacc = reinterpret_cast<T*>(btgt + kTB);                                     // [2][kTB][2] sums (chunk parity)
-    uint32_t* wlist = reinterpret_cast<uint32_t*>(bacc + 2 * kTB * 2);              // [kStages][kTB] (q << 16) | tile mask
+    int4* hdr = reinterpret_cast<int4*>(empty + kStages);                           // {item, chunk, -, -}
+    unsigned char* sbuf = reinterpret_cast<unsigned char*>(hdr + kStages);          // survivors: one chunk in tile layout
+    Tile<T>* dtile = reinterpret_cast<Tile<T>*>(sbuf + (size_t)kCS * sizeof(Xycs<T>));      // [kCT] their circles
+    Xycs<T>* btgt = reinterpret_cast<Xycs<T>*>(dtile + kCT);                        // [kTB] targets of the block
+    T* bacc = reinterpret_cast<T*>(btgt + kTB);                                     // [kTB][2] their sums
+    T* lobe = bacc + kTB * 2;                                                       // [kLobeBins] reach table
+    uint32_t* wlist = reinterpret_cast<uint32_t*>(lobe + kLobeBins);                // [kTB] (q << 16) | tile mask
+    uint2* fmask = reinterpret_cast<uint2*>(wlist + kTB);                           // [kStages][kCT] filter ballots
+    int* lctl = reinterpret_cast<int*>(fmask + kStages * kCT);                      // list length, next entry
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -331,9 +376,9 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kTW);
         }
-        mbar_init(cbar, kTW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int i = threadIdx.x; i < kLobeBins; i += blockDim.x) lobe[i] = cc.lobe[i];
     __syncthreads();
 
     const unsigned int n_items = (unsigned int)n_tblocks * (unsigned int)n_groups;
@@ -398,38 +443,38 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
     }
 
     // ===== consumer warps =====
-    // Per chunk: (1) cull -- every warp tests its own tpw targets against the chunk's 16 tiles, two
-    // targets per pass (lanes 0-15 / 16-31), and appends the non-empty (target, tile mask) entries to the
-    // stage's work list; (2) evaluate -- warps take entries from the list one at a time (shared
-    // counter), so a chunk's work is balanced over the CTA whatever the targets' headings.
-    // The two phases are software pipelined: a warp culls chunk k+1 and *arrives* on the consumers'
-    // barrier, evaluates chunk k, and only then *waits* for the barrier -- by then every warp has long
-    // finished its cull, so nobody idles at the phase boundary.  Chunks k and k+1 can therefore be in
-    // evaluation at the same time (never k and k+2): their sums go to two accumulator sets selected by
-    // the chunk's parity.  One warp per (target, chunk), chunks of one parity in sequence ->
-    // deterministic sums without atomics on floats.
-    uint32_t it = 0, cpar = 0;
+    // Per streamed chunk: (1) filter -- every source is tested against the target block's circle with
+    // the lobe test (lobe_reaches): most sources of a chunk near the block cannot matter for any of its
+    // targets, because a source's field reaches far only in a narrow range of directions; the
+    // survivors are appended, in stream order, to a shared-memory buffer that holds one chunk's worth
+    // (16 dynamic tiles of 64) in the same tile layout.  When the buffer would overflow, and when the
+    // item closes, it is flushed: (2) bounding circles of the dynamic tiles, (3) cull -- every warp
+    // tests its own targets' view cones against the 16 circles, two targets per pass, and appends
+    // (target, tile mask) entries to a work list, (4) evaluate -- warps take entries from the list one
+    // at a time (shared counter; the targets' headings make the per-target work very uneven).
+    // One warp per (target, flush), flushes separated by barriers: deterministic sums, no float atomics.
+    uint32_t it = 0;
     unsigned long long n_eval = 0;
-    int cur = -1, cg = 0, nq = 0;
+    int cur = -1, cg = 0, nq = 0, count = 0;
     const int q0 = warp * tpw;           // this warp's targets in the block: [q0, q0 + nq)
     long long myj = -1;
-    auto consumers_arrive = [&]() {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(cbar);
+    Tile<T> blk;                         // bounding circle of the block's targets
+    typedef decltype(SrcA<T>().x0) P;    // payload position type
+
+    auto write_entry = [&](int kidx, P x, P y, T c, T s) {
+        unsigned char* tb = sbuf + (size_t)(kidx >> 6) * TileBytes<T>::v;
+        const int r = kidx & 63, l = r & 31, h = r >> 5;
+        P* pa = reinterpret_cast<P*>(reinterpret_cast<SrcA<T>*>(tb) + l);
+        T* pb = reinterpret_cast<T*>(reinterpret_cast<SrcB<T>*>(tb + 32 * sizeof(SrcA<T>)) + l);
+        pa[h] = x;
+        pa[2 + h] = y;
+        pb[h] = c;
+        pb[2 + h] = s;
     };
-    auto consumers_wait = [&]() {
-        mbar_wait(cbar, cpar);
-        cpar ^= 1;
-    };
-    auto cull = [&](int stage, int chunk) {
-        const int nt = (int)min((int64_t)kCT, n_tiles - (int64_t)chunk * kCT);
-        const unsigned char* base = smem_raw + stage * kStageBytes;
-        const Tile<T>* trec = reinterpret_cast<const Tile<T>*>(base + (size_t)kCS * sizeof(Xycs<T>));
-        uint32_t* list = wlist + stage * kTB;
-        int* lcount = &hdr[stage].z;
+    auto cull = [&](int nt) {
         const int tl = lane & (kCT - 1), half = lane >> 4;
         Tile<T> mytile;
-        if (tl < nt) mytile = trec[tl];
+        if (tl < nt) mytile = dtile[tl];
         for (int i0 = 0; i0 < nq; i0 += 2) {          // warp-uniform trip count (ballot inside)
             const int i = i0 + half;
             const bool valid = (i < nq) && (tl < nt);
@@ -439,23 +484,20 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
             const uint32_t m2 = __ballot_sync(0xffffffffu, v);
             const uint32_t m = half ? (m2 >> 16) : (m2 & 0xffffu);
             if (tl == 0 && m) {
-                list[atomicAdd(lcount, 1)] = ((uint32_t)(q0 + i) << 16) | m;
+                wlist[atomicAdd(&lctl[0], 1)] = ((uint32_t)(q0 + i) << 16) | m;
                 if (stats) n_eval += (unsigned long long)__popc(m) * kTileS;
             }
         }
     };
-    auto evaluate = [&](int stage, int par) {
-        const unsigned char* base = smem_raw + stage * kStageBytes;
-        const uint32_t* list = wlist + stage * kTB;
-        const int n_list = hdr[stage].z;
-        int* lnext = &hdr[stage].w;
-        T* acc = bacc + par * kTB * 2;
+    auto evaluate = [&]() {
+        const unsigned char* base = sbuf;
+        const int n_list = lctl[0];
         for (;;) {
             int e = 0;
-            if (lane == 0) e = atomicAdd(lnext, 1);
+            if (lane == 0) e = atomicAdd(&lctl[1], 1);
             e = __shfl_sync(0xffffffffu, e, 0);
             if (e >= n_list) break;
-            const uint32_t ent = list[e];
+            const uint32_t ent = wlist[e];
             const int q = (int)(ent >> 16);
             uint32_t mask = ent & 0xffffu;
             const Xycs<T> te = btgt[q];
@@ -493,9 +535,36 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
             mine += __shfl_xor_sync(0xffffffffu, other, 16);
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-            if ((lane & 15) == 0) acc[q * 2 + (lane >> 4)] += mine;
+            if ((lane & 15) == 0) bacc[q * 2 + (lane >> 4)] += mine;
         }
     };
+    // evaluate the `count` survivors in the buffer against every target of the block
+    auto flush = [&]() {
+        consumer_barrier();                                   // every append has landed
+        const int n_dt = (count + kTileS - 1) / kTileS;
+        {   // pad the last dynamic tile with far-away sentinels (they contribute exactly 0)
+            Xycs<T> pad;
+            pad_entry(pad);
+            for (int kidx = count + (int)threadIdx.x; kidx < n_dt * kTileS; kidx += kTW * 32)
+                write_entry(kidx, pos_x(pad), pos_y(pad), pad.c, pad.s);
+        }
+        if (threadIdx.x == 0) { lctl[0] = 0; lctl[1] = 0; }
+        for (int t = warp; t < n_dt; t += kTW) {              // circles of the dynamic tiles
+            const int valid = min(kTileS, count - t * kTileS);
+            const SrcA<T> A = reinterpret_cast<const SrcA<T>*>(sbuf + (size_t)t * TileBytes<T>::v)[lane];
+            BBox<T> bb;
+            if (lane < valid) bb.add(A.x0, A.y0);
+            if (lane + 32 < valid) bb.add(A.x1, A.y1);
+            bb.warp_reduce();
+            if (lane == 0) dtile[t] = bb.circle(valid);
+        }
+        consumer_barrier();
+        cull(n_dt);
+        consumer_barrier();
+        evaluate();
+        consumer_barrier();                                   // the buffer may be overwritten again
+    };
+
     for (;;) {
         const int stage = it % kStages;
         mbar_wait(&full[stage], (it / kStages) & 1);
@@ -506,54 +575,74 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
             cur = item;
             const int tb = cur % n_tblocks;
             cg = cur / n_tblocks;
+            blk = tblocks[tb];
             const int64_t t_first = ((int64_t)tb * kTW + warp) * tpw;
             const int64_t left = n_tgt - t_first;
             nq = (int)(left < 0 ? 0 : (left < tpw ? left : tpw));
             myj = -1;
+            count = 0;
             if (lane < nq) {
                 myj = tgt_perm ? tgt_perm[t_first + lane] : (t_first + lane);
                 btgt[q0 + lane] = tgt[myj];
             }
-            if (lane < 2 * nq) {
-                bacc[q0 * 2 + lane] = (T)0;
-                bacc[kTB * 2 + q0 * 2 + lane] = (T)0;
-            }
+            if (lane < 2 * nq) bacc[q0 * 2 + lane] = (T)0;
             __syncwarp();
         }
         if (chunk == -1) {
-            // close the item: once every warp has finished adding, write this warp's targets
-            consumers_arrive();
-            consumers_wait();
+            // close the item: evaluate what is left in the buffer, then write this warp's targets
+            if (count > 0) flush();
+            count = 0;
             const long long jj = __shfl_sync(0xffffffffu, myj, (lane >> 1) & (kMaxTPW - 1));
-            if ((lane >> 1) < nq)
-                partial[((size_t)cg * n_tgt + (size_t)jj) * 2 + (lane & 1)] =
-                    bacc[q0 * 2 + lane] + bacc[kTB * 2 + q0 * 2 + lane];
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
-            ++it;
-            continue;
-        }
-        // first chunk of the item: cull, then a full barrier
-        cull(stage, chunk);
-        consumers_arrive();
-        consumers_wait();
-        for (int par = 0;; par ^= 1) {
-            // the work list of stage (it % kStages) is complete; look at the next stream element
-            const int s0 = it % kStages, s1 = (it + 1) % kStages;
-            mbar_wait(&full[s1], ((it + 1) / kStages) & 1);
-            const int c1 = hdr[s1].y;
-            const bool more = c1 >= 0;               // another chunk of this item (a new item starts after -1)
-            if (more) {
-                cull(s1, c1);
-                consumers_arrive();
+            if ((lane >> 1) < nq) partial[((size_t)cg * n_tgt + (size_t)jj) * 2 + (lane & 1)] = bacc[q0 * 2 + lane];
+        } else {
+            const int nt = (int)min((int64_t)kCT, n_tiles - (int64_t)chunk * kCT);
+            const unsigned char* base = smem_raw + stage * kStageBytes;
+            const Tile<T>* trec = reinterpret_cast<const Tile<T>*>(base + (size_t)kCS * sizeof(Xycs<T>));
+            uint2* fm = fmask + stage * kCT;
+            // (1a) filter: this warp's tiles of the chunk
+            for (int t = warp; t < kCT; t += kTW) {
+                uint32_t b0 = 0, b1 = 0;
+                if (t < nt) {
+                    const int valid = (int)trec[t].cnt;
+                    const SrcA<T> A = reinterpret_cast<const SrcA<T>*>(base + (size_t)t * TileBytes<T>::v)[lane];
+                    const SrcB<T> B = reinterpret_cast<const SrcB<T>*>(base + (size_t)t * TileBytes<T>::v + 32 * sizeof(SrcA<T>))[lane];
+                    const bool p0 = (lane < valid) && lobe_reaches<T, P>(blk, A.x0, A.y0, B.c0, B.s0, lobe, k.tiny);
+                    const bool p1 = (lane + 32 < valid) && lobe_reaches<T, P>(blk, A.x1, A.y1, B.c1, B.s1, lobe, k.tiny);
+                    b0 = __ballot_sync(0xffffffffu, p0);
+                    b1 = __ballot_sync(0xffffffffu, p1);
+                }
+                if (lane == 0) fm[t] = make_uint2(b0, b1);
             }
-            evaluate(s0, par);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s0]);
-            ++it;
-            if (!more) break;
-            consumers_wait();
+            consumer_barrier();
+            // (1b) append in stream order: prefix over the chunk's 16 tiles (every warp computes it)
+            const uint2 mm = fm[lane & (kCT - 1)];
+            const int c16 = __popc(mm.x) + __popc(mm.y);
+            int incl = c16;
+#pragma unroll
+            for (int o = 1; o < kCT; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((lane & (kCT - 1)) >= o) incl += v;
+            }
+            const int tot = __shfl_sync(0xffffffffu, incl, kCT - 1);
+            if (count + tot > kCS) {                          // warp-uniform and the same in every warp
+                flush();
+                count = 0;
+            }
+            for (int t = warp; t < nt; t += kTW) {
+                const int off = count + __shfl_sync(0xffffffffu, incl - c16, t);
+                const uint32_t b0 = __shfl_sync(0xffffffffu, mm.x, t), b1 = __shfl_sync(0xffffffffu, mm.y, t);
+                if ((b0 | b1) == 0) continue;
+                const SrcA<T> A = reinterpret_cast<const SrcA<T>*>(base + (size_t)t * TileBytes<T>::v)[lane];
+                const SrcB<T> B = reinterpret_cast<const SrcB<T>*>(base + (size_t)t * TileBytes<T>::v + 32 * sizeof(SrcA<T>))[lane];
+                const uint32_t lt = (1u << lane) - 1u;
+                if ((b0 >> lane) & 1u) write_entry(off + __popc(b0 & lt), A.x0, A.y0, B.c0, B.s0);
+                if ((b1 >> lane) & 1u) write_entry(off + __popc(b0) + __popc(b1 & lt), A.x1, A.y1, B.c1, B.s1);
+            }
+            count += tot;
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        ++it;
     }
     if (stats && n_eval) atomicAdd(stats, n_eval);
 }
@@ -572,8 +661,10 @@ __global__ void reduce_groups_kernel(const T* __restrict__ partial, int n_groups
 template <typename T> size_t tiled_smem_bytes() {
     constexpr int kStages = Stages<T>::n;
     return kStages * ((size_t)kCS * sizeof(Xycs<T>) + (size_t)kCT * sizeof(Tile<T>)) +
-           (2 * kStages + 2) * sizeof(uint64_t) + kStages * sizeof(int4) + (size_t)kTB * sizeof(Xycs<T>) +
-           (size_t)2 * kTB * 2 * sizeof(T) + (size_t)kStages * kTB * sizeof(uint32_t);
+           2 * kStages * sizeof(uint64_t) + kStages * sizeof(int4) +
+           (size_t)kCS * sizeof(Xycs<T>) + (size_t)kCT * sizeof(Tile<T>) + (size_t)kTB * sizeof(Xycs<T>) +
+           (size_t)kTB * 2 * sizeof(T) + (size_t)kLobeBins * sizeof(T) + (size_t)kTB * sizeof(uint32_t) +
+           (size_t)kStages * kCT * sizeof(uint2) + 4 * sizeof(int);
 }
 
 int g_tiled_ctas[2] = {0, 0};
@@ -664,26 +755,69 @@ double field_min_decay_rate(const CsfFieldParams* fp) {
     return best < 1e300 ? best : 0.0;
 }
 
+// Per c-cell lower bound of the decay rate (min over all heading differences), same interval
+// arithmetic as field_min_decay_rate; rate_c[j] covers cos(phi) in [-1 + 2j/NC, -1 + 2(j+1)/NC].
+// Returns false if the field has no positive bound somewhere.
+bool field_decay_rate_by_angle(const CsfFieldParams* fp, int NC, double* rate_c) {
+    const int NS = 256;
+    for (int j = 0; j < NC; ++j) rate_c[j] = 1e300;
+    for (int i = 0; i < NS; ++i) {
+        const double s_lo = (double)i / NS, s_hi = (double)(i + 1) / NS;
+        const double e_a = fp->e_0 - fp->e_1 * s_lo, e_b = fp->e_0 - fp->e_1 * s_hi;
+        const double emax = fmax(fabs(e_a), fabs(e_b));
+        const double A_hi = fmax(fp->sigma_0 + fp->sigma_1 * s_lo, fp->sigma_0 + fp->sigma_1 * s_hi);
+        const double B_a = fp->sigma_2 + fp->sigma_3 * s_lo, B_b = fp->sigma_2 + fp->sigma_3 * s_hi;
+        for (int j = 0; j < NC; ++j) {
+            const double c_lo = -1.0 + 2.0 * j / NC, c_hi = -1.0 + 2.0 * (j + 1) / NC;
+            const double cmax = fmax(fabs(c_lo), fabs(c_hi));
+            const double q2 = 1.0 - emax * emax * cmax * cmax;
+            if (!(q2 > 0.0)) return false;
+            const double h_lo = sqrt(fmax(0.0, (1.0 - c_hi) * 0.5)), h_hi = sqrt(fmax(0.0, (1.0 - c_lo) * 0.5));
+            const double bh = fmin(fmin(B_a * h_lo, B_a * h_hi), fmin(B_b * h_lo, B_b * h_hi));
+            const double sig_hi = A_hi - bh;
+            if (!(sig_hi > 0.0)) return false;
+            rate_c[j] = fmin(rate_c[j], sqrt(q2) / sig_hi);
+        }
+    }
+    return true;
+}
+
 template <typename T> CullConst<T> make_cull(const CsfFieldParams* fp, bool is_f32) {
     CullConst<T> c;
     const double a = fmin(fp->hfov * 0.5, CSF_PI);
     c.ca = (T)cos(a);
     c.sa = (T)sin(a);
     if (a >= CSF_PI) { c.ca = (T)-1; c.sa = (T)0; }
-    c.dmax = (T)(is_f32 ? 3.0e9 : 1e150);                 // never (payload positions span < 2^31 units)
+    const T never = (T)(is_f32 ? 3.0e9 : 1e150);          // (payload positions span < 2^31 units)
+    c.dmax = never;
+    for (int b = 0; b < kLobeBins; ++b) c.lobe[b] = never;
     if (is_f32) {
-        // exp(-d * rate) = 2^-cutoff_log2  ->  d_cut; cached per parameter set
+        // exp(-d * rate) = 2^-cutoff_log2  ->  reach d; cached per parameter set
+        constexpr int NC = 512;
         static CsfFieldParams cached;
-        static double cached_rate = -1.0;
+        static double cached_rate = -1.0, cached_rate_c[NC];
+        static bool cached_ok = false;
         if (cached_rate < 0.0 || cached.e_0 != fp->e_0 || cached.e_1 != fp->e_1 || cached.sigma_0 != fp->sigma_0 ||
             cached.sigma_1 != fp->sigma_1 || cached.sigma_2 != fp->sigma_2 || cached.sigma_3 != fp->sigma_3) {
             cached = *fp;
             cached_rate = field_min_decay_rate(fp);
+            cached_ok = field_decay_rate_by_angle(fp, NC, cached_rate_c);
         }
         const double bits = fp->cutoff_log2 > 0.0 ? fp->cutoff_log2 : 40.0;
-        if (cached_rate > 0.0) {
-            const double d_units = bits * 0.6931471805599453 / cached_rate * 1.0001 / fp->q_scale;
-            if (d_units < 3.0e9) c.dmax = (T)d_units;
+        const double L = bits * 0.6931471805599453 * 1.0001 / fp->q_scale;
+        if (cached_rate > 0.0 && L / cached_rate < 3.0e9) {
+            c.dmax = (T)(L / cached_rate);
+            if (cached_ok) {
+                // lobe[b] = max reach over all cells with cos(phi) below the bin's upper edge
+                double run = 0.0;
+                const int per = NC / kLobeBins;
+                for (int b = 0; b < kLobeBins; ++b) {
+                    for (int j = b * per; j < (b + 1) * per; ++j) run = fmax(run, L / cached_rate_c[j]);
+                    c.lobe[b] = (T)fmin(run, (double)c.dmax);
+                }
+            } else {
+                for (int b = 0; b < kLobeBins; ++b) c.lobe[b] = c.dmax;
+            }
         }
     }
     return c;
