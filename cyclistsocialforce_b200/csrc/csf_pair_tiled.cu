@@ -599,10 +599,15 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
             const unsigned char* base = smem_raw + stage * kStageBytes;
             const Tile<T>* trec = reinterpret_cast<const Tile<T>*>(base + (size_t)kCS * sizeof(Xycs<T>));
             uint2* fm = fmask + stage * kCT;
-            // (1a) filter: this warp's tiles of the chunk
+            // (1a) filter: this warp's tiles of the chunk; tiles wholly out of reach of the block first
+            uint32_t tnear;
+            {
+                const int tl = lane & (kCT - 1);
+                tnear = __ballot_sync(0xffffffffu, tl < nt && circles_near(trec[tl < nt ? tl : 0], blk, cc.dmax));
+            }
             for (int t = warp; t < kCT; t += kTW) {
                 uint32_t b0 = 0, b1 = 0;
-                if (t < nt) {
+                if ((tnear >> t) & 1u) {
                     const int valid = (int)trec[t].cnt;
                     const SrcA<T> A = reinterpret_cast<const SrcA<T>*>(base + (size_t)t * TileBytes<T>::v)[lane];
                     const SrcB<T> B = reinterpret_cast<const SrcB<T>*>(base + (size_t)t * TileBytes<T>::v + 32 * sizeof(SrcA<T>))[lane];
