@@ -340,6 +340,43 @@ __device__ __forceinline__ bool lobe_reaches(const Tile<T>& blk, P x, P y, T c, 
     return d - Rb <= lobe[bin] * (T)1.0001;
 }
 
+// both sources of a lane at once; f32: the FP32 arithmetic packed two-wide (FFMA2), same operations
+__device__ __forceinline__ void lobe_reaches2(const Tile<float>& blk, const SrcA<float>& A, const SrcB<float>& B,
+                                              const float* __restrict__ lobe, float tiny, bool& r0, bool& r1) {
+    const F2 DX = pk((float)(blk.cx - A.x0), (float)(blk.cx - A.x1));
+    const F2 DY = pk((float)(blk.cy - A.y0), (float)(blk.cy - A.y1));
+    const F2 D2 = fma2(DY, DY, fma2(DX, DX, splat(tiny)));
+    float a0, a1;
+    up(D2, a0, a1);
+    const F2 RINV = pk(M<float>::rsqrt(a0), M<float>::rsqrt(a1));
+    const F2 D = mul2(D2, RINV);
+    const F2 SC = pk(B.c0, B.c1), SS = pk(B.s0, B.s1);
+    const F2 CPHI = mul2(fma2(DY, SS, mul2(DX, SC)), RINV);
+    const F2 SPHI = mul2(abs2(fma2(DY, SC, neg2(mul2(DX, SS)))), RINV);
+    const F2 SDELr = mul2(splat(blk.R), RINV);
+    up(SDELr, a0, a1);
+    const F2 SDEL = pk(fminf(a0, 1.f), fminf(a1, 1.f));
+    const F2 CD2 = fma2(neg2(SDEL), SDEL, splat(1.f));
+    up(CD2, a0, a1);
+    const float cd0 = M<float>::sqrt(fmaxf(a0, 0.f)), cd1 = M<float>::sqrt(fmaxf(a1, 0.f));
+    const F2 CMIN = fma2(CPHI, pk(cd0, cd1), mul2(SPHI, SDEL));
+    float c0, c1, p0, p1, d0, d1;
+    up(CMIN, c0, c1);
+    up(CPHI, p0, p1);
+    up(D, d0, d1);
+    c0 = (p0 >= cd0) ? 1.f : c0;
+    c1 = (p1 >= cd1) ? 1.f : c1;
+    const int b0 = min(max((int)((c0 + 1.00002f) * (float)(kLobeBins / 2)), 0), kLobeBins - 1);
+    const int b1 = min(max((int)((c1 + 1.00002f) * (float)(kLobeBins / 2)), 0), kLobeBins - 1);
+    r0 = d0 - blk.R <= lobe[b0] * 1.0001f;
+    r1 = d1 - blk.R <= lobe[b1] * 1.0001f;
+}
+__device__ __forceinline__ void lobe_reaches2(const Tile<double>& blk, const SrcA<double>& A, const SrcB<double>& B,
+                                              const double* __restrict__ lobe, double tiny, bool& r0, bool& r1) {
+    r0 = lobe_reaches<double, double>(blk, A.x0, A.y0, B.c0, B.s0, lobe, tiny);
+    r1 = lobe_reaches<double, double>(blk, A.x1, A.y1, B.c1, B.s1, lobe, tiny);
+}
+
 // named barrier 1 among the consumer warps only (the producer warp never joins)
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kTW * 32) : "memory"); }
 
@@ -611,10 +648,10 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                     const int valid = (int)trec[t].cnt;
                     const SrcA<T> A = reinterpret_cast<const SrcA<T>*>(base + (size_t)t * TileBytes<T>::v)[lane];
                     const SrcB<T> B = reinterpret_cast<const SrcB<T>*>(base + (size_t)t * TileBytes<T>::v + 32 * sizeof(SrcA<T>))[lane];
-                    const bool p0 = (lane < valid) && lobe_reaches<T, P>(blk, A.x0, A.y0, B.c0, B.s0, lobe, k.tiny);
-                    const bool p1 = (lane + 32 < valid) && lobe_reaches<T, P>(blk, A.x1, A.y1, B.c1, B.s1, lobe, k.tiny);
-                    b0 = __ballot_sync(0xffffffffu, p0);
-                    b1 = __ballot_sync(0xffffffffu, p1);
+                    bool p0, p1;
+                    lobe_reaches2(blk, A, B, lobe, k.tiny, p0, p1);
+                    b0 = __ballot_sync(0xffffffffu, p0 && (lane < valid));
+                    b1 = __ballot_sync(0xffffffffu, p1 && (lane + 32 < valid));
                 }
                 if (lane == 0) fm[t] = make_uint2(b0, b1);
             }
@@ -707,17 +744,21 @@ int env_int(const char* name, int dflt) {
 struct TiledPlan { int tpw, n_tblocks, n_groups, group_chunks, grid; int64_t n_tiles, n_chunks; };
 template <typename T> TiledPlan tiled_plan(int64_t n_src, int64_t n_tgt) {
     static const int env_tpw = env_int("CSF_TILED_TPW", 0), env_groups = env_int("CSF_TILED_GROUPS", 0),
-                     env_ipw = env_int("CSF_TILED_ITEMS_PER_SLOT", 8);
+                     env_ipw = env_int("CSF_TILED_ITEMS_PER_SLOT", 4);
     TiledPlan p;
     p.n_tiles = (n_src + kTileS - 1) / kTileS;
     p.n_chunks = (p.n_tiles + kCT - 1) / kCT;
     const int64_t slots = (int64_t)csf_sm_count() * tiled_ctas<T>();
     const int64_t want = (int64_t)env_ipw * slots;
-    int tpw = kMaxTPW;
+    // 64 targets per block balance the lobe filter's cost (per block) against its selectivity (block
+    // radius); smaller blocks only to give every CTA slot a few items
+    int tpw = 8;
     while (tpw > 4 && (n_tgt + (int64_t)kTW * tpw - 1) / ((int64_t)kTW * tpw) < want) tpw >>= 1;
     if (env_tpw >= 1 && env_tpw <= kMaxTPW) tpw = env_tpw;
     const int64_t tb = (n_tgt + (int64_t)kTW * tpw - 1) / ((int64_t)kTW * tpw);
-    int64_t groups = (want + tb - 1) / tb;
+    // splitting the chunk range of a block over several items repeats the block's set-up: only when
+    // there are fewer blocks than CTA slots (small shards)
+    int64_t groups = tb < slots ? (want + tb - 1) / tb : 1;
     if (env_groups >= 1) groups = env_groups;
     if (groups < 1) groups = 1;
     if (groups > kTMaxGroups) groups = kTMaxGroups;
