@@ -756,9 +756,9 @@ template <typename T> TiledPlan tiled_plan(int64_t n_src, int64_t n_tgt) {
     while (tpw > 4 && (n_tgt + (int64_t)kTW * tpw - 1) / ((int64_t)kTW * tpw) < want) tpw >>= 1;
     if (env_tpw >= 1 && env_tpw <= kMaxTPW) tpw = env_tpw;
     const int64_t tb = (n_tgt + (int64_t)kTW * tpw - 1) / ((int64_t)kTW * tpw);
-    // splitting the chunk range of a block over several items repeats the block's set-up: only when
-    // there are fewer blocks than CTA slots (small shards)
-    int64_t groups = tb < slots ? (want + tb - 1) / tb : 1;
+    // splitting the chunk range of a block over several items repeats the block's set-up and splits its
+    // survivor buffer: only when there are far fewer blocks than CTA slots (small crowds)
+    int64_t groups = 2 * tb < slots ? (slots + tb - 1) / tb : 1;
     if (env_groups >= 1) groups = env_groups;
     if (groups < 1) groups = 1;
     if (groups > kTMaxGroups) groups = kTMaxGroups;
