@@ -227,9 +227,14 @@ __global__ void block_bounds_kernel(const Xycs<T>* __restrict__ tgt, const int64
 // keys; any order gives correct results).  Consecutive runs of a Hilbert order are compact -- the mean
 // bounding radius of a 64-source tile is 27 m at 4 m spacing against 40 m for a Morton order, which
 // is 23 % fewer evaluated pairs after culling.
-__device__ __forceinline__ void key_xy(const Xycs<float>& e, double, double, double, uint32_t& kx, uint32_t& ky) {
-    kx = min(((uint32_t)(e.xq + (1 << 30))) >> 15, 65535u);  // 16 bits of the 31-bit range
-    ky = min(((uint32_t)(e.yq + (1 << 30))) >> 15, 65535u);
+// (x0, y0) = lower corner of the crowd's bounding box, inv_cell = 65535 / its larger side, both in
+// payload units: the curve then covers exactly the occupied region.  With a fixed, larger key domain
+// the few road users that drift across one of its quadrant boundaries sort far away from their
+// neighbours and blow up the bounding circles of the tiles and target blocks they land in.
+__device__ __forceinline__ void key_xy(const Xycs<float>& e, double x0, double y0, double inv_cell, uint32_t& kx,
+                                       uint32_t& ky) {
+    kx = (uint32_t)fmin(fmax(((double)e.xq - x0) * inv_cell, 0.0), 65535.0);
+    ky = (uint32_t)fmin(fmax(((double)e.yq - y0) * inv_cell, 0.0), 65535.0);
 }
 __device__ __forceinline__ void key_xy(const Xycs<double>& e, double x0, double y0, double inv_cell, uint32_t& kx,
                                        uint32_t& ky) {
@@ -751,14 +756,16 @@ template <typename T> TiledPlan tiled_plan(int64_t n_src, int64_t n_tgt) {
     const int64_t slots = (int64_t)csf_sm_count() * tiled_ctas<T>();
     const int64_t want = (int64_t)env_ipw * slots;
     // 64 targets per block balance the lobe filter's cost (per block) against its selectivity (block
-    // radius); smaller blocks only to give every CTA slot a few items
+    // radius).  Items must be plentiful -- a few per CTA slot -- because their cost follows the local
+    // density of the crowd (a jammed cluster costs several times the mean) and an item is the unit of
+    // dynamic scheduling: when there are too few blocks, the chunk range of each block is split over
+    // several items (each chunk is still filtered once per block).
     int tpw = 8;
-    while (tpw > 4 && (n_tgt + (int64_t)kTW * tpw - 1) / ((int64_t)kTW * tpw) < want) tpw >>= 1;
+    while (tpw > 1 && (int64_t)kTW * tpw > 2 * n_tgt) tpw >>= 1;      // tiny crowds
     if (env_tpw >= 1 && env_tpw <= kMaxTPW) tpw = env_tpw;
     const int64_t tb = (n_tgt + (int64_t)kTW * tpw - 1) / ((int64_t)kTW * tpw);
-    // splitting the chunk range of a block over several items repeats the block's set-up and splits its
-    // survivor buffer: only when there are far fewer blocks than CTA slots (small crowds)
-    int64_t groups = 2 * tb < slots ? (slots + tb - 1) / tb : 1;
+    int64_t groups = (want + tb - 1) / tb;
+    if (groups > 8) groups = 8;
     if (env_groups >= 1) groups = env_groups;
     if (groups < 1) groups = 1;
     if (groups > kTMaxGroups) groups = kTMaxGroups;

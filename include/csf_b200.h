@@ -176,8 +176,10 @@ int csf_bicycle_eccentricity_f64(const double* v, int64_t n, double v_max, doubl
  * contribution is below 2^-cutoff_log2 f_0 (|F| = f_0 exp(-rho q/sigma), vehicle.py:1613-1648);
  * the f64 build never truncates.  Sources are passed as a spatially sorted, tile-padded copy
  * with one bounding record per tile of 64 and per chunk of 16 tiles:
- *   csf_morton_keys_*   : int64 Morton key per payload element (x0,y0,cell only used by _f64);
- *                         the caller sorts the keys (any sort) to obtain `perm`
+ *   csf_morton_keys_*   : int64 space-filling-curve key per payload element; (x0, y0) = lower corner
+ *                         of the road users' bounding box and cell = its larger side / 65535, in
+ *                         payload units (f32: integer position units, f64: metres); the caller
+ *                         sorts the keys (any sort) to obtain `perm`
  *   csf_tile_sources_*  : sorted <- xycs[perm[.]] (perm NULL = identity) in the kernel's tile
  *                         layout, csf_tiled_padded_sources(n) elements; tiles:
  *                         csf_tiled_num_tiles(n) records of csf_tiled_tile_bytes(elem) bytes

@@ -32,7 +32,7 @@ int main(int argc, char** argv) {
     }
     if (argc > 3) {  // tiled variant
         int64_t* keys; cudaMalloc(&keys, n * 8);
-        csf_morton_keys_f32(d, n, 0, 0, 1, keys, 0);
+        csf_morton_keys_f32(d, n, 0, 0, (4.0 * sqrt((double)n) / q) / 65535.0, keys, 0);   // key domain = bounding box
         std::vector<int64_t> hk(n), perm(n);
         cudaMemcpy(hk.data(), keys, n * 8, cudaMemcpyDeviceToHost);
         std::iota(perm.begin(), perm.end(), 0);
