@@ -253,6 +253,8 @@ def run(args, out):
     clocks = sampler.stop()
     step_ms = [a.elapsed_time(c) for a, c in ev]
     total_ms = sum(step_ms)
+    if os.environ.get("CSF_BENCH_DEBUG"):
+        print("per-step ms:", " ".join(f"{t:.3f}" for t in step_ms), file=sys.stderr, flush=True)
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

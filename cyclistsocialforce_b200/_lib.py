@@ -100,6 +100,8 @@ SIGNATURES = {
     "csf_pair_tiled_workspace_bytes": (_sz, [_i64, _i64, C.c_int]),
     "csf_morton_keys_f32": (C.c_int, [_vp, _i64, _dbl, _dbl, _dbl, _vp, _vp]),
     "csf_morton_keys_f64": (C.c_int, [_vp, _i64, _dbl, _dbl, _dbl, _vp, _vp]),
+    "csf_spatial_keys_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
+    "csf_spatial_keys_f64": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "csf_tile_sources_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "csf_tile_sources_f64": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "csf_pair_forces_tiled_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp]),

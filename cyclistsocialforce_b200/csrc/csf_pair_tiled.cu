@@ -256,9 +256,14 @@ __device__ __forceinline__ uint32_t hilbert_index(uint32_t x, uint32_t y) {
 }
 template <typename T>
 __global__ void morton_kernel(const Xycs<T>* __restrict__ xycs, int64_t n, double x0, double y0, double inv_cell,
-                              int64_t* __restrict__ keys) {
+                              const double* __restrict__ box, int64_t* __restrict__ keys) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (box) {      // {xmin, xmax, ymin, ymax} on the device: no host round trip
+        x0 = box[0];
+        y0 = box[2];
+        inv_cell = 65535.0 / fmax(fmax(box[1] - box[0], box[3] - box[2]), 1e-300);
+    }
     uint32_t kx, ky;
     key_xy(xycs[i], x0, y0, inv_cell, kx, ky);
     keys[i] = (int64_t)hilbert_index(kx, ky);
@@ -960,14 +965,28 @@ double csf_field_cutoff_distance(const CsfFieldParams* fp) {
 int csf_morton_keys_f32(const void* xycs, int64_t n, double x0, double y0, double cell, int64_t* keys, csf_stream_t st) {
     if (n <= 0) return 0;
     morton_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)st>>>((const Xycs<float>*)xycs, n, x0, y0,
-                                                                                  1.0 / cell, keys);
+                                                                                  1.0 / cell, nullptr, keys);
     CSF_CHECK_LAUNCH("morton_kernel");
     return 0;
 }
 int csf_morton_keys_f64(const void* xycs, int64_t n, double x0, double y0, double cell, int64_t* keys, csf_stream_t st) {
     if (n <= 0) return 0;
     morton_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)st>>>((const Xycs<double>*)xycs, n, x0,
-                                                                                   y0, 1.0 / cell, keys);
+                                                                                   y0, 1.0 / cell, nullptr, keys);
+    CSF_CHECK_LAUNCH("morton_kernel");
+    return 0;
+}
+int csf_spatial_keys_f32(const void* xycs, int64_t n, const double* box_dev, int64_t* keys, csf_stream_t st) {
+    if (n <= 0) return 0;
+    morton_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)st>>>((const Xycs<float>*)xycs, n, 0.0, 0.0,
+                                                                                  1.0, box_dev, keys);
+    CSF_CHECK_LAUNCH("morton_kernel");
+    return 0;
+}
+int csf_spatial_keys_f64(const void* xycs, int64_t n, const double* box_dev, int64_t* keys, csf_stream_t st) {
+    if (n <= 0) return 0;
+    morton_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)st>>>((const Xycs<double>*)xycs, n, 0.0,
+                                                                                   0.0, 1.0, box_dev, keys);
     CSF_CHECK_LAUNCH("morton_kernel");
     return 0;
 }

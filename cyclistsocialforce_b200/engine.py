@@ -435,26 +435,24 @@ class Engine:
         keys on the device (csf_morton_keys_*), sort by torch (plumbing), written into buffers whose
         addresses never change (a captured CUDA graph keeps pointing at them)."""
         st = self._stream()
-        # key domain = bounding box of all road users (one host round trip per re-sort): see key_xy
+        # key domain = bounding box of all road users, reduced and consumed on the device: see key_xy
         px, py = self.payload[:self.n_total, 0], self.payload[:self.n_total, 1]
-        box = torch.stack([px.min(), px.max(), py.min(), py.max()]).to(torch.float64).cpu().numpy()
-        span = float(max(box[1] - box[0], box[3] - box[2], 1e-9 if not self.f32 else 1.0))
-        self._key_box = (float(box[0]), float(box[2]), span / 65535.0)
+        self._key_box = torch.stack([px.min(), px.max(), py.min(), py.max()]).to(torch.float64)
         for ci, (s, c, _, fp) in enumerate(self.classes):
             if fp.field_kind == 1:
                 continue
             tl = self._tiles[ci]
             src = C.c_void_p(self.payload.data_ptr() + s * self.elem_bytes)
-            _lib.check(self._fn("csf_morton_keys")(src, c, self._key_box[0], self._key_box[1], self._key_box[2],
-                                                   _ptr(tl["keys"]), st), "csf_morton_keys")
+            _lib.check(self._fn("csf_spatial_keys")(src, c, _ptr(self._key_box), _ptr(tl["keys"]), st),
+                       "csf_spatial_keys")
             tl["perm"].copy_(torch.argsort(tl["keys"]))
             self.gpu_launches += 1
         if self._single_class:      # one class covering exactly the targets: same order
             self._tgt_perm = self._tiles[0]["perm"]
         else:
             tgt = C.c_void_p(self.payload.data_ptr() + self.global_offset * self.elem_bytes)
-            _lib.check(self._fn("csf_morton_keys")(tgt, self.n_agents, self._key_box[0], self._key_box[1],
-                                                   self._key_box[2], _ptr(self._tgt_keys), st), "csf_morton_keys")
+            _lib.check(self._fn("csf_spatial_keys")(tgt, self.n_agents, _ptr(self._key_box), _ptr(self._tgt_keys), st),
+                       "csf_spatial_keys")
             if self._tgt_perm is None:
                 self._tgt_perm = torch.zeros(self.n_agents, dtype=torch.int64, device=self.device)
             self._tgt_perm.copy_(torch.argsort(self._tgt_keys))

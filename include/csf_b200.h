@@ -196,6 +196,10 @@ int csf_morton_keys_f32(const void* xycs, int64_t n, double x0, double y0, doubl
                         csf_stream_t stream);
 int csf_morton_keys_f64(const void* xycs, int64_t n, double x0, double y0, double cell, int64_t* keys,
                         csf_stream_t stream);
+/* same keys with the bounding box {xmin, xmax, ymin, ymax} (payload units, double) read from DEVICE
+ * memory, so that a caller that reduces the box on the device needs no host round trip */
+int csf_spatial_keys_f32(const void* xycs, int64_t n, const double* box_dev, int64_t* keys, csf_stream_t stream);
+int csf_spatial_keys_f64(const void* xycs, int64_t n, const double* box_dev, int64_t* keys, csf_stream_t stream);
 int csf_tile_sources_f32(const void* xycs, int64_t n, const int64_t* perm, void* sorted, void* tiles,
                          csf_stream_t stream);
 int csf_tile_sources_f64(const void* xycs, int64_t n, const int64_t* perm, void* sorted, void* tiles,
