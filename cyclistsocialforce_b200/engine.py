@@ -284,7 +284,7 @@ class Engine:
 
     def __init__(self, groups, obstacles=None, priority_rule="unregulated", road_edges=(),
                  dtype=torch.float32, device="cuda", q_scale=None, extent=None, scenario_size=None,
-                 n_global=None, global_offset=0, exchange=None, pair_mode="auto", resort_every=32,
+                 n_global=None, global_offset=0, exchange=None, pair_mode="auto", resort_every=64,
                  count_pairs=False, graph=False):
         """``n_global`` / ``global_offset`` / ``exchange``: agent-range sharding of one crowd over
         several GPUs -- this engine owns agents [global_offset, global_offset + n) of an
