@@ -107,6 +107,7 @@ SIGNATURES = {
     "csf_pair_forces_tiled_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp]),
     "csf_pair_forces_tiled_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp]),
     "csf_field_cutoff_distance": (_dbl, [_FP]),
+    "csf_field_reach_table": (C.c_int, [_FP, C.c_int, C.POINTER(C.c_double)]),
     "csf_road_forces_f32": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _dbl, _dbl, _vp, C.c_int, _vp]),
     "csf_road_forces_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _dbl, _dbl, _vp, C.c_int, _vp]),
     "csf_agent_forces_f32": (C.c_int, [C.c_int, _AS, _AP, _i64, _vp, _vp, _vp, _vp, _vp]),

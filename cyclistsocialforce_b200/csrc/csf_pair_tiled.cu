@@ -962,6 +962,16 @@ double csf_field_cutoff_distance(const CsfFieldParams* fp) {
     const double bits = fp->cutoff_log2 > 0.0 ? fp->cutoff_log2 : 40.0;
     return rate > 0.0 ? bits * 0.6931471805599453 / rate : INFINITY;
 }
+int csf_field_reach_table(const CsfFieldParams* fp, int n_bins, double* reach_m) {
+    // host-only: the reach table of the lobe filter in metres (bin b covers cos(phi) in
+    // [-1 + 2b/n_bins, -1 + 2(b+1)/n_bins]); n_bins must be kLobeBins
+    if (n_bins != kLobeBins) return -1;
+    CsfFieldParams q = *fp;
+    if (!(q.q_scale > 0.0)) q.q_scale = 1.0;
+    const CullConst<float> c = make_cull<float>(&q, true);
+    for (int b = 0; b < kLobeBins; ++b) reach_m[b] = c.lobe[b] >= 2.9e9f ? INFINITY : (double)c.lobe[b] * q.q_scale;
+    return 0;
+}
 int csf_morton_keys_f32(const void* xycs, int64_t n, double x0, double y0, double cell, int64_t* keys, csf_stream_t st) {
     if (n <= 0) return 0;
     morton_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)st>>>((const Xycs<float>*)xycs, n, x0, y0,

@@ -192,6 +192,11 @@ int64_t csf_tiled_num_tiles(int64_t n_src);
 int csf_tiled_tile_bytes(int elem_bytes);
 size_t csf_pair_tiled_workspace_bytes(int64_t n_src, int64_t n_tgt, int elem_bytes);
 double csf_field_cutoff_distance(const CsfFieldParams* fp); /* metres; INFINITY if unbounded */
+/* host-only: the direction-dependent reach table the f32 kernel filters sources with, in metres:
+ * reach_m[b] >= the largest distance at which |F| >= 2^-cutoff_log2 f_0 for any direction phi
+ * (from the source's heading) with cos(phi) <= -1 + 2(b+1)/n_bins and any heading difference.
+ * n_bins must be 64.  Returns 0, or -1 for a wrong n_bins. */
+int csf_field_reach_table(const CsfFieldParams* fp, int n_bins, double* reach_m);
 int csf_morton_keys_f32(const void* xycs, int64_t n, double x0, double y0, double cell, int64_t* keys,
                         csf_stream_t stream);
 int csf_morton_keys_f64(const void* xycs, int64_t n, double x0, double y0, double cell, int64_t* keys,
