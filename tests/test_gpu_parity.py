@@ -322,3 +322,45 @@ def test_tiled_mixed_classes_sparse_domain(dtype, p2r):
     report(test="tiled_mixed_classes", dtype=str(dtype), p2r=p2r, max_rel=float(err.max()))
     assert err.max() < tol
     assert _vec_rel(res["tiled"], res["dense"], 1e-3).max() < (1e-10 if dtype == torch.float64 else 2e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_tiled_clusters_with_gaps(dtype):
+    """A crowd that is not compact: three clusters kilometres apart, of sizes that are not multiples of
+    the tile or block size, plus a few stragglers in between -- tiles, chunks and target blocks that
+    straddle a gap get huge bounding circles (everything passes the filters for them).  The tiled
+    kernel must still agree with the dense one and with the oracle."""
+    from cyclistsocialforce_b200 import parameters as P
+    from cyclistsocialforce_b200.engine import AgentGroup, Engine
+    from cyclistsocialforce_b200.synthetic import queues_with_start
+    parts = []
+    for k, (n, ox, oy) in enumerate(((1111, 0.0, 0.0), (777, 4000.0, -2500.0), (1300, -3000.0, 5000.0))):
+        s, q = co.synthetic_crowd(n, seed=40 + k, spacing=3.0)
+        s[:, 0] += ox; s[:, 1] += oy; q[..., 0] += ox; q[..., 1] += oy
+        parts.append((s, q))
+    s, q = co.synthetic_crowd(9, seed=50, spacing=900.0)      # stragglers
+    s[:, 0] -= 1000.0; q[..., 0] -= 1000.0
+    parts.append((s, q))
+    s0 = np.concatenate([p[0] for p in parts]); q = np.concatenate([p[1] for p in parts])
+    rng = np.random.default_rng(3)
+    sh = rng.permutation(len(s0)); s0, q = s0[sh], q[sh]
+    n = len(s0)
+    res = {}
+    for mode in ("tiled", "dense"):
+        g = AgentGroup("twod", s0, P.InvPendulumBicycleParameters(), destqueues=list(queues_with_start(s0, q)), dtype=dtype)
+        eng = Engine([g], dtype=dtype, pair_mode=mode)
+        eng._pair_and_road()
+        f0 = eng.frep.cpu().numpy().astype(float)
+        for _ in range(6):
+            eng.step()
+        eng.check_status()
+        res[mode] = (f0, g.states_numpy())
+    p = co.default_params("twod")
+    tj = np.arange(0, n, 7)
+    ref, margin = co.pair_forces(s0[:, 0], s0[:, 1], s0[:, 2], co.field_params_array([p])[0], tgt=tj, return_margin=True)
+    ok = margin > (1e-9 if dtype == torch.float64 else 1e-5)
+    err = _vec_rel(res["tiled"][0][tj][ok], ref[ok], 1e-6 if dtype == torch.float64 else 1e-3)
+    report(test="tiled_clusters_with_gaps", dtype=str(dtype), n=n, max_rel=float(err.max()))
+    assert err.max() < (F64_TOL if dtype == torch.float64 else F32_TOL)
+    assert _vec_rel(res["tiled"][0], res["dense"][0], 1e-3).max() < (1e-10 if dtype == torch.float64 else 2e-5)
+    assert np.abs(res["tiled"][1] - res["dense"][1]).max() < (1e-9 if dtype == torch.float64 else 2e-3)
