@@ -171,8 +171,15 @@ def run(args, out):
                        dtype=torch.float32, device=dev)
     exchange_kind = os.environ.get("CSF_BENCH_EXCHANGE", "peer") if (world > 1 and not emu) else "none"
     xb = None if emu else bounds
-    exch = (PeerExchange(N_AGENTS, rank, world, torch.float32, dev, bounds=xb) if exchange_kind == "peer"
-            else PayloadExchange(N_AGENTS, rank, world, bounds=xb))
+    exch = None
+    if exchange_kind == "peer":
+        try:
+            exch = PeerExchange(N_AGENTS, rank, world, torch.float32, dev, bounds=xb)
+        except RuntimeError as e:      # raised on every rank alike (see PeerExchange.__init__)
+            print(f"[bench] peer-memory exchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
+            exchange_kind = "nccl"
+    if exch is None:
+        exch = PayloadExchange(N_AGENTS, rank, world, bounds=xb)
     if emu:
         full = AgentGroup("twod", s0, P.InvPendulumBicycleParameters(), destqueues=list(queues),
                           dtype=torch.float32, device=dev)

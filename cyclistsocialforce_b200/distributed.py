@@ -132,23 +132,47 @@ class PeerExchange:
         base = C.c_void_p()
         hb = self.lib.csf_peer_handle_bytes()
         handle = (C.c_ubyte * hb)()
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.csf_peer_alloc(self.bytes, C.byref(base), handle), "csf_peer_alloc")
-        self.base = int(base.value)
+        # every step below is collective: a failure on one rank (no peer access, IPC not permitted ...) is
+        # agreed on by all ranks before anybody raises, so that callers can fall back to PayloadExchange
+        err = None
+        self.base = None
+        try:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.csf_peer_alloc(self.bytes, C.byref(base), handle), "csf_peer_alloc")
+            self.base = int(base.value)
+        except Exception as e:          # noqa: BLE001
+            err = e
         self.peers = [None] * world
         self.peers[rank] = self.base
         if world > 1:
             handles = [None] * world
-            dist.all_gather_object(handles, bytes(handle), group=group)
-            with torch.cuda.device(self.device):
-                for p in range(world):
-                    if p == rank:
-                        continue
-                    ptr = C.c_void_p()
-                    buf = (C.c_ubyte * hb).from_buffer_copy(handles[p])
-                    _lib.check(self.lib.csf_peer_open(buf, C.byref(ptr)), "csf_peer_open")
-                    self.peers[p] = int(ptr.value)
-            dist.barrier(group=group)
+            dist.all_gather_object(handles, bytes(handle) if err is None else None, group=group)
+            if err is None and any(h is None for h in handles):
+                err = RuntimeError("PeerExchange: a peer could not allocate its buffer")
+            if err is None:
+                try:
+                    with torch.cuda.device(self.device):
+                        for p in range(world):
+                            if p == rank:
+                                continue
+                            ptr = C.c_void_p()
+                            buf = (C.c_ubyte * hb).from_buffer_copy(handles[p])
+                            _lib.check(self.lib.csf_peer_open(buf, C.byref(ptr)), "csf_peer_open")
+                            self.peers[p] = int(ptr.value)
+                except Exception as e:  # noqa: BLE001
+                    err = e
+            flags = [None] * world
+            dist.all_gather_object(flags, err is None, group=group)
+            if not all(flags):
+                for p, ptr in enumerate(self.peers):
+                    if p != rank and ptr:
+                        self.lib.csf_peer_close(C.c_void_p(ptr))
+                if self.base:
+                    self.lib.csf_peer_free(C.c_void_p(self.base))
+                self.base = None
+                raise RuntimeError(f"PeerExchange unavailable on this node: {err or 'a peer failed'}")
+        elif err is not None:
+            raise err
         comm = _lib.CsfPeerComm()
         comm.world, comm.rank = world, rank
         for p in range(world):
