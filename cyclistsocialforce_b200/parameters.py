@@ -112,6 +112,9 @@ class VehicleParameters:
         fp.p_0 = getattr(self, "p_0", 0.0)
         fp.p_decay = getattr(self, "p_decay", 1.0)
         fp.v_max = getattr(self, "v_max_riding", [0.0, 1.0])[1]
+        # f32 tiled kernel: contributions below 2^-cutoff_log2 f_0 may be dropped (0 = library default 40;
+        # set ``params.cutoff_log2 = 32`` to trade 18 % of the pair kernel's time for a looser bound)
+        fp.cutoff_log2 = float(getattr(self, "cutoff_log2", 0.0))
         return fp
 
     def field_key(self, field_kind: int = 0):

@@ -19,6 +19,7 @@ int main(int argc, char** argv) {
     cudaMalloc(&d, n * sizeof(Xycs<float>)); cudaMalloc(&f, n * 8);
     cudaMemcpy(d, h.data(), n * sizeof(Xycs<float>), cudaMemcpyHostToDevice);
     CsfFieldParams fp = {7.0, 0.995, 0.7, 0.5, 5.0, 0.3, 4.9, 2.0943951023931953, q, 0, 0, 0, 0, 0, 0};
+    if (getenv("CSF_PB_CUTOFF_LOG2")) fp.cutoff_log2 = atof(getenv("CSF_PB_CUTOFF_LOG2"));   // default 40
     size_t wsb = csf_pair_workspace_bytes(n, n, 4);
     cudaMalloc(&ws, wsb);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
