@@ -289,10 +289,12 @@ def run(args, out):
     ms_per_step = total_ms / args.steps
 
     # ---- end to end: host buffers in, host buffers out, every step --------------------------
-    host_in = {n: getattr(group, n).cpu().pin_memory() for n in ("x", "y", "psi", "v", "delta")}
-    host_out = {n: torch.empty_like(t).pin_memory() for n, t in host_in.items()}
+    # the CSF state (x, y double; psi, v, delta float) travels as one pinned slab each way, the total force
+    # as a second device->host copy
+    host_in = group.state_slab.cpu().pin_memory()
+    host_out = torch.empty_like(host_in).pin_memory()
     host_force = torch.empty((n_local, 2), dtype=torch.float32).pin_memory()
-    h2d = sum(t.numel() * t.element_size() for t in host_in.values())
+    h2d = host_in.numel()
     d2h = h2d + host_force.numel() * host_force.element_size()
     eng.use_graph = use_graph
     for _ in range(2):

@@ -69,12 +69,24 @@ class AgentGroup:
             return torch.as_tensor(np.ascontiguousarray(a), dtype=f64, device=dev)
 
         z = np.zeros(n)
-        self.x, self.y = t64(s0[:, 0]), t64(s0[:, 1])
-        self.psi, self.v = tT(s0[:, 2]), tT(s0[:, 3])
-        self.delta = tT(s0[:, 4]) if ns > 4 else None
-        self.theta = tT(s0[:, 5]) if ns > 5 else None
-        self.deltadot = tT(s0[:, 6]) if ns > 6 else None
-        self.thetadot = tT(s0[:, 7]) if ns > 7 else None
+        # the CSF state columns (x, y double; psi, v, delta ... in T) are views into ONE device slab, so
+        # that a host-driven loop moves the whole state with a single copy each way (Engine.step_host)
+        names = ["x", "y", "psi", "v", "delta", "theta", "deltadot", "thetadot"][:ns]
+        esz = torch.empty(0, dtype=T).element_size()
+        offs, off = {}, 0
+        for k, name in enumerate(names):
+            offs[name] = (off, 8 if k < 2 else esz)
+            off += (n * offs[name][1] + 255) // 256 * 256
+        self.state_slab = torch.zeros(max(off, 256), dtype=torch.uint8, device=dev)
+        self.state_layout = {name: (o, n, f64 if b == 8 and name in ("x", "y") else T) for name, (o, b) in offs.items()}
+        for k, name in enumerate(["x", "y", "psi", "v", "delta", "theta", "deltadot", "thetadot"]):
+            if name in offs:
+                o, b = offs[name]
+                view = self.state_slab[o:o + n * b].view(f64 if k < 2 else T)
+                view.copy_(t64(s0[:, k]) if k < 2 else tT(s0[:, k]))
+                setattr(self, name, view)
+            else:
+                setattr(self, name, None)
         vd = np.full(n, getattr(params, "v_desired_default", 0.0)) if vd_default is None else np.broadcast_to(
             np.asarray(vd_default, float), (n,))
         self.vd_default = tT(vd)
@@ -602,14 +614,20 @@ class Engine:
         of every group-0 agent, step, download the new state and the total force.  This is the
         call a host-side co-simulation loop makes; bench.py's ``e2e`` times it."""
         g = self.groups[0]
-        for name, src in host_in.items():
-            getattr(g, name).copy_(src, non_blocking=True)
+        if torch.is_tensor(host_in):                # one pinned slab (layout: g.state_layout): one copy each way
+            g.state_slab.copy_(host_in, non_blocking=True)
+        else:
+            for name, src in host_in.items():
+                getattr(g, name).copy_(src, non_blocking=True)
         self.pack()
         if self.exchange is not None:
             self.exchange(self.payload)
         self.step()
-        for name, dst in host_out.items():
-            dst.copy_(getattr(g, name), non_blocking=True)
+        if torch.is_tensor(host_out):
+            host_out.copy_(g.state_slab, non_blocking=True)
+        else:
+            for name, dst in host_out.items():
+                dst.copy_(getattr(g, name), non_blocking=True)
         if host_force is not None:
             host_force.copy_(self.force[:g.n], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
