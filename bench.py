@@ -6,6 +6,9 @@
     python bench.py --impl reference --steps K --warmup W     # CPU oracle port, all host threads
 
 Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for how every field is obtained.
+Environment knobs (tuning / diagnostics, never needed for the reported numbers): CSF_BENCH_N (crowd size),
+CSF_BENCH_GRAPH=0 (kernel-by-kernel launches), CSF_BENCH_EXCHANGE=nccl|peer, CSF_BENCH_BALANCE=0,
+CSF_BENCH_EMULATE_WORLD=k (time one shard of a k-way split on one GPU), CSF_BENCH_DEBUG=1 (per-step times).
 """
 from __future__ import annotations
 
@@ -119,6 +122,8 @@ def run(args, out):
     if args.impl == "reference":
         if rank != 0:
             return 0
+        # torchrun pins OMP_NUM_THREADS=1 for its children: the CPU arm uses every host thread
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
         r = cpu_oracle_run(args.steps, args.warmup)
         line = {
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "agent-steps/s",
