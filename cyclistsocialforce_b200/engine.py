@@ -24,6 +24,11 @@ from .parameters import VehicleParameters, choose_q_scale
 
 N_STATES = dict(twod=5, invpendulum=6, balancingrider=8, planarpoint=4, bicycle=5, uncontrolled=4)
 _WRAP_MODELS = ("twod", "invpendulum", "bicycle")
+_STATE_COLS = ("x", "y", "psi", "v", "delta", "theta", "deltadot", "thetadot")
+# per-agent device fields and the axis the agent index runs along (churn: AgentGroup.select / concat)
+_FIELD_AXIS = dict(vd_default=0, step_i=0, destq=0, dest_len=0, dest_ptr=0, znav=0, znav_v0=0, znav_d0=0, znav_d1=0,
+                   prev_x=0, prev_y=0, hist_x=1, hist_y=1, hist_step=0, ip_x=1, ip_zrid=0, ip_delta_run=0,
+                   dyn_x=1, dyn_v=0, br_gains=1)
 HIST_CAP = 128
 
 
@@ -69,24 +74,8 @@ class AgentGroup:
             return torch.as_tensor(np.ascontiguousarray(a), dtype=f64, device=dev)
 
         z = np.zeros(n)
-        # the CSF state columns (x, y double; psi, v, delta ... in T) are views into ONE device slab, so
-        # that a host-driven loop moves the whole state with a single copy each way (Engine.step_host)
-        names = ["x", "y", "psi", "v", "delta", "theta", "deltadot", "thetadot"][:ns]
-        esz = torch.empty(0, dtype=T).element_size()
-        offs, off = {}, 0
-        for k, name in enumerate(names):
-            offs[name] = (off, 8 if k < 2 else esz)
-            off += (n * offs[name][1] + 255) // 256 * 256
-        self.state_slab = torch.zeros(max(off, 256), dtype=torch.uint8, device=dev)
-        self.state_layout = {name: (o, n, f64 if b == 8 and name in ("x", "y") else T) for name, (o, b) in offs.items()}
-        for k, name in enumerate(["x", "y", "psi", "v", "delta", "theta", "deltadot", "thetadot"]):
-            if name in offs:
-                o, b = offs[name]
-                view = self.state_slab[o:o + n * b].view(f64 if k < 2 else T)
-                view.copy_(t64(s0[:, k]) if k < 2 else tT(s0[:, k]))
-                setattr(self, name, view)
-            else:
-                setattr(self, name, None)
+        self._make_state_slab(n, {name: (t64(s0[:, k]) if k < 2 else tT(s0[:, k]))
+                                  for k, name in enumerate(_STATE_COLS[:ns])})
         vd = np.full(n, getattr(params, "v_desired_default", 0.0)) if vd_default is None else np.broadcast_to(
             np.asarray(vd_default, float), (n,))
         self.vd_default = tT(vd)
@@ -139,6 +128,81 @@ class AgentGroup:
         self.payload_offset = 0
         self._cstate = None
         self._cparams = None
+
+    def _make_state_slab(self, n, cols):
+        """The CSF state columns (x, y double; psi, v, delta ... in T) are views into ONE device slab, so
+        that a host-driven loop moves the whole state with a single copy each way (Engine.step_host).
+        ``cols``: name -> device tensor of length n (missing columns become None)."""
+        T, f64, dev = self.dtype, torch.float64, self.device
+        esz = torch.empty(0, dtype=T).element_size()
+        offs, off = {}, 0
+        for name in _STATE_COLS:
+            if name in cols:
+                b = 8 if name in ("x", "y") else esz
+                offs[name] = (off, b)
+                off += (n * b + 255) // 256 * 256
+        self.state_slab = torch.zeros(max(off, 256), dtype=torch.uint8, device=dev)
+        self.state_layout = {name: (o, n, f64 if name in ("x", "y") else T) for name, (o, b) in offs.items()}
+        for name in _STATE_COLS:
+            if name in offs:
+                o, b = offs[name]
+                view = self.state_slab[o:o + n * b].view(f64 if name in ("x", "y") else T)
+                view.copy_(cols[name])
+                setattr(self, name, view)
+            else:
+                setattr(self, name, None)
+
+    # ---- churn on the device (reference intersection.py:458-539, :576-634) -------------------------
+    @classmethod
+    def _from_fields(cls, like, n, cols, fields, destq_host, dest_len_host, q_cap):
+        g = object.__new__(cls)
+        g.model, g.params, g.dtype, g.device = like.model, like.params, like.dtype, like.device
+        g.n, g.q_cap = int(n), int(q_cap)
+        g._make_state_slab(g.n, cols)
+        for name in _FIELD_AXIS:
+            setattr(g, name, fields.get(name))
+        g.destq_host, g.dest_len_host = destq_host, dest_len_host
+        g.status = torch.zeros(1, dtype=torch.int32, device=g.device)
+        g.payload_offset = 0
+        g._cstate = g._cparams = None
+        return g
+
+    def select(self, keep):
+        """New group with the agents ``keep`` (indices, any order) -- every per-agent field, including
+        the navigation machine, the history rings and the dynamic state, gathered on the device."""
+        keep_h = np.asarray(keep, dtype=np.int64).reshape(-1)
+        idx = torch.as_tensor(keep_h, device=self.device)
+        cols = {name: getattr(self, name).index_select(0, idx) for name in _STATE_COLS if getattr(self, name) is not None}
+        fields = {name: getattr(self, name).index_select(ax, idx).contiguous()
+                  for name, ax in _FIELD_AXIS.items() if getattr(self, name) is not None}
+        return AgentGroup._from_fields(self, len(keep_h), cols, fields, self.destq_host[keep_h].copy(),
+                                       self.dest_len_host[keep_h].copy(), self.q_cap)
+
+    @staticmethod
+    def concat(a, b):
+        """Agents of ``a`` followed by those of ``b`` (same model and parameter set), joined on the device."""
+        assert a.model == b.model and a.dtype == b.dtype
+        q_cap = max(a.q_cap, b.q_cap)
+
+        def padq(g):
+            if g.q_cap == q_cap:
+                return g.destq, g.destq_host
+            dq = torch.zeros((g.n, q_cap, 3), dtype=torch.float64, device=g.device)
+            dq[:, :g.q_cap] = g.destq
+            hq = np.zeros((g.n, q_cap, 3))
+            hq[:, :g.q_cap] = g.destq_host
+            return dq, hq
+
+        (da, ha), (db, hb) = padq(a), padq(b)
+        cols = {name: torch.cat([getattr(a, name), getattr(b, name)]) for name in _STATE_COLS
+                if getattr(a, name) is not None}
+        fields = {}
+        for name, ax in _FIELD_AXIS.items():
+            ta, tb = (da, db) if name == "destq" else (getattr(a, name), getattr(b, name))
+            if ta is not None:
+                fields[name] = torch.cat([ta, tb], dim=ax).contiguous()
+        return AgentGroup._from_fields(a, a.n + b.n, cols, fields, np.concatenate([ha, hb]),
+                                       np.concatenate([a.dest_len_host, b.dest_len_host]), q_cap)
 
     def _initial_br_gains(self, v0):
         """BalancingRiderDynamics.__init__ -> _get_gains(v) (dynamics.py:305-306, :602-615):

@@ -219,16 +219,83 @@ class SocialForceIntersection:
                     v._owner, v._group, v._k = self, None, -1
                 obs.append(o)
         self._groups, self._obstacle_groups = groups, obs
+        self._make_engine()
+
+    def _make_engine(self):
+        """(Re)bind the engine to the current device groups."""
+        self.n_bikes = len(self.vehicles)
         self._obstacles_dirty = False
         edges = [e for el in self.road_elements for e in el.edges_flat()]
         if self.n_bikes > 0:
-            self._engine = Engine(groups, obstacles=obs, priority_rule=self.priority_rule, road_edges=edges,
-                                  dtype=self.dtype, device=self.device)
+            self._engine = Engine(self._groups, obstacles=self._obstacle_groups, priority_rule=self.priority_rule,
+                                  road_edges=edges, dtype=self.dtype, device=self.device)
         else:
             self._engine = None
         self._invalidate()
         rt = self._record_traj_opt
         self.record_traj = (self.n_bikes <= 64) if rt is None else bool(rt)
+
+    # ---- churn without a host round trip of the crowd (reference :458-539, :576-634) -------------------
+    def _device_add(self, user):
+        """Append one controlled road user to the device group of its (model, parameter set): the
+        group's state stays on the device (AgentGroup.concat).  False if there is no such group."""
+        if self._engine is None or user.MODEL is None:
+            return False
+        key = (user.MODEL, _params_key(user.params))
+        for gi, g in enumerate(self._groups):
+            if (g.model, _params_key(g.params)) == key:
+                break
+        else:
+            return False
+        one = AgentGroup(user.MODEL, np.asarray(user._s, float)[None, :], g.params,
+                         vd_default=[user.params.v_desired_default], destqueues=[user._destqueue],
+                         dtype=self.dtype, device=self.device)
+        if user._record is not None:
+            one.import_record(0, user._record)
+        new = AgentGroup.concat(g, one)
+        for v in self.vehicles:
+            if v._group is g:
+                v._group = new
+        user._owner, user._group, user._k = self, new, g.n
+        self._groups[gi] = new
+        self._make_engine()
+        return True
+
+    def _device_remove(self, removed):
+        """Drop controlled road users from their device groups (AgentGroup.select); only the removed
+        users' records travel to the host.  False if an obstacle is among them (full rebuild)."""
+        if self._engine is None or any(v._group is None for v in removed):
+            return False
+        by_group = {}
+        for v in removed:
+            by_group.setdefault(id(v._group), []).append(v)
+        groups = []
+        for g in self._groups:
+            vs = by_group.get(id(g))
+            if not vs:
+                groups.append(g)
+                continue
+            rm = sorted(v._k for v in vs)
+            recs = g.select(rm).export_records()
+            for v in vs:
+                r = recs[rm.index(v._k)]
+                v._record, v._s = r, r["_s"]
+                v._i, v._destpointer = int(r["step_i"]), int(r["dest_ptr"])
+            gone = set(rm)
+            keep = [k for k in range(g.n) if k not in gone]
+            newk = {k: j for j, k in enumerate(keep)}
+            new = g.select(keep) if keep else None
+            for v in self.vehicles:
+                if v._group is g and v._k in newk:
+                    v._group, v._k = new, newk[v._k]
+            if new is not None:
+                groups.append(new)
+        for v in removed:
+            v._owner = v._group = None
+            v._k = -1
+        self._groups = groups
+        self._make_engine()
+        return True
 
     def _pull_records(self):
         for g in self._groups:
@@ -297,30 +364,35 @@ class SocialForceIntersection:
     def add_road_user(self, user):
         """reference :458-539."""
         self.vehicles.append(user)
-        self._rebuild()
+        if not self._device_add(user):
+            self._rebuild()
 
     def get_road_user_ids(self):
         return [v.id for v in self.vehicles]
 
     def remove_road_user(self, i):
         """reference :576-616."""
-        self._pull_records()
         v = self.vehicles.pop(i)
-        v._owner = v._group = None
-        self._rebuild()
+        if not self._device_remove([v]):
+            self.vehicles.insert(i, v)
+            self._pull_records()
+            self.vehicles.pop(i)
+            v._owner = v._group = None
+            self._rebuild()
         return v
 
     def remove_road_users_by_id(self, ids):
         """reference :618-634."""
-        self._pull_records()
-        keep = []
-        for v in self.vehicles:
-            if v.id in ids:
-                v._owner = v._group = None
-            else:
-                keep.append(v)
+        gone = [v for v in self.vehicles if v.id in ids]
+        keep = [v for v in self.vehicles if v.id not in ids]
         self.vehicles = keep
-        self._rebuild()
+        if not self._device_remove(gone):
+            self.vehicles = keep + gone
+            self._pull_records()
+            self.vehicles = keep
+            for v in gone:
+                v._owner = v._group = None
+            self._rebuild()
 
     # ---- the hot path ---------------------------------------------------------------------------------------
     def _force_in_vehicle_order(self):

@@ -253,3 +253,49 @@ def test_graph_step_equals_kernel_by_kernel_step():
         out[graph] = (g.states_numpy(), eng.force.cpu().numpy())
     assert np.array_equal(out[False][0], out[True][0])
     assert np.array_equal(out[False][1], out[True][1])
+
+
+def test_device_side_churn_select_concat():
+    """AgentGroup.select / AgentGroup.concat (the device-side half of add_road_user / remove_road_user,
+    reference intersection.py:458-539, :576-634): removing and re-adding far-away road users leaves the
+    rest of a 2,500-cyclist crowd on the trajectory of a crowd that never changed, and the re-added users
+    come back with their complete device record (navigation machine, history rings)."""
+    from cyclistsocialforce_b200.engine import AgentGroup, Engine
+    from cyclistsocialforce_b200.synthetic import queues_with_start
+    n_main, n_far = 2500, 40
+    s0, q = co.synthetic_crowd(n_main, seed=6, spacing=3.0)
+    sf, qf = co.synthetic_crowd(n_far, seed=7, spacing=300.0)
+    sf[:, 0] += 4000.0; qf[..., 0] += 4000.0
+    S, Q = np.concatenate([s0, sf]), np.concatenate([q, qf])
+
+    def group():
+        return AgentGroup("twod", S, P.InvPendulumBicycleParameters(), destqueues=list(queues_with_start(S, Q)),
+                          dtype=torch.float64)
+
+    ga = group()
+    ea = Engine([ga], dtype=torch.float64, pair_mode="tiled")
+    for _ in range(30):
+        ea.step()
+    gb = group()
+    eb = Engine([gb], dtype=torch.float64, pair_mode="tiled")
+    for _ in range(10):
+        eb.step()
+    far = gb.select(np.arange(n_main, n_main + n_far))
+    far_state = far.states_numpy()
+    gm = gb.select(np.arange(n_main))
+    assert gm.n == n_main and far.n == n_far
+    eb = Engine([gm], dtype=torch.float64, pair_mode="tiled")
+    for _ in range(10):
+        eb.step()
+    gc = AgentGroup.concat(gm, far)
+    assert gc.n == n_main + n_far
+    assert np.array_equal(gc.states_numpy()[n_main:], far_state)
+    assert np.array_equal(gc.hist_step.cpu().numpy()[n_main:], far.hist_step.cpu().numpy())
+    assert np.array_equal(gc.dest_ptr.cpu().numpy()[n_main:], far.dest_ptr.cpu().numpy())
+    eb = Engine([gc], dtype=torch.float64, pair_mode="tiled")
+    for _ in range(10):
+        eb.step()
+    eb.check_status()
+    a, b = ga.states_numpy()[:n_main], gc.states_numpy()[:n_main]
+    assert np.abs(a - b).max() < 1e-9
+    assert np.array_equal(ga.dest_ptr.cpu().numpy()[:n_main], gc.dest_ptr.cpu().numpy()[:n_main])
