@@ -850,17 +850,30 @@ template <typename T> CullConst<T> make_cull(const CsfFieldParams* fp, bool is_f
     c.dmax = never;
     for (int b = 0; b < kLobeBins; ++b) c.lobe[b] = never;
     if (is_f32) {
-        // exp(-d * rate) = 2^-cutoff_log2  ->  reach d; cached per parameter set
-        constexpr int NC = 512;
-        static CsfFieldParams cached;
-        static double cached_rate = -1.0, cached_rate_c[NC];
-        static bool cached_ok = false;
-        if (cached_rate < 0.0 || cached.e_0 != fp->e_0 || cached.e_1 != fp->e_1 || cached.sigma_0 != fp->sigma_0 ||
-            cached.sigma_1 != fp->sigma_1 || cached.sigma_2 != fp->sigma_2 || cached.sigma_3 != fp->sigma_3) {
-            cached = *fp;
-            cached_rate = field_min_decay_rate(fp);
-            cached_ok = field_decay_rate_by_angle(fp, NC, cached_rate_c);
+        // exp(-d * rate) = 2^-cutoff_log2  ->  reach d.  The bounds cost ~1 ms of host time per parameter
+        // set: a small cache (several source classes alternate within a step)
+        constexpr int NC = 512, kCache = 8;
+        struct Entry { CsfFieldParams fp; double rate; double rate_c[NC]; bool ok; bool used; };
+        static Entry cache[kCache];
+        static int next_slot = 0;
+        Entry* hit = nullptr;
+        for (int i = 0; i < kCache && !hit; ++i) {
+            const Entry& e = cache[i];
+            if (e.used && e.fp.e_0 == fp->e_0 && e.fp.e_1 == fp->e_1 && e.fp.sigma_0 == fp->sigma_0 &&
+                e.fp.sigma_1 == fp->sigma_1 && e.fp.sigma_2 == fp->sigma_2 && e.fp.sigma_3 == fp->sigma_3)
+                hit = &cache[i];
         }
+        if (!hit) {
+            hit = &cache[next_slot];
+            next_slot = (next_slot + 1) % kCache;
+            hit->fp = *fp;
+            hit->rate = field_min_decay_rate(fp);
+            hit->ok = field_decay_rate_by_angle(fp, NC, hit->rate_c);
+            hit->used = true;
+        }
+        const double cached_rate = hit->rate;
+        const double* cached_rate_c = hit->rate_c;
+        const bool cached_ok = hit->ok;
         const double bits = fp->cutoff_log2 > 0.0 ? fp->cutoff_log2 : 40.0;
         const double L = bits * 0.6931471805599453 * 1.0001 / fp->q_scale;
         if (cached_rate > 0.0 && L / cached_rate < 3.0e9) {
