@@ -3,7 +3,10 @@ the agent-range sharded crowd (payload all-gather over NCCL every step) must rep
 single-GPU crowd.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29511 tools/check_sharded.py
+        --master-port 29511 tools/check_sharded.py [--peer]
+
+--peer: payload exchange over NVLink peer memory (csf_peer_*) inside the CUDA-graph step instead of the
+NCCL all-gather.
 """
 import os
 import sys
