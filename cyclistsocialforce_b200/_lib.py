@@ -71,7 +71,7 @@ class CsfAgentState(C.Structure):
         ("hist_step", C.c_void_p),
         ("ip_x", C.c_void_p), ("ip_zrid", C.c_void_p), ("ip_delta_run", C.c_void_p),
         ("dyn_x", C.c_void_p), ("dyn_v", C.c_void_p), ("br_gains", C.c_void_p),
-        ("status", C.c_void_p),
+        ("status", C.c_void_p), ("status_host", C.c_void_p),
     ]
 
 
@@ -104,8 +104,10 @@ SIGNATURES = {
     "csf_spatial_keys_f64": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "csf_tile_sources_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "csf_tile_sources_f64": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
-    "csf_pair_forces_tiled_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp]),
-    "csf_pair_forces_tiled_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp]),
+    "csf_pair_forces_tiled_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "csf_pair_forces_tiled_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "csf_tiled_num_items": (_i64, [_i64, _i64, C.c_int]),
+    "csf_tiled_item_order": (C.c_int, [_vp, _i64, _vp, _vp]),
     "csf_field_cutoff_distance": (_dbl, [_FP]),
     "csf_field_reach_table": (C.c_int, [_FP, C.c_int, C.POINTER(C.c_double)]),
     "csf_road_forces_f32": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _dbl, _dbl, _vp, C.c_int, _vp]),

@@ -21,6 +21,7 @@ enum { MODE_FORCES = 0, MODE_ADVANCE = 1, MODE_STEP = 2 };
 // ----------------------------------------------------------------------------------------
 // per-agent register image
 // ----------------------------------------------------------------------------------------
+constexpr int kQW = 6;  // destination-queue window held in registers: entries ptr0 .. ptr0 + 5
 template <typename T> struct Agent {
     double x, y;
     T psi, v, delta, theta;
@@ -30,11 +31,63 @@ template <typename T> struct Agent {
     int znav;         // bit0 go, bit1 decel, bit2 arrived
     T z_v0, z_d0, z_d1;
     const double* q;  // this agent's destination queue [q_cap][3]
+    // The queue entries the step can touch, fetched with independent loads when the kernel starts,
+    // relative to the position at that time (x0, y0): entry min(ptr0 + j, qlen - 1) for j < kQW.
+    // updateDestination advances the pointer by at most 2 per call and the spline looks 3 entries
+    // ahead, so only a step with three pointer updates in a row (spline fall-back) leaves the window;
+    // it then reads the queue itself.
+    double x0, y0;
+    int ptr0;
+    T wx[kQW], wy[kQW];
+    unsigned wstop;   // bit j: stop flag of window entry j
     int flags;        // status bits raised by this agent
 };
 
+template <typename T> __device__ __forceinline__ void load_window(Agent<T>& a) {
+    a.x0 = a.x;
+    a.y0 = a.y;
+    a.ptr0 = a.ptr;
+    a.wstop = 0;
+    double qx[kQW], qy[kQW], qs[kQW];
+#pragma unroll
+    for (int j = 0; j < kQW; ++j) {
+        const int idx = min(a.ptr + j, a.qlen - 1);
+        qx[j] = a.q[idx * 3 + 0];
+        qy[j] = a.q[idx * 3 + 1];
+        qs[j] = a.q[idx * 3 + 2];
+    }
+#pragma unroll
+    for (int j = 0; j < kQW; ++j) {
+        a.wx[j] = (T)(qx[j] - a.x);
+        a.wy[j] = (T)(qy[j] - a.y);
+        a.wstop |= (qs[j] != 0.0) ? (1u << j) : 0u;
+    }
+}
+// queue entry idx relative to (x0, y0), and its stop flag
+template <typename T> __device__ __forceinline__ void queue_entry(const Agent<T>& a, int idx, T& rx, T& ry, bool& stop) {
+    const int j = min(idx, a.qlen - 1) - a.ptr0;
+    if (j >= 0 && j < kQW) {
+        rx = a.wx[0];
+        ry = a.wy[0];
+#pragma unroll
+        for (int u = 1; u < kQW; ++u) {
+            rx = (j == u) ? a.wx[u] : rx;
+            ry = (j == u) ? a.wy[u] : ry;
+        }
+        stop = (a.wstop >> j) & 1u;
+    } else {
+        const int k = min(idx, a.qlen - 1);
+        rx = (T)(a.q[k * 3 + 0] - a.x0);
+        ry = (T)(a.q[k * 3 + 1] - a.y0);
+        stop = a.q[k * 3 + 2] != 0.0;
+    }
+}
+
+// distance to queue entry idx (from the position the step started at; it moves only in K3's last lines)
 template <typename T> __device__ __forceinline__ T dist_to(const Agent<T>& a, int idx) {
-    const T dx = (T)(a.q[idx * 3 + 0] - a.x), dy = (T)(a.q[idx * 3 + 1] - a.y);
+    T dx, dy;
+    bool st;
+    queue_entry(a, idx, dx, dy, st);
     return sqrt(dx * dx + dy * dy);
 }
 
@@ -90,12 +143,14 @@ template <typename T> __device__ T update_nav_state(Agent<T>& a, const CsfAgentP
 // Bicycle.calcDestinationForceField (vehicle.py:1168-1187) == calc_direct_approach_dest_force (:2096-2108)
 template <typename T> __device__ void dest_force_direct(Agent<T>& a, const CsfAgentParams& p, T& fx, T& fy) {
     update_destination(a, p);
-    const double* d = a.q + a.ptr * 3;
+    T rx, ry;
+    bool stop;
+    queue_entry(a, a.ptr, rx, ry, stop);
     T dd;
-    const T vd = update_nav_state(a, p, d[2] != 0.0, &dd);
+    const T vd = update_nav_state(a, p, stop, &dd);
     if (dd > (T)0) {
-        fx = -vd * (T)(a.x - d[0]) / dd;
-        fy = -vd * (T)(a.y - d[1]) / dd;
+        fx = -vd * (-rx) / dd;
+        fy = -vd * (-ry) / dd;
     } else {
         fx = (T)0;
         fy = (T)0;
@@ -261,11 +316,12 @@ __device__ void spline_eval(const Spline<T>& s, T u, bool der, T& x, T& y, T& dx
 
 // TwoDBicycle.calcDestinationForce, vehicle.py:1443-1558
 template <typename T>
-__device__ void dest_force_twod(Agent<T>& a, const CsfAgentParams& p, const CsfAgentState& st, int64_t k, T& fx,
-                                T& fy) {
+__device__ void dest_force_twod(Agent<T>& a, const CsfAgentParams& p, const CsfAgentState& st, int64_t k, double pv_x,
+                                double pv_y, T& fx, T& fy) {
     update_destination(a, p);
-    const double* d = a.q + a.ptr * 3;
-    const bool stop = d[2] != 0.0;
+    T drx, dry;
+    bool stop;
+    queue_entry(a, a.ptr, drx, dry, stop);
     T dd;
     const T vd = update_nav_state(a, p, stop, &dd);
     if (a.i == 0) {  // :1455-1458
@@ -283,28 +339,27 @@ __device__ void dest_force_twod(Agent<T>& a, const CsfAgentParams& p, const CsfA
     // control points relative to the current position (index of the current position: 1 or 2)
     T px[6], py[6];
     int m, cur;
-    const T pvx = (T)(st.prev_x[k] - a.x), pvy = (T)(st.prev_y[k] - a.y);
+    const T pvx = (T)(pv_x - a.x), pvy = (T)(pv_y - a.y);
     if (!last) {  // [traj[i-1], traj[i], destqueue[ptr : ptr+4]]  :1468-1479
         px[0] = pvx; py[0] = pvy;
         px[1] = (T)0; py[1] = (T)0;
         const int nd = min(4, a.qlen - a.ptr);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int idx = min(a.ptr + j, a.qlen - 1);
-            px[2 + j] = (T)(a.q[idx * 3 + 0] - a.x);
-            py[2 + j] = (T)(a.q[idx * 3 + 1] - a.y);
+            bool sj;
+            queue_entry(a, a.ptr + j, px[2 + j], py[2 + j], sj);
         }
         m = 2 + nd;
         cur = 1;
     } else {  // [traj[max(0, i-100)], traj[i-1], traj[i], dest]  :1486-1492
         const int back = min(a.i, p.hist_len);
-        const int hs = st.hist_step[k];
+        const int hs = st.hist_step[k];      // (the last-destination branch only)
         const int row = (hs - back) & (p.hist_cap - 1);
         px[0] = (T)(st.hist_x[(size_t)row * st.n + k] - a.x);
         py[0] = (T)(st.hist_y[(size_t)row * st.n + k] - a.y);
         px[1] = pvx; py[1] = pvy;
         px[2] = (T)0; py[2] = (T)0;
-        px[3] = (T)(d[0] - a.x); py[3] = (T)(d[1] - a.y);
+        px[3] = drx; py[3] = dry;
         px[4] = px[5] = py[4] = py[5] = (T)0;
         m = 4;
         cur = 2;
@@ -351,16 +406,16 @@ __device__ void dest_force_twod(Agent<T>& a, const CsfAgentParams& p, const CsfA
 }
 
 template <typename T, int MODEL>
-__device__ void destination_force(Agent<T>& a, const CsfAgentParams& p, const CsfAgentState& st, int64_t k, T& fx,
-                                  T& fy) {
-    if (MODEL == CSF_MODEL_TWOD || MODEL == CSF_MODEL_INVPENDULUM) dest_force_twod(a, p, st, k, fx, fy);
+__device__ void destination_force(Agent<T>& a, const CsfAgentParams& p, const CsfAgentState& st, int64_t k, double pv_x,
+                                  double pv_y, T& fx, T& fy) {
+    if (MODEL == CSF_MODEL_TWOD || MODEL == CSF_MODEL_INVPENDULUM) dest_force_twod(a, p, st, k, pv_x, pv_y, fx, fy);
     else if (MODEL == CSF_MODEL_BICYCLE) dest_force_direct(a, p, fx, fy);              // vehicle.py:1189-1194
     else if (MODEL == CSF_MODEL_BALANCINGRIDER) {
         update_destination(a, p);                                                      // vehicle.py:295-297
         dest_force_direct(a, p, fx, fy);
     } else {                                                                           // planarpoint
         update_destination(a, p);                                                      // vehicle.py:295-297
-        dest_force_twod(a, p, st, k, fx, fy);                                          // vehicle.py:2025
+        dest_force_twod(a, p, st, k, pv_x, pv_y, fx, fy);                              // vehicle.py:2025
     }
 }
 
@@ -612,16 +667,37 @@ __global__ void __launch_bounds__(128) agent_kernel(CsfAgentState st, CsfAgentPa
     a.z_d1 = ldT<T>(st.znav_d1, k);
     a.q = st.destq + (size_t)k * p.q_cap * 3;
     a.flags = 0;
+    // everything else the step reads from global memory, issued before the first use (independent loads:
+    // one round trip instead of a chain of them)
+    constexpr bool kHist = MODEL == CSF_MODEL_TWOD || MODEL == CSF_MODEL_INVPENDULUM || MODEL == CSF_MODEL_PLANARPOINT;
+    double pv_x = 0.0, pv_y = 0.0;
+    int hist_step = 0;
+    if (kHist) {
+        pv_x = st.prev_x[k];
+        pv_y = st.prev_y[k];
+        hist_step = st.hist_step[k];
+    }
+    T frx0 = (T)0, fry0 = (T)0, fox = (T)0, foy = (T)0;
+    const bool have_rep = MODE != MODE_ADVANCE && n_total > 1 && frep != nullptr;
+    if (have_rep) {
+        frx0 = frep[k * 2];
+        fry0 = frep[k * 2 + 1];
+    }
+    if (MODE != MODE_ADVANCE && froad != nullptr) {
+        fox = froad[k * 2];
+        foy = froad[k * 2 + 1];
+    }
+    load_window(a);
 
     T Fx, Fy;
     if (MODE != MODE_ADVANCE) {
         // ---- K2: destination force + assembly (intersection.py:797-799, :841-862) ----
         T fdx, fdy;
-        destination_force<T, MODEL>(a, p, st, k, fdx, fdy);
+        destination_force<T, MODEL>(a, p, st, k, pv_x, pv_y, fdx, fdy);
         T frx = (T)0, fry = (T)0;
-        if (n_total > 1 && frep != nullptr) {
-            frx = frep[k * 2];
-            fry = frep[k * 2 + 1];
+        if (have_rep) {
+            frx = frx0;
+            fry = fry0;
             const T rin = sqrt(frx * frx + fry * fry), r = sqrt(fdx * fdx + fdy * fdy);
             if (rin > r) {  // utils.limitMagnitude, utils.py:79-84
                 frx = frx * r / rin;
@@ -630,10 +706,8 @@ __global__ void __launch_bounds__(128) agent_kernel(CsfAgentState st, CsfAgentPa
         }
         Fx = frx + fdx;
         Fy = fry + fdy;
-        if (froad != nullptr) {
-            Fx += froad[k * 2];
-            Fy += froad[k * 2 + 1];
-        }
+        Fx += fox;
+        Fy += foy;
         if (force != nullptr) { force[k * 2] = Fx; force[k * 2 + 1] = Fy; }
         if (fdest_out != nullptr) { fdest_out[k * 2] = fdx; fdest_out[k * 2 + 1] = fdy; }
         st.dest_ptr[k] = a.ptr;
@@ -774,7 +848,7 @@ __global__ void __launch_bounds__(128) agent_kernel(CsfAgentState st, CsfAgentPa
         if (MODEL != CSF_MODEL_BALANCINGRIDER && MODEL != CSF_MODEL_BICYCLE) {
             st.prev_x[k] = ox;
             st.prev_y[k] = oy;
-            const int hs = st.hist_step[k] + 1;
+            const int hs = hist_step + 1;
             st.hist_step[k] = hs;
             const int row = hs & (p.hist_cap - 1);
             st.hist_x[(size_t)row * st.n + k] = a.x;
@@ -787,7 +861,11 @@ __global__ void __launch_bounds__(128) agent_kernel(CsfAgentState st, CsfAgentPa
             if (ovf) a.flags |= 4;
         }
     }
-    if (a.flags && st.status != nullptr) atomicOr(st.status, a.flags);
+    if (a.flags && st.status != nullptr) {
+        atomicOr(st.status, a.flags);
+        // host-mapped mirror: the host polls it without a copy or a synchronisation
+        if (st.status_host != nullptr) *reinterpret_cast<volatile int32_t*>(st.status_host) = 1;
+    }
 }
 
 template <typename T>

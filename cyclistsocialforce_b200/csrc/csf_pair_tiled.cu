@@ -1,48 +1,66 @@
-// K1 (tiled): all-pairs repulsive force with hierarchical culling.
+// K1 (tiled): all-pairs repulsive force with hierarchical culling, warp-specialised.
 //
 // The masked sum  Frep_j = sum_i mask(i,j) F(i -> j)  (reference intersection.py:788-843,
-// vehicle.py:1560-1648) has two sources of exact or negligible zeros:
+// vehicle.py:1560-1648) has three families of exact or negligible zeros:
 //   * ~2/3 of the ordered pairs are masked by the *target's* field of view
 //     (intersection.py:733-736; hfov = 2 pi / 3);
 //   * |F(i -> j)| = f_0 exp(-rho q / sigma) (vehicle.py:1613-1648): beyond rho = d_cut every
 //     contribution is below 2^-cutoff_log2 f_0 (f32 build only; d_cut ~ 160 m with the default
-//     parameters; the f64 verification build never truncates).
-// Both are turned into skipped work at three levels:
-//   1. sources live in a spatially sorted copy (Morton order, re-sorted by the host every few
-//      steps) cut into tiles of 64 and chunks of 16 tiles, each with a bounding circle; targets are
-//      visited in Morton order too, in blocks of 8 warps x tpw targets with a bounding circle;
-//   2. the producer warp of a CTA streams only the chunks that can be within d_cut of the
-//      target block (lane-parallel circle/circle test) into a shared-memory ring with TMA bulk
-//      copies + mbarriers;
-//   3. a consumer warp works on ONE target at a time: its lanes test one tile each against the
-//      target's view cone expanded by the tile radius and the cut-off distance (warp-uniform
-//      decision after a ballot), then evaluate the surviving tiles two sources per lane with the
-//      same pair_eval as the dense kernel (which still applies the exact per-pair mask).
-// Culled pairs are pairs whose contribution is exactly 0 (mask) or < 2^-cutoff_log2 f_0 (f32), so
-// the result equals the dense kernel's up to the order of summation and that bound.
-// Work items (target block x chunk group) are handed out dynamically (atomic counter); partial
-// sums per chunk group are reduced in fixed order (deterministic, no float atomics).
+//     parameters; the f64 verification build never truncates);
+//   * the reach of a source is strongly anisotropic (160 m ahead of it, 55 m from 90 deg on).
+// Sources live in a Hilbert-ordered copy cut into tiles of 64 and chunks of 16 tiles, each with a
+// bounding circle; targets are visited in the same order in blocks of 64 with a bounding circle.
+// A work item is (target block x chunk group).  A CTA is three kinds of warps that only meet
+// through mbarriers -- no CTA-wide barrier anywhere:
+//   producer (1 warp)  fetches items from an atomic counter, tests chunk and tile circles against
+//                      the block circle and streams the tiles that can be within d_cut of the block
+//                      into a ring of shared-memory stages (8 tiles each) with 1-D TMA bulk copies;
+//   filter   (2 warps) take the stages, drop every source whose field cannot reach the block circle
+//                      (lobe test, packed FP32x2) and append the survivors, in stream order, to one
+//                      of two survivor buffers (16 dynamic tiles of 64, with bounding circles); they
+//                      also load the block's targets, ordered by heading so that every evaluate warp
+//                      owns targets looking in all directions (its work per buffer is then even);
+//   evaluate (6 warps) own the targets r = w, w + 6, ... of the block: per survivor buffer a warp
+//                      tests its targets' view cones against the 16 circles (two targets per
+//                      ballot), evaluates the surviving tiles two sources per lane (pair_eval2, which
+//                      still applies the exact per-pair mask), and keeps the running sums of target
+//                      i in lanes i and 16 + i.  The buffer is handed back when all six are done.
+// While the evaluate warps work on one buffer the filter warps fill the other, and the producer is
+// stages ahead of both.  Culled pairs contribute exactly 0 (mask) or < 2^-cutoff_log2 f_0 (f32), so
+// the result equals the dense kernel's up to the order of summation and that bound.  Every sum has
+// a fixed order (stream order of the survivors, static ownership of targets): deterministic, no
+// float atomics; partial sums per chunk group are reduced in fixed order.
 #include "csf_common.cuh"
 #include "csf_pair_common.cuh"
 #include <stdlib.h>
 
 namespace {
 
-#ifndef CSF_TILED_WARPS
-#define CSF_TILED_WARPS 8        // consumer warps per CTA
+#ifndef CSF_TILED_FILTER_WARPS
+#define CSF_TILED_FILTER_WARPS 2
 #endif
+constexpr int kFW = CSF_TILED_FILTER_WARPS;   // filter warps per CTA
+#ifndef CSF_TILED_EVAL_WARPS
+#define CSF_TILED_EVAL_WARPS 6
+#endif
+constexpr int kEW = CSF_TILED_EVAL_WARPS;   // evaluate warps per CTA
 #ifndef CSF_TILED_MINB
 #define CSF_TILED_MINB 3
 #endif
-constexpr int kTW = CSF_TILED_WARPS;
-constexpr int kTThreads = (kTW + 1) * 32;
-constexpr int kMaxTPW = 16;              // targets per warp per item (runtime tpw <= kMaxTPW)
-constexpr int kTB = kTW * kMaxTPW;       // targets per block, at most
+constexpr int kTThreads = (1 + kFW + kEW) * 32;
+constexpr int kBT = 64;                  // targets per block
 constexpr int kTileS = 64;               // sources per tile (2 per lane)
-constexpr int kCT = 16;                  // tiles per chunk = one shared-memory stage
-constexpr int kCS = kCT * kTileS;        // sources per chunk
+constexpr int kCT = 16;                  // tiles per chunk of the sorted copy = dynamic tiles per survivor buffer
+constexpr int kCS = kCT * kTileS;        // sources per chunk / survivor buffer
+constexpr int kST = 8;                   // tiles per shared-memory stage
 constexpr int kTMaxGroups = 64;
-template <typename T> struct Stages { static constexpr int n = 3; };
+template <typename T> struct Stages { static constexpr int n = 4; };
+static_assert(kST % kFW == 0 && kBT % (kFW * 32) == 0, "filter warps split stages and target blocks evenly");
+// Capacity of the k-th survivor buffer of an item (slow start): the evaluate warps get their first
+// buffer of a new item after 256 survivors instead of 1024 -- the bubble at every item boundary is a
+// quarter as long -- and steady-state buffers are large, so that the fixed cost per (target, buffer)
+// stays small.  A fixed function of k: the order of every sum stays fixed.
+__device__ __forceinline__ int buffer_cap(int k) { return k == 0 ? 4 * kTileS : (k == 1 ? 8 * kTileS : kCS); }
 
 template <typename T> struct Tile;
 template <> struct __align__(16) Tile<float> { int32_t cx, cy; float R; int32_t cnt; };
@@ -120,14 +138,11 @@ template <> struct BBox<float> {
     int xmin = INT32_MAX, xmax = INT32_MIN, ymin = INT32_MAX, ymax = INT32_MIN;
     __device__ __forceinline__ void add(int x, int y) { xmin = min(xmin, x); xmax = max(xmax, x); ymin = min(ymin, y); ymax = max(ymax, y); }
     __device__ __forceinline__ void add(const Xycs<float>& e) { add(e.xq, e.yq); }
-    __device__ __forceinline__ void warp_reduce() {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
-            xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
-            ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
-            ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
-        }
+    __device__ __forceinline__ void warp_reduce() {      // REDUX.MIN/MAX: one instruction per bound
+        xmin = __reduce_min_sync(0xffffffffu, xmin);
+        xmax = __reduce_max_sync(0xffffffffu, xmax);
+        ymin = __reduce_min_sync(0xffffffffu, ymin);
+        ymax = __reduce_max_sync(0xffffffffu, ymax);
     }
     __device__ __forceinline__ Tile<float> circle(int64_t cnt) const {
         Tile<float> t;
@@ -387,59 +402,93 @@ __device__ __forceinline__ void lobe_reaches2(const Tile<double>& blk, const Src
     r1 = lobe_reaches<double, double>(blk, A.x1, A.y1, B.c1, B.s1, lobe, tiny);
 }
 
-// named barrier 1 among the consumer warps only (the producer warp never joins)
-__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kTW * 32) : "memory"); }
+// named barrier 1 among the filter warps only
+__device__ __forceinline__ void filter_barrier() {
+    if (kFW > 1) asm volatile("bar.sync 1, %0;" ::"n"(kFW * 32) : "memory");
+    else __syncwarp();
+}
+
+enum { BUF_LAST = 1, BUF_EXIT = 2 };
 
 // ---- the tiled pair kernel ---------------------------------------------------------------------------
 // item -> (target block tb = item % n_tblocks, chunk group cg = item / n_tblocks); a group is
 // `group_chunks` consecutive chunks.  partial[cg][target][2].
-// Stage protocol: the producer fills hdr[stage] = {item, chunk} and the stage's bytes; chunk == -1
-// closes the item (consumers write their partial sums), chunk == -2 ends the kernel.
+// Stage protocol (producer -> filter warps): hdr[stage] = {item, n}: n = 1..kST tiles of the sorted copy
+// with their circle records; n == -1 closes the item, n == -2 ends the kernel.
+// Buffer protocol (filter -> evaluate warps): bdesc[slot] = {item, dynamic tiles, flags, target set}:
+// BUF_LAST = last buffer of the item (the evaluate warps write their sums), BUF_EXIT = leave.
 template <typename T, bool P2R>
 __global__ void __launch_bounds__(kTThreads, sizeof(T) == 4 ? CSF_TILED_MINB : 1)
 pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __restrict__ tiles, int64_t n_tiles,
                   const Xycs<T>* __restrict__ tgt, const int64_t* __restrict__ tgt_perm, int64_t n_tgt,
                   const Tile<T>* __restrict__ tblocks, PairConst<T> k, CullConst<T> cc, T* __restrict__ partial,
-                  int tpw, int group_chunks, int n_groups, int n_tblocks, unsigned int* __restrict__ counter,
+                  int group_chunks, int n_groups, int n_tblocks, unsigned int* __restrict__ counter,
+                  const unsigned int* __restrict__ item_order, unsigned int* __restrict__ item_cost,
                   unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kStages = Stages<T>::n;
-    constexpr size_t kStageBytes = (size_t)kCS * sizeof(Xycs<T>) + (size_t)kCT * sizeof(Tile<T>);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * kStageBytes);
-    uint64_t* empty = full + kStages;
-    int4* hdr = reinterpret_cast<int4*>(empty + kStages);                           // {item, chunk, -, -}
-    unsigned char* sbuf = reinterpret_cast<unsigned char*>(hdr + kStages);          // survivors: one chunk in tile layout
-    Tile<T>* dtile = reinterpret_cast<Tile<T>*>(sbuf + (size_t)kCS * sizeof(Xycs<T>));      // [kCT] their circles
-    Xycs<T>* btgt = reinterpret_cast<Xycs<T>*>(dtile + kCT);                        // [kTB] targets of the block
-    T* bacc = reinterpret_cast<T*>(btgt + kTB);                                     // [kTB][2] their sums
-    T* lobe = bacc + kTB * 2;                                                       // [kLobeBins] reach table
-    uint32_t* wlist = reinterpret_cast<uint32_t*>(lobe + kLobeBins);                // [kTB] (q << 16) | tile mask
-    uint2* fmask = reinterpret_cast<uint2*>(wlist + kTB);                           // [kStages][kCT] filter ballots
-    int* lctl = reinterpret_cast<int*>(fmask + kStages * kCT);                      // list length, next entry
+    constexpr size_t kTileB = TileBytes<T>::v;
+    unsigned char* stage_src = smem_raw;                                            // [kStages][kST] tiles
+    unsigned char* sbuf = stage_src + (size_t)kStages * kST * kTileB;               // [2][kCT] survivor tiles
+    Tile<T>* srec = reinterpret_cast<Tile<T>*>(sbuf + (size_t)2 * kCT * kTileB);    // [kStages][kST] circles of the staged tiles
+    Tile<T>* dtile = srec + kStages * kST;                                          // [2][kCT] circles of the survivor tiles
+    Xycs<T>* btgt = reinterpret_cast<Xycs<T>*>(dtile + 2 * kCT);                    // [2][kBT] targets, by heading rank
+    long long* bj = reinterpret_cast<long long*>(btgt + 2 * kBT);                   // [2][kBT] their indices
+    uint64_t* full = reinterpret_cast<uint64_t*>(bj + 2 * kBT);                     // [kStages]
+    uint64_t* empty = full + kStages;                                               // [kStages]
+    uint64_t* ready = empty + kStages;                                              // [2]
+    uint64_t* freeb = ready + 2;                                                    // [2]
+    int4* hdr = reinterpret_cast<int4*>(freeb + 2);                                 // [kStages] {item, n, -, -}
+    int4* bdesc = hdr + kStages;                                                    // [2] {item, n_dt, flags, target set}
+    uint2* fmask = reinterpret_cast<uint2*>(bdesc + 2);                             // [kStages][kST] filter ballots
+    T* lobe = reinterpret_cast<T*>(fmask + kStages * kST);                          // [kLobeBins] reach table
+    T* bacc = lobe + kLobeBins;                                                     // [2 items][2 buffer parities][kBT][2] sums
+    int* nextq = reinterpret_cast<int*>(bacc + 2 * 2 * kBT * 2);                    // [2] next target of the buffer in the slot
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kTW);
+            mbar_init(&empty[s], kFW);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&ready[s], 1);
+            mbar_init(&freeb[s], kEW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < kLobeBins; i += blockDim.x) lobe[i] = cc.lobe[i];
+    for (int i = threadIdx.x; i < 2 * 2 * kBT * 2; i += blockDim.x) bacc[i] = (T)0;
     __syncthreads();
 
     const unsigned int n_items = (unsigned int)n_tblocks * (unsigned int)n_groups;
     const int64_t n_chunks = (n_tiles + kCT - 1) / kCT;
     const Tile<T>* chunks = tiles + n_tiles;
 
-    if (warp == kTW) {
-        // ===== producer warp: fetch items, cull chunks against the target block, stream the rest =====
+    if (warp == 0) {
+        // ===== producer warp: fetch items, cull chunks and tiles against the target block, stream the rest =====
         uint32_t it = 0;
+        int fill = 0;                                   // tiles in the open stage
+        auto close_stage = [&](int item, int n) {
+            __syncwarp();                               // the circle records of every lane have been written
+            if (lane == 0) {
+                const int stage = it % kStages;
+                hdr[stage] = make_int4(item, n, 0, 0);
+                mbar_arrive(&full[stage]);
+            }
+            ++it;
+            fill = 0;
+        };
+        auto open_stage = [&]() {                       // wait until the filter warps have released the stage
+            if (lane == 0) mbar_wait_backoff(&empty[it % kStages], ((it / kStages) & 1) ^ 1);
+            __syncwarp();
+        };
         for (;;) {
             unsigned int item = 0;
             if (lane == 0) item = atomicAdd(counter, 1u);
             item = __shfl_sync(0xffffffffu, item, 0);
             if (item >= n_items) break;
+            if (item_order) item = item_order[item];        // heaviest items first (previous step's costs)
             const int tb = (int)(item % (unsigned int)n_tblocks), cg = (int)(item / (unsigned int)n_tblocks);
             const Tile<T> tbr = tblocks[tb];
             const int64_t c_begin = (int64_t)cg * group_chunks, c_end = min(n_chunks, c_begin + group_chunks);
@@ -451,252 +500,357 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                 while (m) {
                     const int64_t ch = c0 + (__ffs(m) - 1);
                     m &= m - 1;
-                    const int stage = it % kStages;
-                    const uint32_t phase = (it / kStages) & 1;
-                    if (lane == 0) {
-                        mbar_wait_backoff(&empty[stage], phase ^ 1);
-                        const int64_t t0 = ch * kCT;
-                        const uint32_t nt = (uint32_t)min((int64_t)kCT, n_tiles - t0);
-                        const uint32_t bsrc = nt * (uint32_t)TileBytes<T>::v, btile = nt * (uint32_t)sizeof(Tile<T>);
-                        unsigned char* base = smem_raw + stage * kStageBytes;
-                        hdr[stage] = make_int4((int)item, (int)ch, 0, 0);
-                        mbar_expect_tx(&full[stage], bsrc + btile);
-                        tma_bulk_g2s(base, sorted + (size_t)t0 * TileBytes<T>::v, bsrc, &full[stage]);
-                        tma_bulk_g2s(base + (size_t)kCS * sizeof(Xycs<T>), tiles + t0, btile, &full[stage]);
+                    const int64_t t0 = ch * kCT;
+                    Tile<T> rec;
+                    bool tn = false;
+                    if (lane < kCT && t0 + lane < n_tiles) {
+                        rec = tiles[t0 + lane];
+                        tn = circles_near(rec, tbr, cc.dmax);
                     }
-                    ++it;
+                    uint32_t tm = __ballot_sync(0xffffffffu, tn);
+                    while (tm) {
+                        if (fill == 0) open_stage();
+                        const int stage = it % kStages;
+                        const int room = kST - fill;
+                        const int rank = __popc(tm & ((1u << lane) - 1u));
+                        const bool mine = ((tm >> lane) & 1u) && rank < room;
+                        const int take = min(__popc(tm), room);
+                        if (lane == 0) mbar_expect_tx_only(&full[stage], (uint32_t)take * (uint32_t)kTileB);
+                        __syncwarp();
+                        if (mine) {
+                            const int slot = stage * kST + fill + rank;
+                            srec[slot] = rec;
+                            tma_bulk_g2s(stage_src + (size_t)slot * kTileB, sorted + (size_t)(t0 + lane) * kTileB,
+                                         (uint32_t)kTileB, &full[stage]);
+                        }
+                        tm &= ~__ballot_sync(0xffffffffu, mine);
+                        fill += take;
+                        if (fill == kST) close_stage((int)item, kST);
+                    }
                 }
             }
-            {   // close the item
-                const int stage = it % kStages;
-                const uint32_t phase = (it / kStages) & 1;
-                if (lane == 0) {
-                    mbar_wait_backoff(&empty[stage], phase ^ 1);
-                    hdr[stage] = make_int4((int)item, -1, 0, 0);
-                    mbar_arrive(&full[stage]);
-                }
-                ++it;
-            }
-            __syncwarp();
+            if (fill > 0) close_stage((int)item, fill);
+            open_stage();
+            close_stage((int)item, -1);                 // close the item
         }
-        if (lane == 0) {
+        open_stage();
+        close_stage(0, -2);
+        return;
+    }
+
+    typedef decltype(SrcA<T>().x0) P;    // payload position type
+
+    if (warp <= kFW) {
+        // ===== filter warps =====
+        // Per stage: (1) every source of the staged tiles is tested against the target block's circle
+        // with the lobe test (lobe_reaches2): most sources near the block cannot matter for any of its
+        // targets, because a source's field reaches far only in a narrow range of directions;
+        // (2) the survivors are appended, in stream order, to the open survivor buffer (same tile
+        // layout); when it has reached its capacity (buffer_cap), and when the item closes, the buffer
+        // gets its bounding circles and is published to the evaluate warps.
+        const int fw = warp - 1, ftid = fw * 32 + lane;
+        uint32_t it = 0, bk = 0;             // stages consumed, buffers published
+        int cur = -1, count = 0, par = 0, kbuf = 0, surv = 0;
+        uint32_t n_open = 0;                 // items opened
+        bool have_slot = false;
+        Tile<T> blk;                         // bounding circle of the block's targets
+        auto write_entry = [&](unsigned char* sb, int kidx, P x, P y, T c, T s) {
+            unsigned char* tb = sb + (size_t)(kidx >> 6) * kTileB;
+            const int r = kidx & 63, l = r & 31, h = r >> 5;
+            P* pa = reinterpret_cast<P*>(reinterpret_cast<SrcA<T>*>(tb) + l);
+            T* pb = reinterpret_cast<T*>(reinterpret_cast<SrcB<T>*>(tb + 32 * sizeof(SrcA<T>)) + l);
+            pa[h] = x;
+            pa[2 + h] = y;
+            pb[h] = c;
+            pb[2 + h] = s;
+        };
+        // retire buffer b: wait until every evaluate warp has left it.  If it was the last buffer of an
+        // item, every buffer of that item has been evaluated by now (buffer b - 1 was retired before its
+        // slot was refilled): the item's sums go out, target q by filter thread q, and its accumulators
+        // are cleared for the item after the next one.
+        int pend_item0 = -1, pend_item1 = -1, pend_par0 = 0, pend_par1 = 0;     // per slot
+        auto retire = [&](uint32_t b) {
+            const int slot = (int)(b & 1u);
+            if (lane == 0) mbar_wait_backoff(&freeb[slot], (b >> 1) & 1);
+            __syncwarp();
+            const int p_item = slot ? pend_item1 : pend_item0, p_par = slot ? pend_par1 : pend_par0;
+            if (p_item >= 0) {
+                const int tb = p_item % n_tblocks, cg = p_item / n_tblocks;
+                T* a0 = bacc + (size_t)p_par * 2 * kBT * 2;
+                for (int q = ftid; q < kBT; q += kFW * 32) {
+                    const long long jj = bj[p_par * kBT + q];
+                    const T sx = a0[q * 2] + a0[kBT * 2 + q * 2], sy = a0[q * 2 + 1] + a0[kBT * 2 + q * 2 + 1];
+                    a0[q * 2] = a0[q * 2 + 1] = a0[kBT * 2 + q * 2] = a0[kBT * 2 + q * 2 + 1] = (T)0;
+                    if (jj >= 0 && (int64_t)tb * kBT + q < n_tgt) {
+                        partial[((size_t)cg * n_tgt + (size_t)jj) * 2] = sx;
+                        partial[((size_t)cg * n_tgt + (size_t)jj) * 2 + 1] = sy;
+                    }
+                }
+                if (slot) pend_item1 = -1; else pend_item0 = -1;
+            }
+        };
+        auto acquire = [&]() {               // the slot of buffer bk is free when buffer bk - 2 has been retired
+            if (bk >= 2) retire(bk - 2);
+            have_slot = true;
+            count = 0;
+        };
+        // every append is followed by a filter_barrier before publish() is entered
+        auto publish = [&](int flags) {
+            const int slot = bk & 1;
+            unsigned char* sb = sbuf + (size_t)slot * kCT * kTileB;
+            const int n_dt = (count + kTileS - 1) / kTileS;
+            {   // pad the last dynamic tile with far-away sentinels (they contribute exactly 0)
+                Xycs<T> pad;
+                pad_entry(pad);
+                for (int kidx = count + ftid; kidx < n_dt * kTileS; kidx += kFW * 32)
+                    write_entry(sb, kidx, pos_x(pad), pos_y(pad), pad.c, pad.s);
+            }
+            for (int t = fw; t < n_dt; t += kFW) {            // circles of the dynamic tiles
+                const int valid = min(kTileS, count - t * kTileS);
+                const SrcA<T> A = reinterpret_cast<const SrcA<T>*>(sb + (size_t)t * kTileB)[lane];
+                BBox<T> bb;
+                if (lane < valid) bb.add(A.x0, A.y0);
+                if (lane + 32 < valid) bb.add(A.x1, A.y1);
+                bb.warp_reduce();
+                if (lane == 0) dtile[slot * kCT + t] = bb.circle(valid);
+            }
+            filter_barrier();
+            if (ftid == 0) {
+                bdesc[slot] = make_int4(cur, n_dt, flags, par | ((kbuf & 1) << 1));
+                nextq[slot] = 0;
+                mbar_arrive(&ready[slot]);
+            }
+            if (flags & BUF_LAST) {
+                if (slot) { pend_item1 = cur; pend_par1 = par; } else { pend_item0 = cur; pend_par0 = par; }
+            }
+            ++bk;
+            ++kbuf;
+            have_slot = false;
+        };
+        for (;;) {
             const int stage = it % kStages;
-            const uint32_t phase = (it / kStages) & 1;
-            mbar_wait_backoff(&empty[stage], phase ^ 1);
-            hdr[stage] = make_int4(0, -2, 0, 0);
-            mbar_arrive(&full[stage]);
+            if (lane == 0) mbar_wait_backoff(&full[stage], (it / kStages) & 1);
+            __syncwarp();
+            const int item = hdr[stage].x, n = hdr[stage].y;
+            if (n == -2) {
+                acquire();
+                if (bk >= 1) retire(bk - 1);                  // every item's sums are out
+                publish(BUF_EXIT);
+                break;
+            }
+            if (item != cur) {
+                // open the item.  The free slot also says that the last item but one has been retired, so
+                // its set of targets may be overwritten.
+                acquire();
+                cur = item;
+                kbuf = 0;
+                surv = 0;
+                par = (int)(n_open++ & 1u);
+                const int tb = cur % n_tblocks;
+                blk = tblocks[tb];
+                for (int q = ftid; q < kBT; q += kFW * 32) {
+                    const int64_t t = (int64_t)tb * kBT + q;
+                    long long myj = -1;
+                    Xycs<T> e;
+                    pad_entry(e);
+                    if (t < n_tgt) {
+                        myj = tgt_perm ? tgt_perm[t] : t;
+                        e = tgt[myj];
+                    }
+                    btgt[par * kBT + q] = e;
+                    bj[par * kBT + q] = myj;
+                }
+            }
+            if (n == -1) {
+                if (!have_slot) acquire();
+                filter_barrier();                             // targets / last appends have landed
+                publish(BUF_LAST);
+                if (item_cost && ftid == 0) item_cost[cur] = (unsigned int)surv;
+            } else {
+                const unsigned char* base = stage_src + (size_t)stage * kST * kTileB;
+                uint2* fm = fmask + stage * kST;
+                // (1) filter this warp's tiles of the stage
+                constexpr int kTPW = kST / kFW;
+                uint32_t mb0[kTPW], mb1[kTPW];
+#pragma unroll
+                for (int u = 0; u < kTPW; ++u) {
+                    const int t = fw + u * kFW;
+                    mb0[u] = mb1[u] = 0;
+                    if (t < n) {                              // warp-uniform
+                        const int valid = (int)srec[stage * kST + t].cnt;
+                        const SrcA<T> A = reinterpret_cast<const SrcA<T>*>(base + (size_t)t * kTileB)[lane];
+                        const SrcB<T> B = reinterpret_cast<const SrcB<T>*>(base + (size_t)t * kTileB + 32 * sizeof(SrcA<T>))[lane];
+                        bool p0, p1;
+                        lobe_reaches2(blk, A, B, lobe, k.tiny, p0, p1);
+                        mb0[u] = __ballot_sync(0xffffffffu, p0 && (lane < valid));
+                        mb1[u] = __ballot_sync(0xffffffffu, p1 && (lane + 32 < valid));
+                        if (kFW > 1 && lane == 0) fm[t] = make_uint2(mb0[u], mb1[u]);
+                    }
+                }
+                // (2) append in stream order: prefix over the stage's tiles (every filter warp computes it)
+                uint2 mm = make_uint2(0u, 0u);
+                if (kFW > 1) {
+                    filter_barrier();
+                    if (lane < n) mm = fm[lane];
+                } else {
+#pragma unroll
+                    for (int u = 0; u < kTPW; ++u)
+                        if (lane == u) mm = make_uint2(mb0[u], mb1[u]);
+                }
+                const int c8 = __popc(mm.x) + __popc(mm.y);
+                int incl = c8;
+#pragma unroll
+                for (int o = 1; o < kST; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int tot = __shfl_sync(0xffffffffu, incl, kST - 1);
+                if (have_slot && count + tot > kCS) publish(0);     // (warp-uniform, the same in every filter warp)
+                if (!have_slot) acquire();
+                unsigned char* sb = sbuf + (size_t)(bk & 1) * kCT * kTileB;
+                const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+                for (int u = 0; u < kTPW; ++u) {
+                    const int t = fw + u * kFW;
+                    if (t < n && (mb0[u] | mb1[u])) {
+                        const int off = count + __shfl_sync(0xffffffffu, incl - c8, t);
+                        const SrcA<T> A = reinterpret_cast<const SrcA<T>*>(base + (size_t)t * kTileB)[lane];
+                        const SrcB<T> B = reinterpret_cast<const SrcB<T>*>(base + (size_t)t * kTileB + 32 * sizeof(SrcA<T>))[lane];
+                        if ((mb0[u] >> lane) & 1u)
+                            write_entry(sb, off + __popc(mb0[u] & lt), A.x0, A.y0, B.c0, B.s0);
+                        if ((mb1[u] >> lane) & 1u)
+                            write_entry(sb, off + __popc(mb0[u]) + __popc(mb1[u] & lt), A.x1, A.y1, B.c1, B.s1);
+                    }
+                }
+                count += tot;
+                surv += tot;
+                filter_barrier();                             // the appends have landed, the stage has been read
+                if (count >= buffer_cap(kbuf)) publish(0);
+            }
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            ++it;
         }
         return;
     }
 
-    // ===== consumer warps =====
-    // Per streamed chunk: (1) filter -- every source is tested against the target block's circle with
-    // the lobe test (lobe_reaches): most sources of a chunk near the block cannot matter for any of its
-    // targets, because a source's field reaches far only in a narrow range of directions; the
-    // survivors are appended, in stream order, to a shared-memory buffer that holds one chunk's worth
-    // (16 dynamic tiles of 64) in the same tile layout.  When the buffer would overflow, and when the
-    // item closes, it is flushed: (2) bounding circles of the dynamic tiles, (3) cull -- every warp
-    // tests its own targets' view cones against the 16 circles, two targets per pass, and appends
-    // (target, tile mask) entries to a work list, (4) evaluate -- warps take entries from the list one
-    // at a time (shared counter; the targets' headings make the per-target work very uneven).
-    // One warp per (target, flush), flushes separated by barriers: deterministic sums, no float atomics.
-    uint32_t it = 0;
+    // ===== evaluate warps =====
+    // Per survivor buffer the warps take the block's targets two at a time from a shared counter (the
+    // targets' headings make the work per target very uneven): cull -- the view cones of the two
+    // targets against the 16 circles (lanes 0-15 / 16-31, one ballot); evaluate -- the surviving tiles
+    // two at a time (four independent pair evaluations per lane in flight), one butterfly reduces both
+    // force components (lanes 0-15: x, 16-31: y), one lane each adds them to the target's accumulator.
+    // A (buffer, target) sum is formed by one warp in a fixed order whoever takes it, and buffers that
+    // may be in flight together use different accumulators (parity of the buffer's number within its
+    // item, parity of the item): every sum is deterministic.
     unsigned long long n_eval = 0;
-    int cur = -1, cg = 0, nq = 0, count = 0;
-    const int q0 = warp * tpw;           // this warp's targets in the block: [q0, q0 + nq)
-    long long myj = -1;
-    Tile<T> blk;                         // bounding circle of the block's targets
-    typedef decltype(SrcA<T>().x0) P;    // payload position type
-
-    auto write_entry = [&](int kidx, P x, P y, T c, T s) {
-        unsigned char* tb = sbuf + (size_t)(kidx >> 6) * TileBytes<T>::v;
-        const int r = kidx & 63, l = r & 31, h = r >> 5;
-        P* pa = reinterpret_cast<P*>(reinterpret_cast<SrcA<T>*>(tb) + l);
-        T* pb = reinterpret_cast<T*>(reinterpret_cast<SrcB<T>*>(tb + 32 * sizeof(SrcA<T>)) + l);
-        pa[h] = x;
-        pa[2 + h] = y;
-        pb[h] = c;
-        pb[2 + h] = s;
-    };
-    auto cull = [&](int nt) {
-        const int tl = lane & (kCT - 1), half = lane >> 4;
-        Tile<T> mytile;
-        if (tl < nt) mytile = dtile[tl];
-        for (int i0 = 0; i0 < nq; i0 += 2) {          // warp-uniform trip count (ballot inside)
-            const int i = i0 + half;
-            const bool valid = (i < nq) && (tl < nt);
-            const Xycs<T> te = btgt[q0 + (i < nq ? i : 0)];
-            const Tgt<T> tg = *reinterpret_cast<const Tgt<T>*>(&te);
-            const bool v = valid && tile_visible<T, P2R>(mytile, tg, cc);
-            const uint32_t m2 = __ballot_sync(0xffffffffu, v);
-            const uint32_t m = half ? (m2 >> 16) : (m2 & 0xffffu);
-            if (tl == 0 && m) {
-                wlist[atomicAdd(&lctl[0], 1)] = ((uint32_t)(q0 + i) << 16) | m;
-                if (stats) n_eval += (unsigned long long)__popc(m) * kTileS;
-            }
-        }
-    };
-    auto evaluate = [&]() {
-        const unsigned char* base = sbuf;
-        const int n_list = lctl[0];
-        for (;;) {
-            int e = 0;
-            if (lane == 0) e = atomicAdd(&lctl[1], 1);
-            e = __shfl_sync(0xffffffffu, e, 0);
-            if (e >= n_list) break;
-            const uint32_t ent = wlist[e];
-            const int q = (int)(ent >> 16);
-            uint32_t mask = ent & 0xffffu;
-            const Xycs<T> te = btgt[q];
-            const Tgt<T> tg = *reinterpret_cast<const Tgt<T>*>(&te);
-            typename TileAccSel<T, P2R>::type acc0, acc1;
-            // two surviving tiles per iteration: four independent pair evaluations in flight
-            while (mask & (mask - 1)) {
-                const int t0 = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const int t1 = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const unsigned char* p0 = base + (size_t)t0 * TileBytes<T>::v;
-                const unsigned char* p1 = base + (size_t)t1 * TileBytes<T>::v;
-                const SrcA<T> A0 = reinterpret_cast<const SrcA<T>*>(p0)[lane];
-                const SrcB<T> B0 = reinterpret_cast<const SrcB<T>*>(p0 + 32 * sizeof(SrcA<T>))[lane];
-                const SrcA<T> A1 = reinterpret_cast<const SrcA<T>*>(p1)[lane];
-                const SrcB<T> B1 = reinterpret_cast<const SrcB<T>*>(p1 + 32 * sizeof(SrcA<T>))[lane];
-                acc0.eval(A0, B0, tg, k);
-                acc1.eval(A1, B1, tg, k);
-            }
-            if (mask) {
-                const int t0 = __ffs(mask) - 1;
-                const unsigned char* p0 = base + (size_t)t0 * TileBytes<T>::v;
-                const SrcA<T> A0 = reinterpret_cast<const SrcA<T>*>(p0)[lane];
-                const SrcB<T> B0 = reinterpret_cast<const SrcB<T>*>(p0 + 32 * sizeof(SrcA<T>))[lane];
-                acc0.eval(A0, B0, tg, k);
-            }
-            acc0.merge(acc1);
-            T ax, ay;
-            acc0.total(ax, ay);
-            // both sums in one butterfly: lanes 0-15 reduce x, lanes 16-31 reduce y
-            const bool upper = lane >= 16;
-            T mine = upper ? ay : ax;
-            const T other = upper ? ax : ay;
-            mine += __shfl_xor_sync(0xffffffffu, other, 16);
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-            if ((lane & 15) == 0) bacc[q * 2 + (lane >> 4)] += mine;
-        }
-    };
-    // evaluate the `count` survivors in the buffer against every target of the block
-    auto flush = [&]() {
-        consumer_barrier();                                   // every append has landed
-        const int n_dt = (count + kTileS - 1) / kTileS;
-        {   // pad the last dynamic tile with far-away sentinels (they contribute exactly 0)
-            Xycs<T> pad;
-            pad_entry(pad);
-            for (int kidx = count + (int)threadIdx.x; kidx < n_dt * kTileS; kidx += kTW * 32)
-                write_entry(kidx, pos_x(pad), pos_y(pad), pad.c, pad.s);
-        }
-        if (threadIdx.x == 0) { lctl[0] = 0; lctl[1] = 0; }
-        for (int t = warp; t < n_dt; t += kTW) {              // circles of the dynamic tiles
-            const int valid = min(kTileS, count - t * kTileS);
-            const SrcA<T> A = reinterpret_cast<const SrcA<T>*>(sbuf + (size_t)t * TileBytes<T>::v)[lane];
-            BBox<T> bb;
-            if (lane < valid) bb.add(A.x0, A.y0);
-            if (lane + 32 < valid) bb.add(A.x1, A.y1);
-            bb.warp_reduce();
-            if (lane == 0) dtile[t] = bb.circle(valid);
-        }
-        consumer_barrier();
-        cull(n_dt);
-        consumer_barrier();
-        evaluate();
-        consumer_barrier();                                   // the buffer may be overwritten again
-    };
-
-    for (;;) {
-        const int stage = it % kStages;
-        mbar_wait(&full[stage], (it / kStages) & 1);
-        const int item = hdr[stage].x, chunk = hdr[stage].y;
-        if (chunk == -2) break;
-        if (item != cur) {
-            // open the item: lane i < nq of each warp fetches the warp's target i
-            cur = item;
-            const int tb = cur % n_tblocks;
-            cg = cur / n_tblocks;
-            blk = tblocks[tb];
-            const int64_t t_first = ((int64_t)tb * kTW + warp) * tpw;
-            const int64_t left = n_tgt - t_first;
-            nq = (int)(left < 0 ? 0 : (left < tpw ? left : tpw));
-            myj = -1;
-            count = 0;
-            if (lane < nq) {
-                myj = tgt_perm ? tgt_perm[t_first + lane] : (t_first + lane);
-                btgt[q0 + lane] = tgt[myj];
-            }
-            if (lane < 2 * nq) bacc[q0 * 2 + lane] = (T)0;
-            __syncwarp();
-        }
-        if (chunk == -1) {
-            // close the item: evaluate what is left in the buffer, then write this warp's targets
-            if (count > 0) flush();
-            count = 0;
-            const long long jj = __shfl_sync(0xffffffffu, myj, (lane >> 1) & (kMaxTPW - 1));
-            if ((lane >> 1) < nq) partial[((size_t)cg * n_tgt + (size_t)jj) * 2 + (lane & 1)] = bacc[q0 * 2 + lane];
-        } else {
-            const int nt = (int)min((int64_t)kCT, n_tiles - (int64_t)chunk * kCT);
-            const unsigned char* base = smem_raw + stage * kStageBytes;
-            const Tile<T>* trec = reinterpret_cast<const Tile<T>*>(base + (size_t)kCS * sizeof(Xycs<T>));
-            uint2* fm = fmask + stage * kCT;
-            // (1a) filter: this warp's tiles of the chunk; tiles wholly out of reach of the block first
-            uint32_t tnear;
-            {
-                const int tl = lane & (kCT - 1);
-                tnear = __ballot_sync(0xffffffffu, tl < nt && circles_near(trec[tl < nt ? tl : 0], blk, cc.dmax));
-            }
-            for (int t = warp; t < kCT; t += kTW) {
-                uint32_t b0 = 0, b1 = 0;
-                if ((tnear >> t) & 1u) {
-                    const int valid = (int)trec[t].cnt;
-                    const SrcA<T> A = reinterpret_cast<const SrcA<T>*>(base + (size_t)t * TileBytes<T>::v)[lane];
-                    const SrcB<T> B = reinterpret_cast<const SrcB<T>*>(base + (size_t)t * TileBytes<T>::v + 32 * sizeof(SrcA<T>))[lane];
-                    bool p0, p1;
-                    lobe_reaches2(blk, A, B, lobe, k.tiny, p0, p1);
-                    b0 = __ballot_sync(0xffffffffu, p0 && (lane < valid));
-                    b1 = __ballot_sync(0xffffffffu, p1 && (lane + 32 < valid));
+    for (uint32_t bk = 0;; ++bk) {
+        const int slot = (int)(bk & 1u);
+        if (lane == 0) mbar_wait_backoff(&ready[slot], (bk >> 1) & 1);
+        __syncwarp();
+        const int4 d = bdesc[slot];
+        if (d.z & BUF_EXIT) break;
+        const int n_dt = d.y, par = d.w & 1, kpar = (d.w >> 1) & 1;
+        const int tb = d.x % n_tblocks;
+        const int64_t left = n_tgt - (int64_t)tb * kBT;
+        const int nvalid = (int)(left < kBT ? left : kBT);
+        if (n_dt > 0) {
+            const unsigned char* base = sbuf + (size_t)slot * kCT * kTileB;
+            const Xycs<T>* mytgt = btgt + par * kBT;
+            T* acc = bacc + (size_t)(par * 2 + kpar) * kBT * 2;
+            const int tl = lane & (kCT - 1), half = lane >> 4;
+            Tile<T> mytile;
+            if (tl < n_dt) mytile = dtile[slot * kCT + tl];
+            for (;;) {
+                int q0 = 0;
+                if (lane == 0) q0 = atomicAdd(&nextq[slot], 2);
+                q0 = __shfl_sync(0xffffffffu, q0, 0);
+                if (q0 >= nvalid) break;
+                uint32_t m2;
+                {
+                    const int qh = q0 + half;
+                    const Xycs<T> te = mytgt[qh < nvalid ? qh : q0];
+                    const Tgt<T> tg = *reinterpret_cast<const Tgt<T>*>(&te);
+                    const bool v = (qh < nvalid) && (tl < n_dt) && tile_visible<T, P2R>(mytile, tg, cc);
+                    m2 = __ballot_sync(0xffffffffu, v);
                 }
-                if (lane == 0) fm[t] = make_uint2(b0, b1);
-            }
-            consumer_barrier();
-            // (1b) append in stream order: prefix over the chunk's 16 tiles (every warp computes it)
-            const uint2 mm = fm[lane & (kCT - 1)];
-            const int c16 = __popc(mm.x) + __popc(mm.y);
-            int incl = c16;
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t mask = h ? (m2 >> 16) : (m2 & 0xffffu);
+                    if (mask == 0) continue;
+                    const int q = q0 + h;
+                    if (stats) n_eval += (unsigned long long)__popc(mask) * kTileS;
+                    const Xycs<T> te = mytgt[q];
+                    const Tgt<T> tg = *reinterpret_cast<const Tgt<T>*>(&te);
+                    typename TileAccSel<T, P2R>::type acc0, acc1;
+                    // two surviving tiles per iteration: four independent pair evaluations in flight
+                    while (mask & (mask - 1)) {
+                        const int t0 = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const int t1 = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const unsigned char* p0 = base + (size_t)t0 * kTileB;
+                        const unsigned char* p1 = base + (size_t)t1 * kTileB;
+                        const SrcA<T> A0 = reinterpret_cast<const SrcA<T>*>(p0)[lane];
+                        const SrcB<T> B0 = reinterpret_cast<const SrcB<T>*>(p0 + 32 * sizeof(SrcA<T>))[lane];
+                        const SrcA<T> A1 = reinterpret_cast<const SrcA<T>*>(p1)[lane];
+                        const SrcB<T> B1 = reinterpret_cast<const SrcB<T>*>(p1 + 32 * sizeof(SrcA<T>))[lane];
+                        acc0.eval(A0, B0, tg, k);
+                        acc1.eval(A1, B1, tg, k);
+                    }
+                    if (mask) {
+                        const int t0 = __ffs(mask) - 1;
+                        const unsigned char* p0 = base + (size_t)t0 * kTileB;
+                        const SrcA<T> A0 = reinterpret_cast<const SrcA<T>*>(p0)[lane];
+                        const SrcB<T> B0 = reinterpret_cast<const SrcB<T>*>(p0 + 32 * sizeof(SrcA<T>))[lane];
+                        acc0.eval(A0, B0, tg, k);
+                    }
+                    acc0.merge(acc1);
+                    T ax, ay;
+                    acc0.total(ax, ay);
+                    // both sums in one butterfly: lanes 0-15 reduce x, lanes 16-31 reduce y
+                    const bool upper = lane >= 16;
+                    T mine = upper ? ay : ax;
+                    const T other = upper ? ax : ay;
+                    mine += __shfl_xor_sync(0xffffffffu, other, 16);
 #pragma unroll
-            for (int o = 1; o < kCT; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if ((lane & (kCT - 1)) >= o) incl += v;
+                    for (int o = 8; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+                    if ((lane & 15) == 0) acc[q * 2 + (lane >> 4)] += mine;
+                }
             }
-            const int tot = __shfl_sync(0xffffffffu, incl, kCT - 1);
-            if (count + tot > kCS) {                          // warp-uniform and the same in every warp
-                flush();
-                count = 0;
-            }
-            for (int t = warp; t < nt; t += kTW) {
-                const int off = count + __shfl_sync(0xffffffffu, incl - c16, t);
-                const uint32_t b0 = __shfl_sync(0xffffffffu, mm.x, t), b1 = __shfl_sync(0xffffffffu, mm.y, t);
-                if ((b0 | b1) == 0) continue;
-                const SrcA<T> A = reinterpret_cast<const SrcA<T>*>(base + (size_t)t * TileBytes<T>::v)[lane];
-                const SrcB<T> B = reinterpret_cast<const SrcB<T>*>(base + (size_t)t * TileBytes<T>::v + 32 * sizeof(SrcA<T>))[lane];
-                const uint32_t lt = (1u << lane) - 1u;
-                if ((b0 >> lane) & 1u) write_entry(off + __popc(b0 & lt), A.x0, A.y0, B.c0, B.s0);
-                if ((b1 >> lane) & 1u) write_entry(off + __popc(b0) + __popc(b1 & lt), A.x1, A.y1, B.c1, B.s1);
-            }
-            count += tot;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
-        ++it;
+        if (lane == 0) mbar_arrive(&freeb[slot]);
     }
-    if (stats && n_eval) atomicAdd(stats, n_eval);
+    if (stats && n_eval && lane == 0) atomicAdd(stats, n_eval);
+}
+
+// Items in the order of decreasing cost (one CTA, bitonic sort in shared memory): handed out in this
+// order by the atomic counter, the heaviest items start first and the last ones to start are the
+// lightest -- the tail of the launch (SMs idle while the last items finish) shrinks from about one
+// mean item to about one of the cheapest.  cost = survivors the item's filter produced in the previous
+// launch (the crowd moves a few centimetres per step).  Any order gives the same forces.
+constexpr int kMaxOrderItems = 4096;
+__global__ void __launch_bounds__(1024) item_order_kernel(const unsigned int* __restrict__ cost, int n,
+                                                          unsigned int* __restrict__ order) {
+    __shared__ unsigned long long key[kMaxOrderItems];
+    int m = 1;
+    while (m < n) m <<= 1;
+    for (int i = threadIdx.x; i < m; i += blockDim.x)      // descending cost, ties by index: ~cost in the high word
+        key[i] = i < n ? (((unsigned long long)(~cost[i])) << 32) | (unsigned int)i : ~0ull;
+    __syncthreads();
+    for (int k2 = 2; k2 <= m; k2 <<= 1)
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long a = key[i], b = key[l];
+                    const bool up = (i & k2) == 0;
+                    if ((a > b) == up) { key[i] = b; key[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) order[i] = (unsigned int)(key[i] & 0xffffffffu);
 }
 
 template <typename T>
@@ -712,17 +866,24 @@ __global__ void reduce_groups_kernel(const T* __restrict__ partial, int n_groups
 
 template <typename T> size_t tiled_smem_bytes() {
     constexpr int kStages = Stages<T>::n;
-    return kStages * ((size_t)kCS * sizeof(Xycs<T>) + (size_t)kCT * sizeof(Tile<T>)) +
-           2 * kStages * sizeof(uint64_t) + kStages * sizeof(int4) +
-           (size_t)kCS * sizeof(Xycs<T>) + (size_t)kCT * sizeof(Tile<T>) + (size_t)kTB * sizeof(Xycs<T>) +
-           (size_t)kTB * 2 * sizeof(T) + (size_t)kLobeBins * sizeof(T) + (size_t)kTB * sizeof(uint32_t) +
-           (size_t)kStages * kCT * sizeof(uint2) + 4 * sizeof(int);
+    return (size_t)kStages * kST * TileBytes<T>::v + (size_t)2 * kCT * TileBytes<T>::v +
+           (size_t)(kStages * kST + 2 * kCT) * sizeof(Tile<T>) + (size_t)2 * kBT * sizeof(Xycs<T>) +
+           (size_t)2 * kBT * sizeof(long long) + (size_t)(2 * kStages + 4) * sizeof(uint64_t) +
+           (size_t)(kStages + 2) * sizeof(int4) + (size_t)kStages * kST * sizeof(uint2) +
+           (size_t)kLobeBins * sizeof(T) + (size_t)2 * 2 * kBT * 2 * sizeof(T) + 4 * sizeof(int);
 }
 
-int g_tiled_ctas[2] = {0, 0};
-template <typename T> int tiled_ctas() {
+// Resident CTAs per SM of the tiled kernel and the SM count, per device (the shared-memory attribute
+// is a per-device property of the function too).
+constexpr int kMaxDevices = 64;
+int g_tiled_ctas[2][kMaxDevices];
+int g_tiled_sms[kMaxDevices];
+template <typename T> int tiled_ctas(int* sm_count) {
     const int idx = sizeof(T) == 4 ? 0 : 1;
-    if (g_tiled_ctas[idx] == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) dev = 0;
+    if (g_tiled_ctas[idx][dev] == 0) {
         int best = 1 << 30;
         const size_t smem = tiled_smem_bytes<T>();
         {
@@ -739,9 +900,13 @@ template <typename T> int tiled_ctas() {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kTThreads, smem);
             best = nb < best ? nb : best;
         }
-        g_tiled_ctas[idx] = best < 1 ? 1 : best;
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        g_tiled_sms[dev] = sms > 0 ? sms : 148;
+        g_tiled_ctas[idx][dev] = best < 1 ? 1 : best;
     }
-    return g_tiled_ctas[idx];
+    if (sm_count) *sm_count = g_tiled_sms[dev];
+    return g_tiled_ctas[idx][dev];
 }
 
 int env_int(const char* name, int dflt) {
@@ -749,26 +914,23 @@ int env_int(const char* name, int dflt) {
     return (s && *s) ? atoi(s) : dflt;
 }
 
-// Work decomposition: target blocks of kTW * tpw targets; if there are too few blocks to keep every
-// CTA slot busy with several items, shrink tpw (down to 4) and then split the chunk range in groups.
-struct TiledPlan { int tpw, n_tblocks, n_groups, group_chunks, grid; int64_t n_tiles, n_chunks; };
+// Work decomposition: target blocks of kBT targets; if there are too few blocks to keep every CTA slot
+// busy with several items, the chunk range of each block is split in groups.
+struct TiledPlan { int n_tblocks, n_groups, group_chunks, grid; int64_t n_tiles, n_chunks; };
 template <typename T> TiledPlan tiled_plan(int64_t n_src, int64_t n_tgt) {
-    static const int env_tpw = env_int("CSF_TILED_TPW", 0), env_groups = env_int("CSF_TILED_GROUPS", 0),
-                     env_ipw = env_int("CSF_TILED_ITEMS_PER_SLOT", 4);
+    static const int env_groups = env_int("CSF_TILED_GROUPS", 0), env_ipw = env_int("CSF_TILED_ITEMS_PER_SLOT", 4);
     TiledPlan p;
     p.n_tiles = (n_src + kTileS - 1) / kTileS;
     p.n_chunks = (p.n_tiles + kCT - 1) / kCT;
-    const int64_t slots = (int64_t)csf_sm_count() * tiled_ctas<T>();
+    int sms = 0;
+    const int64_t slots = (int64_t)tiled_ctas<T>(&sms) * sms;
     const int64_t want = (int64_t)env_ipw * slots;
     // 64 targets per block balance the lobe filter's cost (per block) against its selectivity (block
     // radius).  Items must be plentiful -- a few per CTA slot -- because their cost follows the local
     // density of the crowd (a jammed cluster costs several times the mean) and an item is the unit of
     // dynamic scheduling: when there are too few blocks, the chunk range of each block is split over
     // several items (each chunk is still filtered once per block).
-    int tpw = 8;
-    while (tpw > 1 && (int64_t)kTW * tpw > 2 * n_tgt) tpw >>= 1;      // tiny crowds
-    if (env_tpw >= 1 && env_tpw <= kMaxTPW) tpw = env_tpw;
-    const int64_t tb = (n_tgt + (int64_t)kTW * tpw - 1) / ((int64_t)kTW * tpw);
+    const int64_t tb = (n_tgt + kBT - 1) / kBT;
     int64_t groups = (want + tb - 1) / tb;
     if (groups > 8) groups = 8;
     if (env_groups >= 1) groups = env_groups;
@@ -777,7 +939,6 @@ template <typename T> TiledPlan tiled_plan(int64_t n_src, int64_t n_tgt) {
     if (groups > p.n_chunks) groups = p.n_chunks;
     const int64_t gc = (p.n_chunks + groups - 1) / groups;
     groups = (p.n_chunks + gc - 1) / gc;
-    p.tpw = tpw;
     p.n_tblocks = (int)tb;
     p.n_groups = (int)groups;
     p.group_chunks = (int)gc;
@@ -912,7 +1073,7 @@ template <typename T> size_t tiled_ws_blocks_bytes(const TiledPlan& pl) {
 template <typename T>
 int pair_tiled(const void* sorted, const void* tiles, int64_t n_src, const void* tgt, const int64_t* tgt_perm,
                int64_t n_tgt, const CsfFieldParams* fp, T* frep, int accumulate, void* ws, size_t wsb,
-               unsigned long long* stats, cudaStream_t st) {
+               const unsigned int* item_order, unsigned int* item_cost, unsigned long long* stats, cudaStream_t st) {
     if (n_tgt <= 0) return 0;
     if (n_src <= 0 || fp->f_0 == 0.0) {
         if (!accumulate) cudaMemsetAsync(frep, 0, sizeof(T) * 2 * n_tgt, st);
@@ -932,17 +1093,16 @@ int pair_tiled(const void* sorted, const void* tiles, int64_t n_src, const void*
     Tile<T>* tblocks = reinterpret_cast<Tile<T>*>((unsigned char*)ws + kWsHeader);
     T* partial = reinterpret_cast<T*>((unsigned char*)ws + off_partial);
     block_bounds_kernel<T><<<(unsigned)(((int64_t)pl.n_tblocks * 32 + 127) / 128), 128, 0, st>>>(
-        (const Xycs<T>*)tgt, tgt_perm, n_tgt, kTW * pl.tpw, tblocks, pl.n_tblocks, counter);
+        (const Xycs<T>*)tgt, tgt_perm, n_tgt, kBT, tblocks, pl.n_tblocks, counter);
     CSF_CHECK_LAUNCH("block_bounds_kernel");
-    tiled_ctas<T>();   // sets the dynamic shared-memory attribute
     if (fp->p2r)
         pair_tiled_kernel<T, true><<<pl.grid, kTThreads, smem, st>>>(
             (const unsigned char*)sorted, (const Tile<T>*)tiles, pl.n_tiles, (const Xycs<T>*)tgt, tgt_perm, n_tgt,
-            tblocks, k, cc, partial, pl.tpw, pl.group_chunks, pl.n_groups, pl.n_tblocks, counter, stats);
+            tblocks, k, cc, partial, pl.group_chunks, pl.n_groups, pl.n_tblocks, counter, item_order, item_cost, stats);
     else
         pair_tiled_kernel<T, false><<<pl.grid, kTThreads, smem, st>>>(
             (const unsigned char*)sorted, (const Tile<T>*)tiles, pl.n_tiles, (const Xycs<T>*)tgt, tgt_perm, n_tgt,
-            tblocks, k, cc, partial, pl.tpw, pl.group_chunks, pl.n_groups, pl.n_tblocks, counter, stats);
+            tblocks, k, cc, partial, pl.group_chunks, pl.n_groups, pl.n_tblocks, counter, item_order, item_cost, stats);
     CSF_CHECK_LAUNCH("pair_tiled_kernel");
     const int64_t n2 = n_tgt * 2;
     reduce_groups_kernel<T><<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(partial, pl.n_groups, n_tgt, (T)fp->f_0, frep,
@@ -1021,15 +1181,32 @@ int csf_tile_sources_f64(const void* xycs, int64_t n, const int64_t* perm, void*
 }
 int csf_pair_forces_tiled_f32(const void* sorted, const void* tiles, int64_t n_src, const void* tgt,
                               const int64_t* tgt_perm, int64_t n_tgt, const CsfFieldParams* fp, float* frep,
-                              int accumulate, void* ws, size_t wsb, unsigned long long* stats, csf_stream_t st) {
-    return pair_tiled<float>(sorted, tiles, n_src, tgt, tgt_perm, n_tgt, fp, frep, accumulate, ws, wsb, stats,
-                             (cudaStream_t)st);
+                              int accumulate, void* ws, size_t wsb, const unsigned int* item_order,
+                              unsigned int* item_cost, unsigned long long* stats, csf_stream_t st) {
+    return pair_tiled<float>(sorted, tiles, n_src, tgt, tgt_perm, n_tgt, fp, frep, accumulate, ws, wsb, item_order,
+                             item_cost, stats, (cudaStream_t)st);
 }
 int csf_pair_forces_tiled_f64(const void* sorted, const void* tiles, int64_t n_src, const void* tgt,
                               const int64_t* tgt_perm, int64_t n_tgt, const CsfFieldParams* fp, double* frep,
-                              int accumulate, void* ws, size_t wsb, unsigned long long* stats, csf_stream_t st) {
-    return pair_tiled<double>(sorted, tiles, n_src, tgt, tgt_perm, n_tgt, fp, frep, accumulate, ws, wsb, stats,
-                              (cudaStream_t)st);
+                              int accumulate, void* ws, size_t wsb, const unsigned int* item_order,
+                              unsigned int* item_cost, unsigned long long* stats, csf_stream_t st) {
+    return pair_tiled<double>(sorted, tiles, n_src, tgt, tgt_perm, n_tgt, fp, frep, accumulate, ws, wsb, item_order,
+                              item_cost, stats, (cudaStream_t)st);
+}
+int64_t csf_tiled_num_items(int64_t n_src, int64_t n_tgt, int elem_bytes) {
+    if (n_src <= 0 || n_tgt <= 0) return 0;
+    const TiledPlan pl = elem_bytes == 4 ? tiled_plan<float>(n_src, n_tgt) : tiled_plan<double>(n_src, n_tgt);
+    return (int64_t)pl.n_tblocks * pl.n_groups;
+}
+int csf_tiled_item_order(const unsigned int* item_cost, int64_t n_items, unsigned int* item_order, csf_stream_t st) {
+    if (n_items <= 0) return 0;
+    if (n_items > kMaxOrderItems) {
+        csf_set_error("csf_tiled_item_order: more than 4096 items (pass item_order = NULL instead)", cudaErrorInvalidValue);
+        return -(int)cudaErrorInvalidValue;
+    }
+    item_order_kernel<<<1, 1024, 0, (cudaStream_t)st>>>(item_cost, (int)n_items, item_order);
+    CSF_CHECK_LAUNCH("item_order_kernel");
+    return 0;
 }
 
 }  // extern "C"

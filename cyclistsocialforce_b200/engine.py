@@ -461,6 +461,14 @@ class Engine:
                     tiles=torch.zeros((n_tiles, tile_elems), dtype=self.payload.dtype, device=self.device),
                     keys=torch.zeros(c, dtype=torch.int64, device=self.device),
                     perm=torch.zeros(c, dtype=torch.int64, device=self.device)))
+                # scheduling of the pair kernel's work items: cost per item (written by every launch) and
+                # the order to hand them out in (heaviest first; refreshed with the spatial order)
+                n_items = int(self.lib.csf_tiled_num_items(c, self.n_agents, eb))
+                tl = self._tiles[-1]
+                tl["n_items"] = n_items
+                tl["item_cost"] = torch.zeros(max(n_items, 1), dtype=torch.int32, device=self.device)
+                tl["item_order"] = (torch.arange(n_items, dtype=torch.int32, device=self.device)
+                                    if 0 < n_items <= 4096 else None)
                 wsb = max(wsb, int(self.lib.csf_pair_tiled_workspace_bytes(c, self.n_agents, eb)))
             # visiting order of the local targets (Morton order too: compact target blocks)
             self._tgt_keys = torch.zeros(self.n_agents, dtype=torch.int64, device=self.device)
@@ -534,6 +542,26 @@ class Engine:
             self._tgt_perm.copy_(torch.argsort(self._tgt_keys))
             self.gpu_launches += 1
         self._order_valid = True
+        self._refresh_item_order()
+
+    def _refresh_item_order(self):
+        """Hand the pair kernel's work items out heaviest first (costs measured by the previous launch)."""
+        st = self._stream()
+        for tl in self._tiles:
+            if tl.get("item_order") is not None:
+                _lib.check(self.lib.csf_tiled_item_order(_ptr(tl["item_cost"]), tl["n_items"],
+                                                         _ptr(tl["item_order"]), st), "csf_tiled_item_order")
+                self.gpu_launches += 1
+
+    def _maybe_refresh(self):
+        """Outside the step's kernel sequence (and outside its CUDA graph): the spatial order every
+        ``resort_every`` steps; the item order also right after the first launch has measured the costs."""
+        if not self.tiled:
+            return
+        if not self._order_valid or self._pair_calls % max(self.resort_every, 1) == 0:
+            self._refresh_order()
+        elif self._pair_calls == 1:
+            self._refresh_item_order()
 
     def _pair_and_road(self):
         st = self._stream()
@@ -555,9 +583,8 @@ class Engine:
                                                                _ptr(self.frep), st), "csf_pair_forces_grouped")
                 self.gpu_launches += 1
             else:
-                if self.tiled and not self._capturing and (
-                        not self._order_valid or self._pair_calls % max(self.resort_every, 1) == 0):
-                    self._refresh_order()
+                if not self._capturing:
+                    self._maybe_refresh()
                 self._pair_calls += 1
                 tgt = C.c_void_p(self.payload.data_ptr() + self.global_offset * self.elem_bytes)
                 for ci, (s, c, _, fp) in enumerate(self.classes):
@@ -579,7 +606,8 @@ class Engine:
                         _lib.check(self._fn("csf_pair_forces_tiled")(
                             _ptr(tl["sorted"]), _ptr(tl["tiles"]), c, tgt, _ptr(self._tgt_perm), self.n_agents,
                             C.byref(fp), _ptr(self.frep), 1 if ci > 0 else 0, _ptr(self.ws), self.ws.numel(),
-                            _ptr(self.pair_stats), st), "csf_pair_forces_tiled")
+                            _ptr(tl["item_order"]), _ptr(tl["item_cost"]), _ptr(self.pair_stats), st),
+                            "csf_pair_forces_tiled")
                         self.gpu_launches += 4   # tile build (+ chunk bounds), block bounds, pair, reduce
                         continue
                     _lib.check(self._fn("csf_pair_forces")(src, c, tgt, self.n_agents,
@@ -646,8 +674,7 @@ class Engine:
 
     def _step_graph(self):
         """The same kernel sequence replayed from a CUDA graph (launch-bound small crowds / shards)."""
-        if self.tiled and (not self._order_valid or self._pair_calls % max(self.resort_every, 1) == 0):
-            self._refresh_order()
+        self._maybe_refresh()
         self._exchange_in_graph = bool(getattr(self.exchange, "capturable", False))
         if self._graph is None:
             launches0 = self.gpu_launches

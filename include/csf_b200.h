@@ -128,6 +128,9 @@ typedef struct CsfAgentState {
     /* device-side status word: bit0 non-finite force/state seen, bit1 invalid nav state,
      * bit2 payload position out of Q range, bit3 degenerate spline (duplicate points) */
     int32_t* status;        /* [1] */
+    /* optional mirror in host-mapped (pinned) memory: set to 1 whenever `status` gets a bit, so that the
+     * host can poll every step without a copy or a synchronisation; may be NULL */
+    int32_t* status_host;   /* [1] */
 } CsfAgentState;
 
 /* ---- library ------------------------------------------------------------------ */
@@ -186,7 +189,13 @@ int csf_bicycle_eccentricity_f64(const double* v, int64_t n, double v_max, doubl
  *   csf_pair_forces_tiled_* : the pair force.  `tgt_perm` (may be NULL) = visiting order of the
  *                         targets (a spatial order makes the block-level culling effective;
  *                         frep is always written in target order); `stats` (may be NULL)
- *                         accumulates the number of pair evaluations actually executed. */
+ *                         accumulates the number of pair evaluations actually executed.
+ *                         Work items (target block x chunk group, csf_tiled_num_items of them) are
+ *                         handed out dynamically; `item_cost` (may be NULL) receives a cost measure
+ *                         per item, `item_order` (may be NULL) is the order to hand them out in
+ *   csf_tiled_item_order : item_order <- items by decreasing cost (<= 4096 items), to be passed to
+ *                         the next launches: the heaviest items start first, the launch has no
+ *                         tail.  Scheduling only: the forces do not depend on it. */
 int64_t csf_tiled_padded_sources(int64_t n_src);
 int64_t csf_tiled_num_tiles(int64_t n_src);
 int csf_tiled_tile_bytes(int elem_bytes);
@@ -212,11 +221,16 @@ int csf_tile_sources_f64(const void* xycs, int64_t n, const int64_t* perm, void*
 int csf_pair_forces_tiled_f32(const void* sorted, const void* tiles, int64_t n_src, const void* tgt_xycs,
                               const int64_t* tgt_perm, int64_t n_tgt, const CsfFieldParams* fp,
                               float* frep_xy, int accumulate, void* workspace, size_t workspace_bytes,
+                              const unsigned int* item_order, unsigned int* item_cost,
                               unsigned long long* stats, csf_stream_t stream);
 int csf_pair_forces_tiled_f64(const void* sorted, const void* tiles, int64_t n_src, const void* tgt_xycs,
                               const int64_t* tgt_perm, int64_t n_tgt, const CsfFieldParams* fp,
                               double* frep_xy, int accumulate, void* workspace, size_t workspace_bytes,
+                              const unsigned int* item_order, unsigned int* item_cost,
                               unsigned long long* stats, csf_stream_t stream);
+int64_t csf_tiled_num_items(int64_t n_src, int64_t n_tgt, int elem_bytes);
+int csf_tiled_item_order(const unsigned int* item_cost, int64_t n_items, unsigned int* item_order,
+                         csf_stream_t stream);
 
 /* ---- road-edge force ------------------------------------------------------------
  * Replaces RoadEdge.calcRepulsiveForce summed over edges (intersection.py:226-242,

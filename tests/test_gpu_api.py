@@ -197,41 +197,75 @@ def test_road_elements_in_intersection():
     assert np.abs(fx - ofx).max() < 1e-9 and np.abs(fy - ofy).max() < 1e-9
 
 
-def test_f32_per_step_error_against_f64_build():
-    """Per-step error of the fp32 production build: both builds start every step from the
-    same (fp64-build) state; north_star tolerance 1e-4 relative per step."""
+F32_STEP_CASES = dict(twod=(768, 16), planarpoint=(320, 10), invpendulum=(320, 10), balancingrider=(128, 8),
+                      bicycle=(384, 12))
+
+
+@pytest.mark.parametrize("model", list(F32_STEP_CASES))
+def test_f32_per_step_error(model):
+    """north_star: the fp32 production build stays within 1e-4 relative PER STEP of the reference
+    arithmetic.  Three crowds step side by side -- the oracle, the f64 build and the f32 build -- and
+    before every step the f32 build is reset to the f64 build's state (every per-agent field), so each
+    f32 step starts from the state the oracle step starts from (the f64 build tracks the oracle to
+    1e-9, asserted here).  The f32 forces and states are compared with the ORACLE's, every agent, every
+    step.  The only agents exempt are those with a source within 1e-5 rad of their field-of-view
+    boundary at the start of the step (the mask is discontinuous there: the reference's own result
+    flips under a 1e-16 perturbation); their number is counted, bounded and reported."""
     from gpu_helpers import make_engine
+    from helpers import oracle_world
     from test_gpu_parity import report, _vec_rel, _rel
-    n = 2048
-    s0, q = co.synthetic_crowd(n, seed=33, spacing=3.0)
-    e64, g64 = make_engine("twod", s0, 5.0, q, dtype=torch.float64)
-    e32, g32 = make_engine("twod", s0, 5.0, q, dtype=torch.float32, q_scale=e64.q_scale)
-    worst_f = worst_s = 0.0
-    fields = ("x", "y", "psi", "v", "delta", "step_i", "dest_ptr", "znav", "znav_v0", "znav_d0", "znav_d1",
-              "prev_x", "prev_y", "hist_x", "hist_y", "hist_step")
-    for step in range(30):
+    from cyclistsocialforce_b200.engine import _FIELD_AXIS, _STATE_COLS
+    n, steps = F32_STEP_CASES[model]
+    s0, q = co.synthetic_crowd(n, seed=33, spacing=3.0, n_states=8)
+    W = oracle_world(model, s0, np.full(n, 5.0), q)
+    A = W.groups[0]
+    e64, g64 = make_engine(model, s0, 5.0, q, dtype=torch.float64)
+    e32, g32 = make_engine(model, s0, 5.0, q, dtype=torch.float32, q_scale=e64.q_scale)
+    fields = [f for f in _STATE_COLS + tuple(_FIELD_AXIS) if f not in ("destq", "dest_len", "vd_default")
+              and getattr(g64, f) is not None]
+    fp = co.field_params_array([A.p])[0]
+    ns = A.s.shape[1]
+    lin = [0, 1] + list(range(3, ns))                       # x, y, v (+ rates): relative to max(|.|, 1)
+    ang = [2] + [c for c in (4, 5) if c < ns]               # psi, delta, theta: absolute, rad
+    lin = [c for c in lin if c not in ang]
+    worst = dict(f32_force=0.0, f32_state=0.0, f64_force=0.0, f64_state=0.0)
+    exempt = 0
+    for step in range(steps):
         for name in fields:
             getattr(g32, name).copy_(getattr(g64, name).to(getattr(g32, name).dtype))
         e32.pack()
+        _, margin = co.pair_forces(A.s[:, 0], A.s[:, 1], A.s[:, 2], fp, return_margin=True)
+        W.step()
         e64.step()
         e32.step()
-        f64 = e64.force.cpu().numpy()
-        f32 = e32.force.cpu().numpy().astype(float)
-        s64, s32 = g64.states_numpy(), g32.states_numpy()
-        # total force = clipped repulsive + destination term (|.| ~ v_d = 5) which may cancel:
-        # the error is taken relative to max(|F|, 1).  States: positions / speed relative to
-        # max(|.|, 1); yaw and steer angle absolute in radians (a nearly cancelled force has an
-        # ill-conditioned direction, which feeds the steer command: 1e-4 rad is the yardstick).
-        ef = _vec_rel(f32, f64, 1.0)
-        es = np.maximum(_rel(s32[:, [0, 1, 3]], s64[:, [0, 1, 3]], 1.0).max(axis=1),
-                        np.abs(s32[:, 4] - s64[:, 4]))
-        es = np.maximum(es, np.abs(np.angle(np.exp(1j * (s32[:, 2] - s64[:, 2])))))
-        # agents whose FOV mask flips between the builds (pair exactly on the boundary) are
-        # tolerated: at most 2 of 2048 per step
-        worst_f = max(worst_f, np.sort(ef)[-3])
-        worst_s = max(worst_s, np.sort(es)[-3])
-        assert (ef > 1e-4).sum() <= 2 and (es > 1e-4).sum() <= 2, (step, np.sort(ef)[-6:], np.sort(es)[-6:])
-    report(test="f32_per_step_vs_f64", n=n, steps=30, force_rel_3rd_worst=float(worst_f), state_rel_3rd_worst=float(worst_s))
+        fo, so = A.force, A.s
+        f64, s64 = e64.force.cpu().numpy(), g64.states_numpy()
+        f32, s32 = e32.force.cpu().numpy().astype(float), g32.states_numpy()
+
+        def errs(f, s):
+            ef = _vec_rel(f, fo, 1.0)
+            es = _rel(s[:, lin], so[:, lin], 1.0).max(axis=1)
+            for c in ang:
+                es = np.maximum(es, np.abs(np.angle(np.exp(1j * (s[:, c] - so[:, c])))))
+            return ef, es
+
+        ef64, es64 = errs(f64, s64)
+        worst["f64_force"] = max(worst["f64_force"], ef64.max())
+        worst["f64_state"] = max(worst["f64_state"], es64.max())
+        assert ef64.max() < 1e-8 and es64.max() < 1e-8, (model, step, ef64.max(), es64.max())
+        ef, es = errs(f32, s32)
+        ok = margin > 1e-5
+        exempt += int((~ok).sum())
+        worst["f32_force"] = max(worst["f32_force"], ef[ok].max())
+        worst["f32_state"] = max(worst["f32_state"], es[ok].max())
+        bad = ok & ((ef > 1e-4) | (es > 1e-4))
+        assert not bad.any(), (model, step, np.flatnonzero(bad)[:8], ef[bad][:8], es[bad][:8], margin[bad][:8])
+    e32.check_status()
+    e64.check_status()
+    report(test="f32_per_step_vs_oracle", model=model, n=n, steps=steps, agent_steps=n * steps,
+           exempt_fov_boundary=exempt, **{k: float(v) for k, v in worst.items()})
+    # a source within 1e-5 rad of the boundary of a 2.09 rad cone: ~n * 2 * 1e-5 / (2 pi) per target and step
+    assert exempt <= max(3, int(20 * n * steps * n * 2e-5 / (2 * np.pi)))
 
 
 def test_graph_step_equals_kernel_by_kernel_step():
