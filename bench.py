@@ -171,7 +171,8 @@ def run(args, out):
     bounds = (balanced_bounds(neighbour_work(s0[:, 0], s0[:, 1], 160.0), nparts) if (balance and nparts > 1)
               else shard_bounds(N_AGENTS, nparts))
     lo, hi = bounds[0] if emu else bounds[rank]
-    extent = 2.0 * float(max(np.abs(s0[:, :2]).max(), np.abs(q[..., :2]).max())) + 1000.0
+    # Q-format frame of the f32 payload, the same on every rank: centred on the crowd and its destinations
+    origin, extent = P.payload_frame([s0[:, :2], q[..., :2]])
     group = AgentGroup("twod", s0[lo:hi], P.InvPendulumBicycleParameters(), destqueues=list(queues[lo:hi]),
                        dtype=torch.float32, device=dev)
     exchange_kind = os.environ.get("CSF_BENCH_EXCHANGE", "peer") if (world > 1 and not emu) else "none"
@@ -188,12 +189,12 @@ def run(args, out):
     if emu:
         full = AgentGroup("twod", s0, P.InvPendulumBicycleParameters(), destqueues=list(queues),
                           dtype=torch.float32, device=dev)
-        e_full = Engine([full], dtype=torch.float32, device=dev, extent=extent, pair_mode="dense")
+        e_full = Engine([full], dtype=torch.float32, device=dev, extent=extent, origin=origin, pair_mode="dense")
         frozen_payload = e_full.payload.clone()
         del e_full, full
     pair_mode = os.environ.get("CSF_PAIR_MODE", "tiled")
     use_graph = os.environ.get("CSF_BENCH_GRAPH", "1") != "0"
-    eng = Engine([group], dtype=torch.float32, device=dev, extent=extent, n_global=N_AGENTS, global_offset=lo,
+    eng = Engine([group], dtype=torch.float32, device=dev, extent=extent, origin=origin, n_global=N_AGENTS, global_offset=lo,
                  exchange=exch, pair_mode=pair_mode, count_pairs=True, graph=False)
     exch(eng.payload)
     if emu:
@@ -237,8 +238,14 @@ def run(args, out):
         eng.pair_stats.zero_()
         eng._pair_and_road()
         sync()
-        executed_pairs = float(eng.pair_stats.item())
+        executed_pairs = float(eng.pair_stats[0].item())
         eng._pair_calls -= 1
+        if os.environ.get("CSF_BENCH_ROLES"):      # cycle accounting of a -DCSF_TILED_PROF build (tools/k1_roles.py)
+            st_ = eng.pair_stats.cpu().numpy().astype(float)
+            if st_[1] > 0:
+                print("roles: evaluate waiting %.1f%%; filter waiting for a stage %.1f%%, for a free slot %.1f%%; producer "
+                      "waiting %.1f%%; buffers %d stages %d units %d" % (100 * st_[2] / st_[1], 100 * st_[4] / st_[3],
+                      100 * st_[5] / st_[3], 100 * st_[7] / st_[6], st_[8], st_[9], st_[10]), file=sys.stderr, flush=True)
     eng.pair_stats_ptr_backup = eng.pair_stats
     eng.pair_stats = None                      # no counting inside the timed region
 
@@ -271,24 +278,29 @@ def run(args, out):
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-    # per-kernel durations: events cannot be placed inside a graph replay, so the split of a step
-    # into K1 / K2+K3 is taken in a second pass of the same K steps launched kernel by kernel
+    # per-kernel durations: events cannot be placed inside a graph replay, so the split of a step into
+    # [tile build + block bounds (+ wait for the peers)] / K1 / [reduce + K2+K3 (+ exchange)] is taken in a second
+    # pass of the same K steps launched kernel by kernel, with CUDA events between the launches
     eng.use_graph = False
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-            torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    fused = eng._fused
+    ev2 = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     for k in range(args.steps):
         flush.fill_(k & 0xFF)
-        a, b, c = ev2[k]
-        a.record()
-        have_rep = eng._pair_and_road()
-        b.record()
-        eng._agent_step(have_rep)
-        c.record()
+        e = ev2[k]
+        if fused:
+            eng._step_fused(mark=lambda i, e=e: e[i].record())
+        else:
+            e[0].record(); e[1].record()
+            have_rep = eng._pair_and_road()
+            e[2].record()
+            eng._agent_step(have_rep)
+            e[3].record()
     sync()
     barrier()
-    pair_ms = [a.elapsed_time(b) for a, b, c in ev2]
-    agent_ms = [b.elapsed_time(c) for a, b, c in ev2]
-    ungraphed_ms = statistics.mean(a.elapsed_time(c) for a, b, c in ev2)
+    prep_ms = [e[0].elapsed_time(e[1]) for e in ev2]
+    pair_ms = [e[1].elapsed_time(e[2]) for e in ev2]
+    agent_ms = [e[2].elapsed_time(e[3]) for e in ev2]
+    ungraphed_ms = statistics.mean(e[0].elapsed_time(e[3]) for e in ev2)
     eng.check_status()
     value = N_AGENTS * args.steps / (total_ms * 1e-3)
     ms_per_step = total_ms / args.steps
@@ -352,7 +364,7 @@ def run(args, out):
                     "d2h_bytes_per_step": d2h * world},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32",
-                         "kernel": "pair_tiled_kernel<float> (+tile build, partial reduce)" if eng.tiled
+                         "kernel": ("pair_tiled_kernel<float>" if fused else "pair_tiled_kernel<float> (+tile build, partial reduce)") if eng.tiled
                          else "pair_kernel<float,2,512> (+partial reduce)",
                          "achieved": achieved, "dense_convention_tflops": dense_equiv,
                          "dense_convention_frac": dense_equiv / fp32_peak_tflops,
@@ -362,8 +374,9 @@ def run(args, out):
                          "traffic": traffic, "peak_source": "csf_ffma_peak micro-benchmark in this run",
                          "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs_per_launch,
                          "kernel_ms": pair_s * 1e3, "share_of_step": pair_s * 1e3 / ungraphed_ms,
+                         "prepare_kernel_ms": statistics.mean(prep_ms),
                          "timing": "second pass of the same K steps, launched kernel by kernel (ms_per_step of that pass: %.4f)" % ungraphed_ms},
-            "roofline_agent_kernel": {"bound": "hbm", "kernel": "agent_kernel<float,TWOD,STEP>",
+            "roofline_agent_kernel": {"bound": "hbm", "kernel": "agent_kernel<float,TWOD,STEP>" + (" (+ reduction of the pair kernel's partial sums" + (", payload exchange" if world > 1 else "") + ")" if fused else ""),
                                       "achieved": n_local * BYTES_PER_AGENT_STEP / agent_s / 1e9, "peak": hbm_peak,
                                       "unit": "GB/s", "frac": n_local * BYTES_PER_AGENT_STEP / agent_s / 1e9 / hbm_peak,
                                       "kernel_ms": agent_s * 1e3,

@@ -26,6 +26,7 @@ class CsfFieldParams(C.Structure):
 
 
 CSF_MAX_PEERS = 16
+CSF_TILED_PREPARED, CSF_TILED_NO_REDUCE = 1, 2
 
 
 class CsfPeerComm(C.Structure):
@@ -34,7 +35,14 @@ class CsfPeerComm(C.Structure):
         ("payload", C.c_void_p * CSF_MAX_PEERS),
         ("data_flags", C.c_void_p * CSF_MAX_PEERS),
         ("read_flags", C.c_void_p * CSF_MAX_PEERS),
-        ("seq", C.c_void_p),
+        ("seq", C.c_void_p), ("status_host", C.c_void_p),
+    ]
+
+
+class CsfStepFusion(C.Structure):
+    _fields_ = [
+        ("partial", C.c_void_p), ("partial_stride", C.c_int64), ("partial_offset", C.c_int64),
+        ("n_groups", C.c_int32), ("f0", C.c_double), ("comm", CsfPeerComm),
     ]
 
 
@@ -53,7 +61,7 @@ class CsfAgentParams(C.Structure):
         ("br_A0", C.c_double * 25), ("br_A1", C.c_double * 25), ("br_A2", C.c_double * 25),
         ("br_B", C.c_double * 5),
         ("br_pole_icpt", C.c_double * 5), ("br_pole_coef", C.c_double * 5),
-        ("q_scale", C.c_double),
+        ("q_scale", C.c_double), ("q_origin", C.c_double * 2),
         ("traj_len", C.c_int32), ("hist_len", C.c_int32), ("hist_cap", C.c_int32), ("q_cap", C.c_int32),
     ]
 
@@ -102,10 +110,19 @@ SIGNATURES = {
     "csf_morton_keys_f64": (C.c_int, [_vp, _i64, _dbl, _dbl, _dbl, _vp, _vp]),
     "csf_spatial_keys_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "csf_spatial_keys_f64": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
+    "csf_spatial_order_workspace_bytes": (_sz, [_i64]),
+    "csf_spatial_bbox_f32": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "csf_spatial_bbox_f64": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "csf_spatial_order_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "csf_spatial_order_f64": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "csf_tile_sources_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "csf_tile_sources_f64": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
-    "csf_pair_forces_tiled_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp, _vp, _vp]),
-    "csf_pair_forces_tiled_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "csf_pair_forces_tiled_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp, _vp, C.c_int, _vp]),
+    "csf_pair_forces_tiled_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp, _vp, C.c_int, _vp]),
+    "csf_tiled_prepare_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp, _vp]),
+    "csf_tiled_prepare_f64": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp, _vp]),
+    "csf_tiled_num_groups": (C.c_int, [_i64, _i64, C.c_int]),
+    "csf_tiled_partial_offset": (_sz, [_i64, _i64, C.c_int]),
     "csf_tiled_num_items": (_i64, [_i64, _i64, C.c_int]),
     "csf_tiled_item_order": (C.c_int, [_vp, _i64, _vp, _vp]),
     "csf_field_cutoff_distance": (_dbl, [_FP]),
@@ -118,10 +135,12 @@ SIGNATURES = {
     "csf_agent_advance_f64": (C.c_int, [C.c_int, _AS, _AP, _vp, _vp, _vp]),
     "csf_agent_step_f32": (C.c_int, [C.c_int, _AS, _AP, _i64, _vp, _vp, _vp, _vp, _vp]),
     "csf_agent_step_f64": (C.c_int, [C.c_int, _AS, _AP, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "csf_agent_step_fused_f32": (C.c_int, [C.c_int, _AS, _AP, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "csf_agent_step_fused_f64": (C.c_int, [C.c_int, _AS, _AP, _i64, _vp, _vp, _vp, _vp, _vp]),
     "csf_pack_xycs_f32": (C.c_int, [_AS, _AP, _vp, _vp]),
     "csf_pack_xycs_f64": (C.c_int, [_AS, _AP, _vp, _vp]),
-    "csf_pack_xypsi_f32": (C.c_int, [_vp, _vp, _vp, _i64, _dbl, _vp, _vp]),
-    "csf_pack_xypsi_f64": (C.c_int, [_vp, _vp, _vp, _i64, _dbl, _vp, _vp]),
+    "csf_pack_xypsi_f32": (C.c_int, [_vp, _vp, _vp, _i64, _dbl, _dbl, _dbl, _vp, _vp]),
+    "csf_pack_xypsi_f64": (C.c_int, [_vp, _vp, _vp, _i64, _dbl, _dbl, _dbl, _vp, _vp]),
     "csf_ffma_peak": (C.c_int, [_i64, _vp, C.POINTER(C.c_double), _vp]),
     "csf_peer_handle_bytes": (C.c_int, []),
     "csf_peer_alloc": (C.c_int, [_sz, C.POINTER(C.c_void_p), _vp]),

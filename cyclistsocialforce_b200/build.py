@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcsf_b200.so")
-SOURCES = ["csf_pair.cu", "csf_pair_tiled.cu", "csf_agent.cu", "csf_peer.cu"]
+SOURCES = ["csf_pair.cu", "csf_pair_tiled.cu", "csf_agent.cu", "csf_peer.cu", "csf_order.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -46,8 +46,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(HERE, "csrc", src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c",
-               os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("CSF_BUILD_DEFINES", "").split(), "-I", os.path.join(ROOT, "include"),
+               "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -13,6 +13,8 @@
 //   BalancingRiderDynamics.step      dynamics.py:602-705,  from_pole_placement :1167-1227
 //   PlanarPointDynamics.step         dynamics.py:996-1079
 #include "csf_common.cuh"
+#include "csf_peer.cuh"
+#include <string.h>
 
 namespace {
 
@@ -643,13 +645,13 @@ __device__ void br_gains(const CsfAgentParams& p, double v, double* K) {
 template <typename T> __device__ __forceinline__ T ldT(const void* p, int64_t k) { return reinterpret_cast<const T*>(p)[k]; }
 template <typename T> __device__ __forceinline__ void stT(void* p, int64_t k, T v) { reinterpret_cast<T*>(p)[k] = v; }
 
+// Everything one agent does in a step; returns true if a new payload element was produced (*out).
 template <typename T, int MODEL, int MODE>
-__global__ void __launch_bounds__(128) agent_kernel(CsfAgentState st, CsfAgentParams p, int64_t n_total,
-                                                    const T* __restrict__ frep, const T* __restrict__ froad,
-                                                    T* __restrict__ force, T* __restrict__ fdest_out,
-                                                    void* __restrict__ next_xycs) {
-    const int64_t k = st.first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= st.first + st.count) return;
+__device__ __forceinline__ bool agent_body(const CsfAgentState& st, const CsfAgentParams& p, int64_t n_total,
+                                           const T* __restrict__ frep, const T* __restrict__ froad,
+                                           T* __restrict__ force, T* __restrict__ fdest_out,
+                                           void* __restrict__ next_xycs, const CsfStepFusion& fu, int64_t k,
+                                           Xycs<T>* out) {
     Agent<T> a;
     a.x = st.x[k];
     a.y = st.y[k];
@@ -667,6 +669,7 @@ __global__ void __launch_bounds__(128) agent_kernel(CsfAgentState st, CsfAgentPa
     a.z_d1 = ldT<T>(st.znav_d1, k);
     a.q = st.destq + (size_t)k * p.q_cap * 3;
     a.flags = 0;
+    bool produced = false;
     // everything else the step reads from global memory, issued before the first use (independent loads:
     // one round trip instead of a chain of them)
     constexpr bool kHist = MODEL == CSF_MODEL_TWOD || MODEL == CSF_MODEL_INVPENDULUM || MODEL == CSF_MODEL_PLANARPOINT;
@@ -678,8 +681,19 @@ __global__ void __launch_bounds__(128) agent_kernel(CsfAgentState st, CsfAgentPa
         hist_step = st.hist_step[k];
     }
     T frx0 = (T)0, fry0 = (T)0, fox = (T)0, foy = (T)0;
-    const bool have_rep = MODE != MODE_ADVANCE && n_total > 1 && frep != nullptr;
-    if (have_rep) {
+    const bool fused_rep = MODE == MODE_STEP && fu.partial != nullptr;
+    const bool have_rep = MODE != MODE_ADVANCE && n_total > 1 && (frep != nullptr || fused_rep);
+    if (have_rep && fused_rep) {
+        // partial sums of the tiled pair kernel, one slab per chunk group, reduced here in fixed order
+        // (what reduce_groups_kernel does as a launch of its own)
+        const T* part = reinterpret_cast<const T*>(fu.partial) + (size_t)(fu.partial_offset + k) * 2;
+        for (int g = 0; g < fu.n_groups; ++g) {
+            frx0 += part[(size_t)g * fu.partial_stride * 2];
+            fry0 += part[(size_t)g * fu.partial_stride * 2 + 1];
+        }
+        frx0 *= (T)fu.f0;
+        fry0 *= (T)fu.f0;
+    } else if (have_rep) {
         frx0 = frep[k * 2];
         fry0 = frep[k * 2 + 1];
     }
@@ -857,8 +871,10 @@ __global__ void __launch_bounds__(128) agent_kernel(CsfAgentState st, CsfAgentPa
         if (!(isfinite(a.x) && isfinite(a.y) && isfinite((double)a.psi) && isfinite((double)a.v))) a.flags |= 1;
         if (next_xycs != nullptr) {
             int ovf = 0;
-            store_xycs<T>(next_xycs, st.payload_offset + k, a.x, a.y, a.psi, 1.0 / p.q_scale, &ovf);
+            *out = store_xycs<T>(next_xycs, st.payload_offset + k, a.x, a.y, a.psi, 1.0 / p.q_scale, p.q_origin[0],
+                                 p.q_origin[1], &ovf);
             if (ovf) a.flags |= 4;
+            produced = true;
         }
     }
     if (a.flags && st.status != nullptr) {
@@ -866,32 +882,94 @@ __global__ void __launch_bounds__(128) agent_kernel(CsfAgentState st, CsfAgentPa
         // host-mapped mirror: the host polls it without a copy or a synchronisation
         if (st.status_host != nullptr) *reinterpret_cast<volatile int32_t*>(st.status_host) = 1;
     }
+    return produced;
+}
+
+// One thread per agent.  With `fu.comm` (a crowd sharded over the GPUs of a node, csf_peer.cu) the kernel
+// is also the step's side of the payload exchange: block 0 tells every peer that this rank has finished
+// reading their payload entries (the pair kernel ran before this one); after the agents have been
+// stepped every block waits for the peers' same signal, stores its agents' new payload elements
+// straight into every peer's buffer (16-byte NVLink stores), and the last block to finish raises the
+// data flags.  No separate wait / signal / push launches, no collective call.
+template <typename T, int MODEL, int MODE>
+__global__ void __launch_bounds__(128) agent_kernel(CsfAgentState st, CsfAgentParams p, int64_t n_total,
+                                                    const T* __restrict__ frep, const T* __restrict__ froad,
+                                                    T* __restrict__ force, T* __restrict__ fdest_out,
+                                                    void* __restrict__ next_xycs, CsfStepFusion fu) {
+    const int64_t k = st.first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = k < st.first + st.count;
+    const bool peers = MODE == MODE_STEP && fu.comm.world > 1;
+    __shared__ uint32_t s_epoch, s_last;
+    if (peers) {
+        if (threadIdx.x == 0) s_epoch = ld_sys(fu.comm.seq + SEQ_PUSH) + 1u;
+        __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x < fu.comm.world && (int)threadIdx.x != fu.comm.rank)
+            st_sys(fu.comm.read_flags[threadIdx.x] + fu.comm.rank, s_epoch);
+    }
+    Xycs<T> mine;
+    bool produced = false;
+    if (active) produced = agent_body<T, MODEL, MODE>(st, p, n_total, frep, froad, force, fdest_out, next_xycs, fu, k, &mine);
+    if (peers) {
+        const CsfPeerComm& c = fu.comm;
+        if (threadIdx.x < c.world && (int)threadIdx.x != c.rank && peer_ok(c)) {
+            if (!spin_ge(c.read_flags[c.rank] + threadIdx.x, s_epoch)) peer_fail(c, 2u);
+        }
+        __syncthreads();
+        if (peer_ok(c)) {
+            if (produced) {
+                const int64_t idx = st.payload_offset + k;
+                for (int q = 0; q < c.world; ++q)
+                    if (q != c.rank) reinterpret_cast<Xycs<T>*>(c.payload[q])[idx] = mine;
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const uint32_t t = atomicAdd(c.seq + SEQ_BLOCKS, 1u);
+                s_last = (t == gridDim.x - 1) ? 1u : 0u;
+                if (s_last) {
+                    c.seq[SEQ_BLOCKS] = 0;
+                    c.seq[SEQ_PUSH] = s_epoch;
+                    __threadfence_system();
+                }
+            }
+            __syncthreads();
+            if (s_last && threadIdx.x < c.world && (int)threadIdx.x != c.rank)
+                st_sys(c.data_flags[threadIdx.x] + c.rank, s_epoch);
+        }
+    }
 }
 
 template <typename T>
-__global__ void pack_state_kernel(CsfAgentState st, double inv_q, void* xycs) {
+__global__ void pack_state_kernel(CsfAgentState st, double inv_q, double ox, double oy, void* xycs) {
     const int64_t k = st.first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= st.first + st.count) return;
     int ovf = 0;
-    store_xycs<T>(xycs, st.payload_offset + k, st.x[k], st.y[k], ldT<T>(st.psi, k), inv_q, &ovf);
-    if (ovf && st.status != nullptr) atomicOr(st.status, 4);
+    store_xycs<T>(xycs, st.payload_offset + k, st.x[k], st.y[k], ldT<T>(st.psi, k), inv_q, ox, oy, &ovf);
+    if (ovf && st.status != nullptr) {
+        atomicOr(st.status, 4);
+        if (st.status_host != nullptr) *reinterpret_cast<volatile int32_t*>(st.status_host) = 1;
+    }
 }
 template <typename T>
 __global__ void pack_xypsi_kernel(const double* x, const double* y, const double* psi, int64_t n, double inv_q,
-                                  void* xycs) {
+                                  double ox, double oy, void* xycs) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     int ovf = 0;
-    store_xycs<T>(xycs, k, x[k], y[k], (T)psi[k], inv_q, &ovf);
+    store_xycs<T>(xycs, k, x[k], y[k], (T)psi[k], inv_q, ox, oy, &ovf);
 }
 
 template <typename T, int MODE>
 int launch_agent(int model, const CsfAgentState* st, const CsfAgentParams* p, int64_t n_total, const T* frep,
-                 const T* froad, T* force, T* fdest, void* next_xycs, cudaStream_t stream) {
-    if (st->count <= 0) return 0;
-    const unsigned grid = (unsigned)((st->count + 127) / 128);
+                 const T* froad, T* force, T* fdest, void* next_xycs, cudaStream_t stream,
+                 const CsfStepFusion* fusion = nullptr) {
+    CsfStepFusion fu;
+    memset(&fu, 0, sizeof(fu));
+    if (fusion) fu = *fusion;
+    if (st->count <= 0 && fu.comm.world <= 1) return 0;
+    const unsigned grid = (unsigned)((st->count + 127) / 128) > 0 ? (unsigned)((st->count + 127) / 128) : 1u;
 #define CSF_LAUNCH(MODEL)                                                                                      \
-    agent_kernel<T, MODEL, MODE><<<grid, 128, 0, stream>>>(*st, *p, n_total, frep, froad, force, fdest, next_xycs)
+    agent_kernel<T, MODEL, MODE><<<grid, 128, 0, stream>>>(*st, *p, n_total, frep, froad, force, fdest, next_xycs, fu)
     switch (model) {
         case CSF_MODEL_TWOD: CSF_LAUNCH(CSF_MODEL_TWOD); break;
         case CSF_MODEL_INVPENDULUM: CSF_LAUNCH(CSF_MODEL_INVPENDULUM); break;
@@ -937,30 +1015,42 @@ int csf_agent_step_f64(int model, const CsfAgentState* st, const CsfAgentParams*
                        const double* frep, const double* froad, double* force, void* next_xycs, csf_stream_t s) {
     return launch_agent<double, MODE_STEP>(model, st, p, n_total, frep, froad, force, nullptr, next_xycs, (cudaStream_t)s);
 }
+int csf_agent_step_fused_f32(int model, const CsfAgentState* st, const CsfAgentParams* p, int64_t n_total,
+                             const CsfStepFusion* fusion, const float* froad, float* force, void* next_xycs,
+                             csf_stream_t s) {
+    return launch_agent<float, MODE_STEP>(model, st, p, n_total, nullptr, froad, force, nullptr, next_xycs,
+                                          (cudaStream_t)s, fusion);
+}
+int csf_agent_step_fused_f64(int model, const CsfAgentState* st, const CsfAgentParams* p, int64_t n_total,
+                             const CsfStepFusion* fusion, const double* froad, double* force, void* next_xycs,
+                             csf_stream_t s) {
+    return launch_agent<double, MODE_STEP>(model, st, p, n_total, nullptr, froad, force, nullptr, next_xycs,
+                                           (cudaStream_t)s, fusion);
+}
 int csf_pack_xycs_f32(const CsfAgentState* st, const CsfAgentParams* p, void* xycs, csf_stream_t s) {
     if (st->count <= 0) return 0;
-    pack_state_kernel<float><<<(unsigned)((st->count + 127) / 128), 128, 0, (cudaStream_t)s>>>(*st, 1.0 / p->q_scale, xycs);
+    pack_state_kernel<float><<<(unsigned)((st->count + 127) / 128), 128, 0, (cudaStream_t)s>>>(*st, 1.0 / p->q_scale, p->q_origin[0], p->q_origin[1], xycs);
     CSF_CHECK_LAUNCH("pack_state_kernel");
     return 0;
 }
 int csf_pack_xycs_f64(const CsfAgentState* st, const CsfAgentParams* p, void* xycs, csf_stream_t s) {
     if (st->count <= 0) return 0;
-    pack_state_kernel<double><<<(unsigned)((st->count + 127) / 128), 128, 0, (cudaStream_t)s>>>(*st, 1.0, xycs);
+    pack_state_kernel<double><<<(unsigned)((st->count + 127) / 128), 128, 0, (cudaStream_t)s>>>(*st, 1.0, 0.0, 0.0, xycs);
     CSF_CHECK_LAUNCH("pack_state_kernel");
     return 0;
 }
-int csf_pack_xypsi_f32(const double* x, const double* y, const double* psi, int64_t n, double q_scale, void* xycs,
-                       csf_stream_t s) {
+int csf_pack_xypsi_f32(const double* x, const double* y, const double* psi, int64_t n, double q_scale,
+                       double origin_x, double origin_y, void* xycs, csf_stream_t s) {
     if (n <= 0) return 0;
-    pack_xypsi_kernel<float><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)s>>>(x, y, psi, n, 1.0 / q_scale, xycs);
+    pack_xypsi_kernel<float><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)s>>>(x, y, psi, n, 1.0 / q_scale, origin_x, origin_y, xycs);
     CSF_CHECK_LAUNCH("pack_xypsi_kernel");
     return 0;
 }
-int csf_pack_xypsi_f64(const double* x, const double* y, const double* psi, int64_t n, double q_scale, void* xycs,
-                       csf_stream_t s) {
-    (void)q_scale;
+int csf_pack_xypsi_f64(const double* x, const double* y, const double* psi, int64_t n, double q_scale,
+                       double origin_x, double origin_y, void* xycs, csf_stream_t s) {
+    (void)q_scale; (void)origin_x; (void)origin_y;
     if (n <= 0) return 0;
-    pack_xypsi_kernel<double><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)s>>>(x, y, psi, n, 1.0, xycs);
+    pack_xypsi_kernel<double><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)s>>>(x, y, psi, n, 1.0, 0.0, 0.0, xycs);
     CSF_CHECK_LAUNCH("pack_xypsi_kernel");
     return 0;
 }

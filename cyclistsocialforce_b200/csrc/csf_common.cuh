@@ -71,20 +71,24 @@ __device__ __forceinline__ int32_t quantise(double x, double inv_q, int* overflo
     if (fabs(r) > 1073741824.0) { *overflow = 1; r = fmax(fmin(r, 1073741824.0), -1073741824.0); }
     return (int32_t)r;
 }
-template <typename T> __device__ __forceinline__ void store_xycs(void* out, int64_t idx, double x, double y, T psi,
-                                                                 double inv_q, int* overflow);
-template <> __device__ __forceinline__ void store_xycs<float>(void* out, int64_t idx, double x, double y, float psi,
-                                                              double inv_q, int* overflow) {
+// (ox, oy) = origin of the Q-format frame: centring the frame on the crowd spends the 31 bits on the
+// occupied region only (the pair kernel sees differences, the origin drops out)
+template <typename T> __device__ __forceinline__ Xycs<T> store_xycs(void* out, int64_t idx, double x, double y, T psi,
+                                                                    double inv_q, double ox, double oy, int* overflow);
+template <> __device__ __forceinline__ Xycs<float> store_xycs<float>(void* out, int64_t idx, double x, double y, float psi,
+                                                                     double inv_q, double ox, double oy, int* overflow) {
     Xycs<float> e;
-    e.xq = quantise(x, inv_q, overflow);
-    e.yq = quantise(y, inv_q, overflow);
+    e.xq = quantise(x - ox, inv_q, overflow);
+    e.yq = quantise(y - oy, inv_q, overflow);
     sincosf(psi, &e.s, &e.c);
     reinterpret_cast<Xycs<float>*>(out)[idx] = e;
+    return e;
 }
-template <> __device__ __forceinline__ void store_xycs<double>(void* out, int64_t idx, double x, double y, double psi,
-                                                               double, int*) {
+template <> __device__ __forceinline__ Xycs<double> store_xycs<double>(void* out, int64_t idx, double x, double y, double psi,
+                                                                       double, double, double, int*) {
     Xycs<double> e;
     e.x = x; e.y = y;
     sincos(psi, &e.s, &e.c);
     reinterpret_cast<Xycs<double>*>(out)[idx] = e;
+    return e;
 }

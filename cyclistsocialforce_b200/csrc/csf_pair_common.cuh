@@ -206,16 +206,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // producer-side wait: the producer is usually far ahead of the consumers; sleep between polls so
 // that its spinning does not take issue slots from the consumer warps of its scheduler
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+#ifndef CSF_WAIT_HINT_NS
+#define CSF_WAIT_HINT_NS 20000u
+#endif
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t hint_ns = CSF_WAIT_HINT_NS) {
     // try_wait with an explicit suspend-time hint: the thread is parked by the hardware for up to
-    // ~20 us per attempt instead of re-issuing the poll
+    // hint_ns per attempt instead of re-issuing the poll
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAITB_%=:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONEB_%=;\n\t"
         "bra WAITB_%=;\n\t"
-        "DONEB_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+        "DONEB_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
 }
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

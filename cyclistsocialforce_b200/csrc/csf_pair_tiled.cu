@@ -33,6 +33,8 @@
 #include "csf_common.cuh"
 #include "csf_pair_common.cuh"
 #include <stdlib.h>
+#include <string.h>
+#include "csf_peer.cuh"
 
 namespace {
 
@@ -238,6 +240,65 @@ __global__ void block_bounds_kernel(const Xycs<T>* __restrict__ tgt, const int64
     if (lane == 0) blocks[b] = bb.circle(i_end - b * (int64_t)group);
 }
 
+// Tile build and target-block bounds in ONE launch (the step's first kernel): CTAs [0, n_chunks) do what
+// tile_sources_kernel does, the rest what block_bounds_kernel does, 16 blocks per CTA.  On a sharded crowd
+// every CTA first waits until the peers' payload pushes of the previous step have landed (csf_peer.cu).
+template <typename T>
+__global__ void __launch_bounds__(kCT * 32)
+tiled_prepare_kernel(const Xycs<T>* __restrict__ xycs, int64_t n, const int64_t* __restrict__ perm,
+                     unsigned char* __restrict__ sorted, Tile<T>* __restrict__ tiles, int64_t n_tiles, int64_t n_chunks,
+                     const Xycs<T>* __restrict__ tgt, const int64_t* __restrict__ tgt_perm, int64_t n_tgt,
+                     Tile<T>* __restrict__ blocks, int64_t n_blocks, unsigned int* __restrict__ item_counter,
+                     CsfPeerComm comm) {
+    if (comm.world > 1) {
+        csf_peer_wait_all(comm);
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *item_counter = 0;   // the pair kernel's dynamic item counter
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if ((int64_t)blockIdx.x >= n_chunks) {
+        const int64_t b = ((int64_t)blockIdx.x - n_chunks) * kCT + w;
+        if (b >= n_blocks) return;
+        BBox<T> bb;
+        const int64_t i_end = min(n_tgt, (b + 1) * (int64_t)kBT);
+        for (int64_t i = b * (int64_t)kBT + lane; i < i_end; i += 32) bb.add(tgt[tgt_perm ? tgt_perm[i] : i]);
+        bb.warp_reduce();
+        if (lane == 0) blocks[b] = bb.circle(i_end - b * (int64_t)kBT);
+        return;
+    }
+    __shared__ __align__(16) unsigned char boxes_raw[kCT * sizeof(BBox<T>)];
+    BBox<T>* boxes = reinterpret_cast<BBox<T>*>(boxes_raw);
+    const int64_t c = blockIdx.x, t = c * kCT + w;
+    BBox<T> bb;
+    if (t < n_tiles) {
+        const int64_t i0 = t * kTileS + lane, i1 = i0 + 32;
+        Xycs<T> a, b;
+        const bool va = i0 < n, vb = i1 < n;
+        if (va) a = xycs[perm ? perm[i0] : i0]; else pad_entry(a);
+        if (vb) b = xycs[perm ? perm[i1] : i1]; else pad_entry(b);
+        SrcA<T> A;
+        SrcB<T> B;
+        split(a, b, A, B);
+        unsigned char* base = sorted + (size_t)t * TileBytes<T>::v;
+        reinterpret_cast<SrcA<T>*>(base)[lane] = A;
+        reinterpret_cast<SrcB<T>*>(base + 32 * sizeof(SrcA<T>))[lane] = B;
+        if (va) bb.add(a);
+        if (vb) bb.add(b);
+        bb.warp_reduce();
+        const int64_t rem = n - t * kTileS;
+        if (lane == 0) tiles[t] = bb.circle(rem < kTileS ? rem : kTileS);
+    }
+    if (lane == 0) boxes[w] = bb;
+    __syncthreads();
+    if (w == 0) {
+        BBox<T> cb;
+        if (lane < kCT) cb = boxes[lane];
+        cb.warp_reduce();
+        const int64_t cnt = min(n, (c + 1) * (int64_t)kCS) - c * (int64_t)kCS;
+        if (lane == 0) tiles[n_tiles + c] = cb.circle(cnt);
+    }
+}
+
 // Spatial sort key of a payload position: index along a 2^16 x 2^16 Hilbert curve (the host sorts the
 // keys; any order gives correct results).  Consecutive runs of a Hilbert order are compact -- the mean
 // bounding radius of a 64-source tile is 27 m at 4 m spacing against 40 m for a Morton order, which
@@ -410,6 +471,27 @@ __device__ __forceinline__ void filter_barrier() {
 
 enum { BUF_LAST = 1, BUF_EXIT = 2 };
 
+// Optional cycle accounting per warp role (build with -DCSF_TILED_PROF; tools/k1_roles.py prints it):
+// stats[1..] += cycles {evaluate: total, waiting for a buffer; filter: total, waiting for a stage,
+// waiting for a free slot; producer: total, waiting for a stage slot}, buffers, stages, (target, buffer)
+// units evaluated.
+// suspend-time hints of the mbarrier waits (ns): hand-offs between the warp roles
+#ifndef CSF_TILED_HINT_NS
+#define CSF_TILED_HINT_NS 1000u
+#endif
+#ifndef CSF_TILED_PRODUCER_HINT_NS
+#define CSF_TILED_PRODUCER_HINT_NS 4000u
+#endif
+#ifdef CSF_TILED_PROF
+#define PROF_T0(v) const long long v = clock64()
+#define PROF_ADD(acc, v) acc += clock64() - v
+#define PROF_INC(acc) acc += 1
+#else
+#define PROF_T0(v)
+#define PROF_ADD(acc, v)
+#define PROF_INC(acc)
+#endif
+
 // ---- the tiled pair kernel ---------------------------------------------------------------------------
 // item -> (target block tb = item % n_tblocks, chunk group cg = item / n_tblocks); a group is
 // `group_chunks` consecutive chunks.  partial[cg][target][2].
@@ -469,6 +551,8 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
         // ===== producer warp: fetch items, cull chunks and tiles against the target block, stream the rest =====
         uint32_t it = 0;
         int fill = 0;                                   // tiles in the open stage
+        long long pr_wait = 0;
+        PROF_T0(pr_t0);
         auto close_stage = [&](int item, int n) {
             __syncwarp();                               // the circle records of every lane have been written
             if (lane == 0) {
@@ -480,8 +564,10 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
             fill = 0;
         };
         auto open_stage = [&]() {                       // wait until the filter warps have released the stage
-            if (lane == 0) mbar_wait_backoff(&empty[it % kStages], ((it / kStages) & 1) ^ 1);
+            PROF_T0(w0);
+            if (lane == 0) mbar_wait_backoff(&empty[it % kStages], ((it / kStages) & 1) ^ 1, CSF_TILED_PRODUCER_HINT_NS);
             __syncwarp();
+            PROF_ADD(pr_wait, w0);
         };
         for (;;) {
             unsigned int item = 0;
@@ -535,6 +621,13 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
         }
         open_stage();
         close_stage(0, -2);
+#ifdef CSF_TILED_PROF
+        if (stats && lane == 0) {
+            atomicAdd(stats + 6, (unsigned long long)(clock64() - pr_t0));
+            atomicAdd(stats + 7, (unsigned long long)pr_wait);
+        }
+#endif
+        (void)pr_wait;
         return;
     }
 
@@ -554,6 +647,8 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
         uint32_t n_open = 0;                 // items opened
         bool have_slot = false;
         Tile<T> blk;                         // bounding circle of the block's targets
+        long long fl_wait_full = 0, fl_wait_free = 0, fl_bufs = 0, fl_stages = 0;
+        PROF_T0(fl_t0);
         auto write_entry = [&](unsigned char* sb, int kidx, P x, P y, T c, T s) {
             unsigned char* tb = sb + (size_t)(kidx >> 6) * kTileB;
             const int r = kidx & 63, l = r & 31, h = r >> 5;
@@ -571,8 +666,10 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
         int pend_item0 = -1, pend_item1 = -1, pend_par0 = 0, pend_par1 = 0;     // per slot
         auto retire = [&](uint32_t b) {
             const int slot = (int)(b & 1u);
-            if (lane == 0) mbar_wait_backoff(&freeb[slot], (b >> 1) & 1);
+            PROF_T0(w0);
+            if (lane == 0) mbar_wait_backoff(&freeb[slot], (b >> 1) & 1, CSF_TILED_HINT_NS);
             __syncwarp();
+            PROF_ADD(fl_wait_free, w0);
             const int p_item = slot ? pend_item1 : pend_item0, p_par = slot ? pend_par1 : pend_par0;
             if (p_item >= 0) {
                 const int tb = p_item % n_tblocks, cg = p_item / n_tblocks;
@@ -626,11 +723,15 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
             ++bk;
             ++kbuf;
             have_slot = false;
+            PROF_INC(fl_bufs);
         };
         for (;;) {
             const int stage = it % kStages;
-            if (lane == 0) mbar_wait_backoff(&full[stage], (it / kStages) & 1);
+            PROF_T0(w0);
+            if (lane == 0) mbar_wait_backoff(&full[stage], (it / kStages) & 1, CSF_TILED_HINT_NS);
             __syncwarp();
+            PROF_ADD(fl_wait_full, w0);
+            PROF_INC(fl_stages);
             const int item = hdr[stage].x, n = hdr[stage].y;
             if (n == -2) {
                 acquire();
@@ -730,6 +831,18 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
             if (lane == 0) mbar_arrive(&empty[stage]);
             ++it;
         }
+#ifdef CSF_TILED_PROF
+        if (stats && lane == 0) {
+            atomicAdd(stats + 3, (unsigned long long)(clock64() - fl_t0));
+            atomicAdd(stats + 4, (unsigned long long)fl_wait_full);
+            atomicAdd(stats + 5, (unsigned long long)fl_wait_free);
+            if (fw == 0) {
+                atomicAdd(stats + 8, (unsigned long long)fl_bufs);
+                atomicAdd(stats + 9, (unsigned long long)fl_stages);
+            }
+        }
+#endif
+        (void)fl_wait_full; (void)fl_wait_free; (void)fl_bufs; (void)fl_stages;
         return;
     }
 
@@ -743,10 +856,14 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
     // may be in flight together use different accumulators (parity of the buffer's number within its
     // item, parity of the item): every sum is deterministic.
     unsigned long long n_eval = 0;
+    long long ev_wait = 0, ev_units = 0;
+    PROF_T0(ev_t0);
     for (uint32_t bk = 0;; ++bk) {
         const int slot = (int)(bk & 1u);
-        if (lane == 0) mbar_wait_backoff(&ready[slot], (bk >> 1) & 1);
+        PROF_T0(w0);
+        if (lane == 0) mbar_wait_backoff(&ready[slot], (bk >> 1) & 1, CSF_TILED_HINT_NS);
         __syncwarp();
+        PROF_ADD(ev_wait, w0);
         const int4 d = bdesc[slot];
         if (d.z & BUF_EXIT) break;
         const int n_dt = d.y, par = d.w & 1, kpar = (d.w >> 1) & 1;
@@ -777,6 +894,7 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                 for (int h = 0; h < 2; ++h) {
                     uint32_t mask = h ? (m2 >> 16) : (m2 & 0xffffu);
                     if (mask == 0) continue;
+                    PROF_INC(ev_units);
                     const int q = q0 + h;
                     if (stats) n_eval += (unsigned long long)__popc(mask) * kTileS;
                     const Xycs<T> te = mytgt[q];
@@ -822,6 +940,14 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
         if (lane == 0) mbar_arrive(&freeb[slot]);
     }
     if (stats && n_eval && lane == 0) atomicAdd(stats, n_eval);
+#ifdef CSF_TILED_PROF
+    if (stats && lane == 0) {
+        atomicAdd(stats + 1, (unsigned long long)(clock64() - ev_t0));
+        atomicAdd(stats + 2, (unsigned long long)ev_wait);
+        atomicAdd(stats + 10, (unsigned long long)ev_units);
+    }
+#endif
+    (void)ev_wait; (void)ev_units;
 }
 
 // Items in the order of decreasing cost (one CTA, bitonic sort in shared memory): handed out in this
@@ -1073,9 +1199,14 @@ template <typename T> size_t tiled_ws_blocks_bytes(const TiledPlan& pl) {
 template <typename T>
 int pair_tiled(const void* sorted, const void* tiles, int64_t n_src, const void* tgt, const int64_t* tgt_perm,
                int64_t n_tgt, const CsfFieldParams* fp, T* frep, int accumulate, void* ws, size_t wsb,
-               const unsigned int* item_order, unsigned int* item_cost, unsigned long long* stats, cudaStream_t st) {
+               const unsigned int* item_order, unsigned int* item_cost, unsigned long long* stats, int flags,
+               cudaStream_t st) {
     if (n_tgt <= 0) return 0;
     if (n_src <= 0 || fp->f_0 == 0.0) {
+        if (flags & CSF_TILED_NO_REDUCE) {
+            csf_set_error("csf_pair_forces_tiled: CSF_TILED_NO_REDUCE needs sources and f_0 != 0", cudaErrorInvalidValue);
+            return -(int)cudaErrorInvalidValue;
+        }
         if (!accumulate) cudaMemsetAsync(frep, 0, sizeof(T) * 2 * n_tgt, st);
         return 0;
     }
@@ -1092,9 +1223,11 @@ int pair_tiled(const void* sorted, const void* tiles, int64_t n_src, const void*
     unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
     Tile<T>* tblocks = reinterpret_cast<Tile<T>*>((unsigned char*)ws + kWsHeader);
     T* partial = reinterpret_cast<T*>((unsigned char*)ws + off_partial);
-    block_bounds_kernel<T><<<(unsigned)(((int64_t)pl.n_tblocks * 32 + 127) / 128), 128, 0, st>>>(
-        (const Xycs<T>*)tgt, tgt_perm, n_tgt, kBT, tblocks, pl.n_tblocks, counter);
-    CSF_CHECK_LAUNCH("block_bounds_kernel");
+    if (!(flags & CSF_TILED_PREPARED)) {
+        block_bounds_kernel<T><<<(unsigned)(((int64_t)pl.n_tblocks * 32 + 127) / 128), 128, 0, st>>>(
+            (const Xycs<T>*)tgt, tgt_perm, n_tgt, kBT, tblocks, pl.n_tblocks, counter);
+        CSF_CHECK_LAUNCH("block_bounds_kernel");
+    }
     if (fp->p2r)
         pair_tiled_kernel<T, true><<<pl.grid, kTThreads, smem, st>>>(
             (const unsigned char*)sorted, (const Tile<T>*)tiles, pl.n_tiles, (const Xycs<T>*)tgt, tgt_perm, n_tgt,
@@ -1104,10 +1237,32 @@ int pair_tiled(const void* sorted, const void* tiles, int64_t n_src, const void*
             (const unsigned char*)sorted, (const Tile<T>*)tiles, pl.n_tiles, (const Xycs<T>*)tgt, tgt_perm, n_tgt,
             tblocks, k, cc, partial, pl.group_chunks, pl.n_groups, pl.n_tblocks, counter, item_order, item_cost, stats);
     CSF_CHECK_LAUNCH("pair_tiled_kernel");
+    if (flags & CSF_TILED_NO_REDUCE) return 0;          // the caller sums partial[group][target][2] * f_0 itself
     const int64_t n2 = n_tgt * 2;
     reduce_groups_kernel<T><<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(partial, pl.n_groups, n_tgt, (T)fp->f_0, frep,
                                                                            accumulate);
     CSF_CHECK_LAUNCH("reduce_groups_kernel");
+    return 0;
+}
+
+template <typename T>
+int tiled_prepare(const void* xycs, int64_t n_src, const int64_t* perm, void* sorted, void* tiles, const void* tgt,
+                  const int64_t* tgt_perm, int64_t n_tgt, void* ws, size_t wsb, const CsfPeerComm* comm, cudaStream_t st) {
+    if (n_src <= 0 || n_tgt <= 0) return 0;
+    const TiledPlan pl = tiled_plan<T>(n_src, n_tgt);
+    if (ws == nullptr || wsb < kWsHeader + tiled_ws_blocks_bytes<T>(pl)) {
+        csf_set_error("csf_tiled_prepare: workspace too small", cudaErrorInvalidValue);
+        return -(int)cudaErrorInvalidValue;
+    }
+    CsfPeerComm c;
+    memset(&c, 0, sizeof(c));
+    if (comm) c = *comm;
+    const int64_t bb_ctas = ((int64_t)pl.n_tblocks + kCT - 1) / kCT;
+    tiled_prepare_kernel<T><<<(unsigned)(pl.n_chunks + bb_ctas), kCT * 32, 0, st>>>(
+        (const Xycs<T>*)xycs, n_src, perm, (unsigned char*)sorted, (Tile<T>*)tiles, pl.n_tiles, pl.n_chunks,
+        (const Xycs<T>*)tgt, tgt_perm, n_tgt, reinterpret_cast<Tile<T>*>((unsigned char*)ws + kWsHeader), pl.n_tblocks,
+        reinterpret_cast<unsigned int*>(ws), c);
+    CSF_CHECK_LAUNCH("tiled_prepare_kernel");
     return 0;
 }
 
@@ -1182,16 +1337,35 @@ int csf_tile_sources_f64(const void* xycs, int64_t n, const int64_t* perm, void*
 int csf_pair_forces_tiled_f32(const void* sorted, const void* tiles, int64_t n_src, const void* tgt,
                               const int64_t* tgt_perm, int64_t n_tgt, const CsfFieldParams* fp, float* frep,
                               int accumulate, void* ws, size_t wsb, const unsigned int* item_order,
-                              unsigned int* item_cost, unsigned long long* stats, csf_stream_t st) {
+                              unsigned int* item_cost, unsigned long long* stats, int flags, csf_stream_t st) {
     return pair_tiled<float>(sorted, tiles, n_src, tgt, tgt_perm, n_tgt, fp, frep, accumulate, ws, wsb, item_order,
-                             item_cost, stats, (cudaStream_t)st);
+                             item_cost, stats, flags, (cudaStream_t)st);
 }
 int csf_pair_forces_tiled_f64(const void* sorted, const void* tiles, int64_t n_src, const void* tgt,
                               const int64_t* tgt_perm, int64_t n_tgt, const CsfFieldParams* fp, double* frep,
                               int accumulate, void* ws, size_t wsb, const unsigned int* item_order,
-                              unsigned int* item_cost, unsigned long long* stats, csf_stream_t st) {
+                              unsigned int* item_cost, unsigned long long* stats, int flags, csf_stream_t st) {
     return pair_tiled<double>(sorted, tiles, n_src, tgt, tgt_perm, n_tgt, fp, frep, accumulate, ws, wsb, item_order,
-                              item_cost, stats, (cudaStream_t)st);
+                              item_cost, stats, flags, (cudaStream_t)st);
+}
+int csf_tiled_prepare_f32(const void* xycs, int64_t n_src, const int64_t* perm, void* sorted, void* tiles, const void* tgt,
+                          const int64_t* tgt_perm, int64_t n_tgt, void* ws, size_t wsb, const CsfPeerComm* comm,
+                          csf_stream_t st) {
+    return tiled_prepare<float>(xycs, n_src, perm, sorted, tiles, tgt, tgt_perm, n_tgt, ws, wsb, comm, (cudaStream_t)st);
+}
+int csf_tiled_prepare_f64(const void* xycs, int64_t n_src, const int64_t* perm, void* sorted, void* tiles, const void* tgt,
+                          const int64_t* tgt_perm, int64_t n_tgt, void* ws, size_t wsb, const CsfPeerComm* comm,
+                          csf_stream_t st) {
+    return tiled_prepare<double>(xycs, n_src, perm, sorted, tiles, tgt, tgt_perm, n_tgt, ws, wsb, comm, (cudaStream_t)st);
+}
+int csf_tiled_num_groups(int64_t n_src, int64_t n_tgt, int elem_bytes) {
+    if (n_src <= 0 || n_tgt <= 0) return 0;
+    return elem_bytes == 4 ? tiled_plan<float>(n_src, n_tgt).n_groups : tiled_plan<double>(n_src, n_tgt).n_groups;
+}
+size_t csf_tiled_partial_offset(int64_t n_src, int64_t n_tgt, int elem_bytes) {
+    if (n_src <= 0 || n_tgt <= 0) return 0;
+    if (elem_bytes == 4) return kWsHeader + tiled_ws_blocks_bytes<float>(tiled_plan<float>(n_src, n_tgt));
+    return kWsHeader + tiled_ws_blocks_bytes<double>(tiled_plan<double>(n_src, n_tgt));
 }
 int64_t csf_tiled_num_items(int64_t n_src, int64_t n_tgt, int elem_bytes) {
     if (n_src <= 0 || n_tgt <= 0) return 0;

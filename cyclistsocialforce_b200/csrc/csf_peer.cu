@@ -3,73 +3,44 @@
 // One crowd is sharded by contiguous agent range (distributed.py); after K2/K3 every rank has new
 // payload entries (16 B / 32 B per agent) for its own range and every other rank needs them before its
 // next K1.  Each rank owns one peer-mapped buffer (cudaMalloc + CUDA IPC): the full payload array plus
-// two arrays of monotonic flags.  Per step, in stream order:
-//   csf_peer_wait_data    : spin until every peer's push #push_seq has landed in MY buffer
-//   ... tile build, K1, reduce (the only readers of the payload) ...
-//   csf_peer_signal_read  : ++read_seq, store it into every peer's read_flags[me]  ("I am done reading")
+// two arrays of monotonic flags.  An exchange epoch e = (pushes completed) + 1; per step, in stream order:
+//   wait data    : spin until every peer's push of epoch e - 1 has landed in MY buffer
+//   ... tile build, K1 (the only readers of the payload) ...
+//   signal read  : store e into every peer's read_flags[me]   ("I am done reading your entries")
 //   ... K2/K3 writes my own range locally ...
-//   csf_peer_push         : wait until every peer has signalled read #read_seq, store my range into
-//                           every peer's buffer (16-byte NVLink stores), system fence, ++push_seq and
-//                           store it into every peer's data_flags[me]
-// All ranks issue the same sequence, so the counters agree without any host round trip and the three
-// kernels have fixed arguments (they replay from a CUDA graph).  Spins are bounded (~4 s): on a
-// timeout the kernel sets a status word and carries on, the host raises at the next check.
-#include "csf_common.cuh"
+//   push         : wait until every peer has signalled read e, store my range into every peer's buffer
+//                  (16-byte NVLink stores), system fence, pushes completed = e, store e into every peer's
+//                  data_flags[me]
+// The production step embeds the three in its own kernels (csf_peer.cuh: the tile-build kernel waits,
+// the per-agent kernel signals, steps the agents and pushes); the stand-alone kernels below do the same
+// for a payload written by something else (Engine.pack after a host upload, the first exchange).  All
+// ranks issue the same sequence, so the counters agree without any host round trip and every kernel has
+// fixed arguments (they replay from a CUDA graph).  Spins are bounded (~4 s); a time-out is sticky: the
+// status word stays set, later waits and pushes are skipped and the host raises at its next step.
+#include "csf_peer.cuh"
+#include <string.h>
 
 namespace {
 
-__device__ __forceinline__ unsigned long long gtimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ uint32_t ld_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// wait until *flag >= want; false on timeout
-__device__ __forceinline__ bool spin_ge(const uint32_t* flag, uint32_t want) {
-    if ((int32_t)(ld_sys(flag) - want) >= 0) return true;
-    const unsigned long long t0 = gtimer();
-    while ((int32_t)(ld_sys(flag) - want) < 0) {
-        if (gtimer() - t0 > 4000000000ull) return false;
-        __nanosleep(100);
-    }
-    return true;
-}
-enum { SEQ_PUSH = 0, SEQ_READ = 1, SEQ_BLOCKS = 2, SEQ_STATUS = 3 };
+__global__ void peer_wait_data_kernel(CsfPeerComm c) { csf_peer_wait_all(c); }
 
-__global__ void peer_wait_data_kernel(CsfPeerComm c) {
-    const int p = threadIdx.x;
-    if (p < c.world && p != c.rank) {
-        const uint32_t want = ld_sys(c.seq + SEQ_PUSH);
-        if (!spin_ge(c.data_flags[c.rank] + p, want)) atomicOr(c.seq + SEQ_STATUS, 1u);
-    }
-    __threadfence_system();
-}
-
+// epoch of the exchange in progress = pushes completed + 1 (every rank signals once and pushes once per epoch)
 __global__ void peer_signal_read_kernel(CsfPeerComm c) {
-    __shared__ uint32_t s;
-    if (threadIdx.x == 0) {
-        s = c.seq[SEQ_READ] + 1;
-        c.seq[SEQ_READ] = s;
-    }
-    __syncthreads();
+    const uint32_t e = ld_sys(c.seq + SEQ_PUSH) + 1u;
     const int p = threadIdx.x;
-    if (p < c.world && p != c.rank) st_sys(c.read_flags[p] + c.rank, s);
+    if (p < c.world && p != c.rank) st_sys(c.read_flags[p] + c.rank, e);
 }
 
 // first16 / n16: this rank's range of the payload in 16-byte units
 __global__ void peer_push_kernel(CsfPeerComm c, int64_t first16, int64_t n16) {
-    if (threadIdx.x < c.world && threadIdx.x != c.rank) {
-        const uint32_t want = ld_sys(c.seq + SEQ_READ);
-        if (!spin_ge(c.read_flags[c.rank] + threadIdx.x, want)) atomicOr(c.seq + SEQ_STATUS, 2u);
+    __shared__ uint32_t s_epoch;
+    if (threadIdx.x == 0) s_epoch = ld_sys(c.seq + SEQ_PUSH) + 1u;
+    __syncthreads();
+    if (threadIdx.x < c.world && threadIdx.x != c.rank && peer_ok(c)) {
+        if (!spin_ge(c.read_flags[c.rank] + threadIdx.x, s_epoch)) peer_fail(c, 2u);
     }
     __syncthreads();
+    if (!peer_ok(c)) return;        // out of step with the peers: nothing is pushed any more
     const uint4* src = reinterpret_cast<const uint4*>(c.payload[c.rank]) + first16;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
         const uint4 v = src[i];
@@ -84,7 +55,7 @@ __global__ void peer_push_kernel(CsfPeerComm c, int64_t first16, int64_t n16) {
         s_last = (t == gridDim.x - 1) ? 1u : 0u;
         if (s_last) {
             c.seq[SEQ_BLOCKS] = 0;
-            s_seq = c.seq[SEQ_PUSH] + 1;
+            s_seq = s_epoch;
             c.seq[SEQ_PUSH] = s_seq;
             __threadfence_system();
         }

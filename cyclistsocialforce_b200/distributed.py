@@ -111,6 +111,7 @@ class PeerExchange:
     CUDA graph.  One node only (CUDA IPC); ``torch.distributed`` is used once, to swap the handles."""
 
     capturable = True
+    fused = True        # the Engine's fused step kernels wait / signal / push themselves (``comm``)
 
     def __init__(self, n_global, rank, world, dtype, device, group=None, bounds=None):
         import ctypes as C
@@ -180,6 +181,9 @@ class PeerExchange:
             comm.data_flags[p] = self.peers[p] + self.off_data
             comm.read_flags[p] = self.peers[p] + self.off_read
         comm.seq = self.base + self.off_seq
+        # host-mapped mirror of the status word: Engine.step() polls it without a copy
+        self.status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        comm.status_host = self.status_host.data_ptr()
         self.comm = comm
         self._C = C
         shape, typestr = ((n_global, 4), "<i4") if self.f32 else ((n_global, 4), "<f8")
@@ -202,12 +206,18 @@ class PeerExchange:
                             "csf_peer_signal_read")
 
     def __call__(self, payload):
+        """One stand-alone exchange epoch for a payload range written by something else than the fused
+        step (Engine.pack): signal "done reading", then push."""
         if self.world == 1:
             return
         assert payload.data_ptr() == self.base, "PeerExchange: the engine must use payload_tensor() as its payload"
         self.calls += 1
+        self.after_pair()
         self._lib_mod.check(self.lib.csf_peer_push(self._C.byref(self.comm), self.lo, self.hi - self.lo,
                                                    self.elem_bytes, self._st()), "csf_peer_push")
+
+    def poll_status(self):
+        return bool(self.status_host[0] != 0)
 
     def check_status(self):
         st = int(self._seq[3].item())

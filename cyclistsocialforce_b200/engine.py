@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .parameters import VehicleParameters, choose_q_scale
+from .parameters import VehicleParameters, choose_q_scale, payload_frame
 
 N_STATES = dict(twod=5, invpendulum=6, balancingrider=8, planarpoint=4, bicycle=5, uncontrolled=4)
 _WRAP_MODELS = ("twod", "invpendulum", "bicycle")
@@ -29,7 +29,17 @@ _STATE_COLS = ("x", "y", "psi", "v", "delta", "theta", "deltadot", "thetadot")
 _FIELD_AXIS = dict(vd_default=0, step_i=0, destq=0, dest_len=0, dest_ptr=0, znav=0, znav_v0=0, znav_d0=0, znav_d1=0,
                    prev_x=0, prev_y=0, hist_x=1, hist_y=1, hist_step=0, ip_x=1, ip_zrid=0, ip_delta_run=0,
                    dyn_x=1, dyn_v=0, br_gains=1)
-HIST_CAP = 128
+HIST_CAP = 128     # smallest ring of past positions (rows); sized per group from t_s, see hist_capacity()
+
+
+def hist_capacity(params):
+    """Rows of the position ring: the look-back of the last-destination spline is int(1 / t_s) steps
+    (reference vehicle.py:1486-1492); the kernel indexes the ring modulo a power of two above it."""
+    need = int(1 / params.t_s) + 2
+    cap = HIST_CAP
+    while cap < need:
+        cap *= 2
+    return cap
 
 
 def _wrap_angle(a):
@@ -99,9 +109,10 @@ class AgentGroup:
         needs_hist = model in ("twod", "invpendulum", "planarpoint")
         self.prev_x = t64(s0[:, 0]) if needs_hist else None
         self.prev_y = t64(s0[:, 1]) if needs_hist else None
+        self.hist_cap = hist_capacity(params)
         if needs_hist:
-            self.hist_x = torch.zeros((HIST_CAP, n), dtype=f64, device=dev)
-            self.hist_y = torch.zeros((HIST_CAP, n), dtype=f64, device=dev)
+            self.hist_x = torch.zeros((self.hist_cap, n), dtype=f64, device=dev)
+            self.hist_y = torch.zeros((self.hist_cap, n), dtype=f64, device=dev)
             self.hist_x[0] = self.x
             self.hist_y[0] = self.y
             self.hist_step = torch.zeros(n, dtype=i32, device=dev)
@@ -124,10 +135,17 @@ class AgentGroup:
         elif model == "planarpoint":
             self.dyn_x = t64(s0[:, 2][None, :])
             self.dyn_v = t64(s0[:, 3])
-        self.status = torch.zeros(1, dtype=i32, device=dev)
+        self._init_status()
         self.payload_offset = 0
         self._cstate = None
         self._cparams = None
+
+    def _init_status(self):
+        """Device status word + its mirror in pinned (host-mapped) memory: the kernels raise the mirror
+        whenever they set a status bit, the host polls it every step without a copy or a sync."""
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.version = 0             # bumped whenever a device pointer or parameter the kernels see changes
 
     def _make_state_slab(self, n, cols):
         """The CSF state columns (x, y double; psi, v, delta ... in T) are views into ONE device slab, so
@@ -162,7 +180,8 @@ class AgentGroup:
         for name in _FIELD_AXIS:
             setattr(g, name, fields.get(name))
         g.destq_host, g.dest_len_host = destq_host, dest_len_host
-        g.status = torch.zeros(1, dtype=torch.int32, device=g.device)
+        g.hist_cap = like.hist_cap
+        g._init_status()
         g.payload_offset = 0
         g._cstate = g._cparams = None
         return g
@@ -238,17 +257,21 @@ class AgentGroup:
                          "ip_zrid", "ip_delta_run", "dyn_x", "dyn_v", "br_gains", "status"):
                 t = getattr(self, name)
                 setattr(s, name, t.data_ptr() if t is not None else None)
+            s.status_host = self.status_host.data_ptr()     # (UVA: pinned host memory is device-addressable)
             self._cstate = s
         return self._cstate
 
-    def cparams(self, q_scale):
-        if self._cparams is None or self._cparams.q_scale != q_scale or self._cparams.q_cap != self.q_cap:
-            self._cparams = self.params.to_agent_params(q_scale, self.q_cap, HIST_CAP)
+    def cparams(self, q_scale, origin=(0.0, 0.0)):
+        c = self._cparams
+        if (c is None or c.q_scale != q_scale or c.q_cap != self.q_cap or c.q_origin[0] != origin[0]
+                or c.q_origin[1] != origin[1]):
+            self._cparams = self.params.to_agent_params(q_scale, self.q_cap, self.hist_cap, origin)
         return self._cparams
 
     def invalidate(self):
         self._cstate = None
         self._cparams = None
+        self.version += 1
 
     # ---- host views -----------------------------------------------------------------------
     def states_numpy(self):
@@ -323,6 +346,10 @@ class AgentGroup:
         s.first, s.count = first, count
         return s
 
+    def poll_status(self):
+        """True if a kernel has raised a status bit since the last check (no copy, no synchronisation)."""
+        return bool(self.status_host[0] != 0)
+
     def check_status(self):
         st = int(self.status.item())
         if st & 1:
@@ -359,10 +386,14 @@ class Engine:
     """One interaction domain (``SocialForceIntersection``): groups + obstacles + road edges."""
 
     def __init__(self, groups, obstacles=None, priority_rule="unregulated", road_edges=(),
-                 dtype=torch.float32, device="cuda", q_scale=None, extent=None, scenario_size=None,
+                 dtype=torch.float32, device="cuda", q_scale=None, extent=None, origin=None, scenario_size=None,
                  n_global=None, global_offset=0, exchange=None, pair_mode="auto", resort_every=64,
                  count_pairs=False, graph=False):
-        """``n_global`` / ``global_offset`` / ``exchange``: agent-range sharding of one crowd over
+        """``q_scale`` / ``extent`` / ``origin``: the Q-format frame of the f32 payload -- positions are
+        stored as int32 multiples of ``q_scale`` (default: the finest power of two that fits ``extent``
+        into 2^30 units) relative to ``origin`` (default with ``extent``/``q_scale``: (0, 0); with neither:
+        frame fitted to the crowd, see ``parameters.payload_frame``).
+        ``n_global`` / ``global_offset`` / ``exchange``: agent-range sharding of one crowd over
         several GPUs -- this engine owns agents [global_offset, global_offset + n) of an
         ``n_global``-agent crowd with homogeneous field parameters; ``exchange(payload)`` is
         called after every step to all-gather the pair payload (see distributed.py).
@@ -397,17 +428,24 @@ class Engine:
         self.n_agents = sum(g.n for g in self.groups)
         self.n_total = off if n_global is None else int(n_global)
         # Q-format scale of the f32 payload
+        if q_scale is None and extent is None and n_global is not None:
+            # every rank must quantise the exchanged payload with the same scale: it cannot be derived
+            # from the local shard
+            raise ValueError("a sharded crowd (n_global) needs q_scale or extent: the same value on every rank")
         if q_scale is None:
             if extent is None:
-                extent = 1.0
+                pts = []
                 for g in self.groups:
-                    extent = max(extent, float(g.x.abs().max()), float(g.y.abs().max()),
-                                 float(np.abs(g.destq_host[..., :2]).max()))
-                for o in self.obstacles:
-                    extent = max(extent, float(np.abs(o.host[:, :2]).max()))
-                extent = 2.0 * extent + 1000.0
+                    pts.append(torch.stack([g.x, g.y], dim=1).cpu().numpy())
+                    valid = np.arange(g.q_cap)[None, :] < g.dest_len_host[:, None]
+                    pts.append(g.destq_host[..., :2][valid])
+                pts += [o.host[:, :2] for o in self.obstacles]
+                fitted, extent = payload_frame(pts)
+                if origin is None:
+                    origin = fitted
             q_scale = choose_q_scale(extent)
         self.q_scale = float(q_scale)
+        self.q_origin = (0.0, 0.0) if origin is None else (float(origin[0]), float(origin[1]))
         self.elem_bytes = 16 if self.f32 else 32
         n = max(self.n_total, 1)
         if exchange is not None and hasattr(exchange, "payload_tensor"):
@@ -447,7 +485,7 @@ class Engine:
                 wsb = max(wsb, int(self.lib.csf_pair_workspace_bytes(c, self.n_agents, 4 if self.f32 else 8)))
         self.tiled = (scenario_size is None and self.n_total > 1 and not self._ecc and
                       (pair_mode == "tiled" or (pair_mode == "auto" and self.n_total >= 2048)))
-        self.pair_stats = torch.zeros(1, dtype=torch.int64, device=self.device) if count_pairs else None
+        self.pair_stats = torch.zeros(16, dtype=torch.int64, device=self.device) if count_pairs else None
         self._tiles = []
         self._pair_calls = 0
         if self.tiled:
@@ -459,7 +497,6 @@ class Engine:
                 self._tiles.append(dict(
                     sorted=torch.zeros((n_pad, 4), dtype=self.payload.dtype, device=self.device),
                     tiles=torch.zeros((n_tiles, tile_elems), dtype=self.payload.dtype, device=self.device),
-                    keys=torch.zeros(c, dtype=torch.int64, device=self.device),
                     perm=torch.zeros(c, dtype=torch.int64, device=self.device)))
                 # scheduling of the pair kernel's work items: cost per item (written by every launch) and
                 # the order to hand them out in (heaviest first; refreshed with the spatial order)
@@ -471,7 +508,7 @@ class Engine:
                                     if 0 < n_items <= 4096 else None)
                 wsb = max(wsb, int(self.lib.csf_pair_tiled_workspace_bytes(c, self.n_agents, eb)))
             # visiting order of the local targets (Morton order too: compact target blocks)
-            self._tgt_keys = torch.zeros(self.n_agents, dtype=torch.int64, device=self.device)
+            self._key_box = None
             self._tgt_perm = None
             self._order_valid = False
             self._single_class = (len(self.classes) == 1 and self.classes[0][0] == self.global_offset
@@ -479,8 +516,16 @@ class Engine:
             self._morton = (-float(extent if extent is not None else 2.0 ** 30 * self.q_scale),
                             2.0 * float(extent if extent is not None else 2.0 ** 30 * self.q_scale) / 65536.0)
         self.ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=self.device)
+        # Fused step (three launches: tile build + block bounds [+ wait for the peers' pushes] -> pair kernel
+        # -> per-agent kernel that also reduces the pair kernel's partial sums [and signals / pushes to the
+        # peers]): one tiled source class, no Bicycle-field sources
+        self._fused = bool(self.tiled and len(self.classes) == 1 and self.classes[0][3].field_kind == 0)
+        self._fusion = {}
         self.gpu_launches = 0
-        self.pack()
+        self._road_version = 0
+        self._graph_version = None
+        with torch.cuda.device(self.device):
+            self.pack()
 
     # ---- helpers ----------------------------------------------------------------------------
     def _stream(self):
@@ -498,49 +543,60 @@ class Engine:
                                       device=self.device).contiguous(), k[0], k[1])
                      for k, v in merged.items()]
         self.froad = torch.zeros_like(self.frep) if self.road else None
+        self._road_version = getattr(self, "_road_version", 0) + 1
+
+    def _version(self):
+        """Changes whenever something a captured step graph has baked in (device pointers of the groups,
+        their parameters, the road vertices) is replaced."""
+        return (self._road_version,) + tuple(g.version for g in self.groups)
 
     def pack(self):
         """update_road_user_positions (intersection.py:660-677): state -> pair payload."""
         st = self._stream()
         for g in self.groups:
-            _lib.check(self._fn("csf_pack_xycs")(C.byref(g.cstate()), C.byref(g.cparams(self.q_scale)),
+            _lib.check(self._fn("csf_pack_xycs")(C.byref(g.cstate()), C.byref(g.cparams(self.q_scale, self.q_origin)),
                                                  _ptr(self.payload), st), "csf_pack_xycs")
             self.gpu_launches += 1
         for o in self.obstacles:
             dst = C.c_void_p(self.payload.data_ptr() + o.payload_offset * self.elem_bytes)
-            _lib.check(self._fn("csf_pack_xypsi")(_ptr(o.x), _ptr(o.y), _ptr(o.psi), o.n, self.q_scale, dst, st),
+            _lib.check(self._fn("csf_pack_xypsi")(_ptr(o.x), _ptr(o.y), _ptr(o.psi), o.n, self.q_scale, self.q_origin[0],
+                                                  self.q_origin[1], dst, st),
                        "csf_pack_xypsi")
             self.gpu_launches += 1
 
     _capturing = False
 
     def _refresh_order(self):
-        """Spatial (Hilbert) visiting order of the sources of every class and of the local targets:
-        keys on the device (csf_morton_keys_*), sort by torch (plumbing), written into buffers whose
-        addresses never change (a captured CUDA graph keeps pointing at them)."""
+        """Spatial (Hilbert) visiting order of the sources of every class and of the local targets, on the
+        device and inside the library: bounding box of all road users, keys, radix sort (csf_spatial_*),
+        written into buffers whose addresses never change (a captured CUDA graph keeps pointing at them)."""
         st = self._stream()
-        # key domain = bounding box of all road users, reduced and consumed on the device: see key_xy
-        px, py = self.payload[:self.n_total, 0], self.payload[:self.n_total, 1]
-        self._key_box = torch.stack([px.min(), px.max(), py.min(), py.max()]).to(torch.float64)
+        if self._key_box is None:
+            self._key_box = torch.zeros(4, dtype=torch.float64, device=self.device)
+            nmax = max([c for _, c, _, _ in self.classes] + [self.n_agents])
+            self._order_ws = torch.empty(int(self.lib.csf_spatial_order_workspace_bytes(nmax)), dtype=torch.uint8,
+                                         device=self.device)
+        _lib.check(self._fn("csf_spatial_bbox")(_ptr(self.payload), self.n_total, _ptr(self._key_box), st),
+                   "csf_spatial_bbox")
+        self.gpu_launches += 1
         for ci, (s, c, _, fp) in enumerate(self.classes):
             if fp.field_kind == 1:
                 continue
             tl = self._tiles[ci]
             src = C.c_void_p(self.payload.data_ptr() + s * self.elem_bytes)
-            _lib.check(self._fn("csf_spatial_keys")(src, c, _ptr(self._key_box), _ptr(tl["keys"]), st),
-                       "csf_spatial_keys")
-            tl["perm"].copy_(torch.argsort(tl["keys"]))
-            self.gpu_launches += 1
+            _lib.check(self._fn("csf_spatial_order")(src, c, _ptr(self._key_box), _ptr(tl["perm"]), _ptr(self._order_ws),
+                                                     self._order_ws.numel(), st), "csf_spatial_order")
+            self.gpu_launches += 2
         if self._single_class:      # one class covering exactly the targets: same order
             self._tgt_perm = self._tiles[0]["perm"]
         else:
             tgt = C.c_void_p(self.payload.data_ptr() + self.global_offset * self.elem_bytes)
-            _lib.check(self._fn("csf_spatial_keys")(tgt, self.n_agents, _ptr(self._key_box), _ptr(self._tgt_keys), st),
-                       "csf_spatial_keys")
             if self._tgt_perm is None:
                 self._tgt_perm = torch.zeros(self.n_agents, dtype=torch.int64, device=self.device)
-            self._tgt_perm.copy_(torch.argsort(self._tgt_keys))
-            self.gpu_launches += 1
+            _lib.check(self._fn("csf_spatial_order")(tgt, self.n_agents, _ptr(self._key_box), _ptr(self._tgt_perm),
+                                                     _ptr(self._order_ws), self._order_ws.numel(), st),
+                       "csf_spatial_order")
+            self.gpu_launches += 2
         self._order_valid = True
         self._refresh_item_order()
 
@@ -559,6 +615,8 @@ class Engine:
         if not self.tiled:
             return
         if not self._order_valid or self._pair_calls % max(self.resort_every, 1) == 0:
+            if self.exchange is not None and hasattr(self.exchange, "begin_step"):
+                self.exchange.begin_step()  # the keys are computed from the peers' payload: wait for their pushes
             self._refresh_order()
         elif self._pair_calls == 1:
             self._refresh_item_order()
@@ -606,7 +664,7 @@ class Engine:
                         _lib.check(self._fn("csf_pair_forces_tiled")(
                             _ptr(tl["sorted"]), _ptr(tl["tiles"]), c, tgt, _ptr(self._tgt_perm), self.n_agents,
                             C.byref(fp), _ptr(self.frep), 1 if ci > 0 else 0, _ptr(self.ws), self.ws.numel(),
-                            _ptr(tl["item_order"]), _ptr(tl["item_cost"]), _ptr(self.pair_stats), st),
+                            _ptr(tl["item_order"]), _ptr(tl["item_cost"]), _ptr(self.pair_stats), 0, st),
                             "csf_pair_forces_tiled")
                         self.gpu_launches += 4   # tile build (+ chunk bounds), block bounds, pair, reduce
                         continue
@@ -626,6 +684,72 @@ class Engine:
                                "csf_road_forces")
                     self.gpu_launches += 1
 
+    def _fusion_of(self, g):
+        """CsfStepFusion of group g: where the pair kernel leaves its partial sums, and the peer exchange."""
+        key = (id(g), g.payload_offset)
+        fu = self._fusion.get(key)
+        if fu is None:
+            s, c, _, fp = self.classes[0]
+            eb = 4 if self.f32 else 8
+            fu = _lib.CsfStepFusion()
+            fu.partial = self.ws.data_ptr() + int(self.lib.csf_tiled_partial_offset(c, self.n_agents, eb))
+            fu.partial_stride = self.n_agents
+            fu.partial_offset = g.payload_offset - self.global_offset
+            fu.n_groups = int(self.lib.csf_tiled_num_groups(c, self.n_agents, eb))
+            fu.f0 = fp.f_0
+            if self._peer_fused():
+                fu.comm = self.exchange.comm
+            self._fusion[key] = fu
+        return fu
+
+    def _peer_fused(self):
+        return self.exchange is not None and bool(getattr(self.exchange, "fused", False))
+
+    def _step_fused(self, exchange=True, mark=None):
+        """The step as three launches (see __init__).  ``mark(i)``, if given, is called before launch i and
+        after the last one (bench.py records CUDA events there: per-kernel durations)."""
+        mark = mark or (lambda i: None)
+        st = self._stream()
+        if not self._capturing:
+            self._maybe_refresh()
+        self._pair_calls += 1
+        s, c, _, fp = self.classes[0]
+        tl = self._tiles[0]
+        src = C.c_void_p(self.payload.data_ptr() + s * self.elem_bytes)
+        tgt = C.c_void_p(self.payload.data_ptr() + self.global_offset * self.elem_bytes)
+        comm = C.byref(self.exchange.comm) if self._peer_fused() else None
+        if self.exchange is not None and not self._peer_fused() and hasattr(self.exchange, "begin_step"):
+            self.exchange.begin_step()
+        mark(0)
+        _lib.check(self._fn("csf_tiled_prepare")(src, c, _ptr(tl["perm"]), _ptr(tl["sorted"]), _ptr(tl["tiles"]), tgt,
+                                                 _ptr(self._tgt_perm), self.n_agents, _ptr(self.ws), self.ws.numel(),
+                                                 comm, st), "csf_tiled_prepare")
+        mark(1)
+        _lib.check(self._fn("csf_pair_forces_tiled")(
+            _ptr(tl["sorted"]), _ptr(tl["tiles"]), c, tgt, _ptr(self._tgt_perm), self.n_agents, C.byref(fp),
+            _ptr(self.frep), 0, _ptr(self.ws), self.ws.numel(), _ptr(tl["item_order"]), _ptr(tl["item_cost"]),
+            _ptr(self.pair_stats), _lib.CSF_TILED_PREPARED | _lib.CSF_TILED_NO_REDUCE, st), "csf_pair_forces_tiled")
+        self.gpu_launches += 2
+        mark(2)
+        if self.exchange is not None and not self._peer_fused() and hasattr(self.exchange, "after_pair"):
+            self.exchange.after_pair()
+        self._road(st)
+        for g in self.groups:
+            _lib.check(self._fn("csf_agent_step_fused")(
+                _lib.MODEL_IDS[g.model], C.byref(g.cstate()), C.byref(g.cparams(self.q_scale, self.q_origin)),
+                self.n_total, C.byref(self._fusion_of(g)), self._off(self.froad, g), self._off(self.force, g),
+                _ptr(self.payload), st), "csf_agent_step_fused")
+            self.gpu_launches += 1
+        mark(3)
+        if exchange and self.exchange is not None and not self._peer_fused():
+            self.exchange(self.payload)
+
+    def _step_kernels(self, exchange=True):
+        if self._fused and self.n_total > 1:
+            self._step_fused(exchange)
+        else:
+            self._agent_step(self._pair_and_road(), exchange=exchange)
+
     def _off(self, t, g):
         if t is None:
             return C.c_void_p(0)
@@ -634,11 +758,13 @@ class Engine:
     # ---- the three public operations -----------------------------------------------------------
     def calc_forces(self):
         """calc_forces (intersection.py:747-864): returns the device tensor force (N, 2)."""
+        if self.poll_status():
+            self.check_status()
         have_rep = self._pair_and_road()
         st = self._stream()
         for g in self.groups:
             _lib.check(self._fn("csf_agent_forces")(
-                _lib.MODEL_IDS[g.model], C.byref(g.cstate()), C.byref(g.cparams(self.q_scale)), self.n_total,
+                _lib.MODEL_IDS[g.model], C.byref(g.cstate()), C.byref(g.cparams(self.q_scale, self.q_origin)), self.n_total,
                 self._off(self.frep, g) if have_rep else C.c_void_p(0), self._off(self.froad, g),
                 self._off(self.force, g), self._off(self.fdest, g), st), "csf_agent_forces")
             self.gpu_launches += 1
@@ -649,7 +775,7 @@ class Engine:
         st = self._stream()
         for g in self.groups:
             _lib.check(self._fn("csf_agent_advance")(
-                _lib.MODEL_IDS[g.model], C.byref(g.cstate()), C.byref(g.cparams(self.q_scale)),
+                _lib.MODEL_IDS[g.model], C.byref(g.cstate()), C.byref(g.cparams(self.q_scale, self.q_origin)),
                 self._off(self.force, g), _ptr(self.payload), st), "csf_agent_advance")
             self.gpu_launches += 1
 
@@ -657,7 +783,7 @@ class Engine:
         st = self._stream()
         for g in self.groups:
             _lib.check(self._fn("csf_agent_step")(
-                _lib.MODEL_IDS[g.model], C.byref(g.cstate()), C.byref(g.cparams(self.q_scale)), self.n_total,
+                _lib.MODEL_IDS[g.model], C.byref(g.cstate()), C.byref(g.cparams(self.q_scale, self.q_origin)), self.n_total,
                 self._off(self.frep, g) if have_rep else C.c_void_p(0), self._off(self.froad, g),
                 self._off(self.force, g), _ptr(self.payload), st), "csf_agent_step")
             self.gpu_launches += 1
@@ -668,14 +794,25 @@ class Engine:
         """SocialForceIntersection.step (intersection.py:866-896), fused per-agent kernel."""
         if self.n_agents == 0:
             return
-        if self.use_graph:
-            return self._step_graph()
-        self._agent_step(self._pair_and_road())
+        if self.poll_status():
+            self.check_status()                 # raises: NaN / navigation state / payload range / exchange time-out
+        with torch.cuda.device(self.device):
+            if self.use_graph:
+                return self._step_graph()
+            self._step_kernels()
+
+    def poll_status(self):
+        """True if any kernel has raised a status bit (host-mapped words: no copy, no synchronisation)."""
+        if any(g.poll_status() for g in self.groups):
+            return True
+        return bool(self.exchange is not None and hasattr(self.exchange, "poll_status") and self.exchange.poll_status())
 
     def _step_graph(self):
         """The same kernel sequence replayed from a CUDA graph (launch-bound small crowds / shards)."""
         self._maybe_refresh()
         self._exchange_in_graph = bool(getattr(self.exchange, "capturable", False))
+        if self._graph is not None and self._graph_version != self._version():
+            self._graph = None              # a destination queue grew / road edges changed: stale device pointers
         if self._graph is None:
             launches0 = self.gpu_launches
             side = torch.cuda.Stream(device=self.device)
@@ -686,7 +823,7 @@ class Engine:
                 with torch.cuda.stream(side):
                     calls = self._pair_calls
                     with torch.cuda.graph(g, stream=side):
-                        self._agent_step(self._pair_and_road(), exchange=self._exchange_in_graph)
+                        self._step_kernels(exchange=self._exchange_in_graph)
                     self._pair_calls = calls
             finally:
                 self._capturing = False
@@ -694,6 +831,7 @@ class Engine:
             self._graph_launches = self.gpu_launches - launches0
             self.gpu_launches = launches0
             self._graph = g
+            self._graph_version = self._version()
         self._graph.replay()
         self._pair_calls += 1
         self.gpu_launches += self._graph_launches
@@ -703,8 +841,22 @@ class Engine:
     def step_host(self, host_in, host_out, host_force=None):
         """One step driven from HOST buffers (pinned): upload the CSF state (x, y, psi, v, delta ...)
         of every group-0 agent, step, download the new state and the total force.  This is the
-        call a host-side co-simulation loop makes; bench.py's ``e2e`` times it."""
+        call a host-side co-simulation loop makes; bench.py's ``e2e`` times it.
+        With ``graph=True`` and slab buffers the whole sequence -- upload, payload re-pack (+ exchange),
+        the step's kernels, both downloads -- is ONE CUDA graph per buffer set: one launch and one
+        synchronisation per step."""
         g = self.groups[0]
+        if self.poll_status():
+            self.check_status()
+        with torch.cuda.device(self.device):
+            if self.use_graph and torch.is_tensor(host_in) and torch.is_tensor(host_out):
+                return self._step_host_graph(host_in, host_out, host_force)
+            self._host_upload(g, host_in)
+            self.step()
+            self._host_download(g, host_out, host_force)
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def _host_upload(self, g, host_in):
         if torch.is_tensor(host_in):                # one pinned slab (layout: g.state_layout): one copy each way
             g.state_slab.copy_(host_in, non_blocking=True)
         else:
@@ -713,7 +865,8 @@ class Engine:
         self.pack()
         if self.exchange is not None:
             self.exchange(self.payload)
-        self.step()
+
+    def _host_download(self, g, host_out, host_force):
         if torch.is_tensor(host_out):
             host_out.copy_(g.state_slab, non_blocking=True)
         else:
@@ -721,6 +874,44 @@ class Engine:
                 dst.copy_(getattr(g, name), non_blocking=True)
         if host_force is not None:
             host_force.copy_(self.force[:g.n], non_blocking=True)
+
+    def _step_host_graph(self, host_in, host_out, host_force):
+        g = self.groups[0]
+        capt = bool(getattr(self.exchange, "capturable", self.exchange is None))
+        if not capt:                                 # a collective that cannot be captured: kernel by kernel
+            self._host_upload(g, host_in)
+            self.step()
+            self._host_download(g, host_out, host_force)
+            return torch.cuda.current_stream(self.device).synchronize()
+        self._maybe_refresh()
+        key = (host_in.data_ptr(), host_out.data_ptr(), host_force.data_ptr() if host_force is not None else 0,
+               self._version())
+        cache = self.__dict__.setdefault("_host_graphs", {})
+        entry = cache.get(key)
+        if entry is None:
+            if len(cache) > 8:
+                cache.clear()
+            launches0 = self.gpu_launches
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            gr = torch.cuda.CUDAGraph()
+            self._capturing = True
+            try:
+                with torch.cuda.stream(side):
+                    calls = self._pair_calls
+                    with torch.cuda.graph(gr, stream=side):
+                        self._host_upload(g, host_in)
+                        self._step_kernels(exchange=True)
+                        self._host_download(g, host_out, host_force)
+                    self._pair_calls = calls
+            finally:
+                self._capturing = False
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            entry = cache[key] = (gr, self.gpu_launches - launches0)
+            self.gpu_launches = launches0
+        entry[0].replay()
+        self._pair_calls += 1
+        self.gpu_launches += entry[1]
         torch.cuda.current_stream(self.device).synchronize()
 
     def check_status(self):
@@ -733,19 +924,19 @@ class Engine:
         """Vehicle.calcDestinationForce() of one agent (mutates its navigation state)."""
         st = g.cstate_range(k, 1)
         _lib.check(self._fn("csf_agent_forces")(
-            _lib.MODEL_IDS[g.model], C.byref(st), C.byref(g.cparams(self.q_scale)), 1, C.c_void_p(0),
+            _lib.MODEL_IDS[g.model], C.byref(st), C.byref(g.cparams(self.q_scale, self.q_origin)), 1, C.c_void_p(0),
             C.c_void_p(0), self._off(self.force, g), self._off(self.fdest, g), self._stream()), "csf_agent_forces")
         self.gpu_launches += 1
-        f = self.fdest[g.payload_offset + k].to(torch.float64).cpu().numpy()
+        f = self.fdest[g.payload_offset - self.global_offset + k].to(torch.float64).cpu().numpy()
         return float(f[0]), float(f[1])
 
     def agent_advance(self, g, k, F1, F2):
         """Vehicle.step(F1, F2) of one agent."""
-        self.force[g.payload_offset + k, 0] = float(F1)
-        self.force[g.payload_offset + k, 1] = float(F2)
+        self.force[g.payload_offset - self.global_offset + k, 0] = float(F1)
+        self.force[g.payload_offset - self.global_offset + k, 1] = float(F2)
         st = g.cstate_range(k, 1)
         _lib.check(self._fn("csf_agent_advance")(
-            _lib.MODEL_IDS[g.model], C.byref(st), C.byref(g.cparams(self.q_scale)), self._off(self.force, g),
+            _lib.MODEL_IDS[g.model], C.byref(st), C.byref(g.cparams(self.q_scale, self.q_origin)), self._off(self.force, g),
             _ptr(self.payload), self._stream()), "csf_agent_advance")
         self.gpu_launches += 1
 
@@ -759,11 +950,12 @@ class Engine:
         ps = np.r_[float(src_xypsi[2]), np.broadcast_to(np.asarray(psi, dtype=float), shape).ravel()]
         n = xs.shape[0]
         dev = self.device
-        q = choose_q_scale(2.0 * float(max(np.abs(xs).max(), np.abs(ys).max())) + 1000.0)
+        (ox, oy), ext = payload_frame([np.c_[xs, ys]], margin_abs=10.0)
+        q = choose_q_scale(ext)
         xd, yd, pd = (torch.as_tensor(a, dtype=torch.float64, device=dev) for a in (xs, ys, ps))
         pay = torch.zeros((n, 4), dtype=self.payload.dtype, device=dev)
         st = self._stream()
-        _lib.check(self._fn("csf_pack_xypsi")(_ptr(xd), _ptr(yd), _ptr(pd), n, q, _ptr(pay), st), "csf_pack_xypsi")
+        _lib.check(self._fn("csf_pack_xypsi")(_ptr(xd), _ptr(yd), _ptr(pd), n, q, ox, oy, _ptr(pay), st), "csf_pack_xypsi")
         fp = params.to_field_params(q, False)
         fp.hfov = 2 * math.pi
         out = torch.zeros((n - 1, 2), dtype=self.dtype, device=dev)

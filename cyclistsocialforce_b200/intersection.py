@@ -35,16 +35,33 @@ class RoadEdge:
         return _road_force_on_device(self.edges_flat(), x, y)
 
 
+def _place(local_xy, pose_xy, angle):
+    """Polyline given in a segment's own frame -> world frame: rotate by ``angle``, move to ``pose_xy``."""
+    c, s_ = np.cos(angle), np.sin(angle)
+    lx, ly = local_xy[:, 0], local_xy[:, 1]
+    return np.column_stack((pose_xy[0] + c * lx - s_ * ly, pose_xy[1] + s_ * lx + c * ly))
+
+
 class RoadSegment:
-    """reference :72-115."""
+    """A piece of road with a left and a right edge (reference :72-115).  Subclasses describe their centre
+    line in the segment's own frame through ``_edge(offset)`` -- the polyline ``offset`` metres to the
+    left of the centre line, sampled every ``ds`` -- and ``_end_pose()``; the base class places both edges
+    and the end pose ``x1`` (start pose of a following segment) in the world."""
 
     def __init__(self, x0, width, ds=0.1, params=None):
-        self.params = RoadElementParameters()
+        self.params = RoadElementParameters()       # (the reference keeps defaults here, :73-74)
         self.x0 = x0
         self.x1 = x0
         self.width = width
         self.edges = []
         self.ds = ds
+
+    def _build(self, frame_angle, params):
+        x0 = np.asarray(self.x0, dtype=float)
+        for side in (-1.0, 1.0):                     # right edge first, then left (reference order)
+            self.edges.append(RoadEdge(_place(self._edge(side * self.width / 2), x0[:2], frame_angle), params=params))
+        end_xy, end_heading = self._end_pose()
+        self.x1 = np.array([*_place(np.array([end_xy]), x0[:2], frame_angle)[0], x0[2] + end_heading])
 
     def edges_flat(self):
         return [e.edges_flat()[0] for e in self.edges]
@@ -54,58 +71,49 @@ class RoadSegment:
 
 
 class StraightRoadSegment(RoadSegment):
-    """reference :118-146."""
+    """Straight segment of ``length`` starting at pose ``x0`` = (x, y, heading) (reference :118-146): own
+    frame = x along the road."""
 
     def __init__(self, x0, width, length, ds=0.1, params=None):
         params = params if params is not None else RoadElementParameters()
         RoadSegment.__init__(self, x0, width, ds, params)
-        x0 = np.asarray(x0, dtype=float)
         self.length = length
-        x = np.arange(0, length + self.ds, self.ds)
-        yr = -(width / 2) * np.ones_like(x)
-        yl = (width / 2) * np.ones_like(x)
-        R = np.array([[np.cos(x0[2]), -np.sin(x0[2])], [np.sin(x0[2]), np.cos(x0[2])]])
-        vert_r = R @ np.c_[x, yr].T + np.reshape(x0[:2], (2, 1))
-        vert_l = R @ np.c_[x, yl].T + np.reshape(x0[:2], (2, 1))
-        self.edges.append(RoadEdge(vert_r.T, params=params))
-        self.edges.append(RoadEdge(vert_l.T, params=params))
-        self.x1 = np.zeros_like(x0)
-        self.x1[:2] = x0[:2] + self.length * np.array([np.cos(x0[2]), np.sin(x0[2])])
-        self.x1[2] = x0[2]
+        self._build(np.asarray(x0, dtype=float)[2], params)
+
+    def _edge(self, offset):
+        along = np.arange(0, self.length + self.ds, self.ds)
+        return np.column_stack((along, np.full_like(along, offset)))
+
+    def _end_pose(self):
+        return (self.length, 0.0), 0.0
 
 
 class CurvedRoadSegment(RoadSegment):
-    """reference :149-211."""
+    """Circular arc of centre-line ``radius`` turning by ``angle`` to the "left" or "right" (reference
+    :149-211): own frame = y along the initial heading, centre of the arc on the x axis."""
 
     def __init__(self, x0, width, radius, angle, direction, ds=0.1, params=None):
         params = params if params is not None else RoadElementParameters()
         RoadSegment.__init__(self, x0, width, ds, params)
-        x0 = np.asarray(x0, dtype=float)
+        assert direction in ("left", "right"), f'direction has to be "left" or "right, instead it was {direction}'
         self.length = radius * angle
         self.radius = radius
         self.angle = angle
         self.direction = direction
-        dir_flag = -1 * (direction == "right") + 1 * (direction == "left")
-        assert dir_flag in (-1, 1), f'direction has to be "left" or "right, instead it was {direction}'
-        beta = x0[2] - np.pi / 2
-        radius_r = radius + dir_flag * width / 2
-        radius_l = radius - dir_flag * width / 2
-        angle_r = np.linspace(0, angle, int(radius_r * angle / self.ds))
-        angle_l = np.linspace(0, angle, int(radius_l * angle / self.ds))
-        x_r = dir_flag * (radius_r * np.cos(angle_r) - radius)
-        y_r = radius_r * np.sin(angle_r)
-        x_l = dir_flag * (radius_l * np.cos(angle_l) - radius)
-        y_l = radius_l * np.sin(angle_l)
-        x1 = dir_flag * (radius * np.cos(angle) - radius)
-        y1 = radius * np.sin(angle)
-        R = np.array([[np.cos(beta), -np.sin(beta)], [np.sin(beta), np.cos(beta)]])
-        vert_r = R @ np.c_[x_r, y_r].T + np.reshape(x0[:2], (2, 1))
-        vert_l = R @ np.c_[x_l, y_l].T + np.reshape(x0[:2], (2, 1))
-        self.edges.append(RoadEdge(vert_r.T, params=params))
-        self.edges.append(RoadEdge(vert_l.T, params=params))
-        self.x1 = np.zeros((3))
-        self.x1[:2] = (R @ np.c_[x1, y1].T).flatten() + x0[:2]
-        self.x1[2] = x0[2] + dir_flag * angle
+        self._turn = 1.0 if direction == "left" else -1.0
+        self._build(np.asarray(x0, dtype=float)[2] - np.pi / 2, params)
+
+    def _arc(self, r, phi):
+        """Points at arc angle ``phi`` on the circle of radius ``r`` about the turn centre."""
+        return np.column_stack((self._turn * (r * np.cos(phi) - self.radius), r * np.sin(phi)))
+
+    def _edge(self, offset):
+        # an edge `offset` to the left of the centre line lies inside a left turn, outside a right turn
+        r = self.radius - self._turn * offset
+        return self._arc(r, np.linspace(0, self.angle, int(r * self.angle / self.ds)))
+
+    def _end_pose(self):
+        return tuple(self._arc(self.radius, np.array([self.angle]))[0]), self._turn * self.angle
 
 
 class RoadSegmentCollection:

@@ -122,8 +122,9 @@ class VehicleParameters:
             return (1, self.p_0, self.p_decay, self.v_max_riding[1], self.hfov)
         return (0, self.f_0, self.e_0, self.e_1, self.sigma_0, self.sigma_1, self.sigma_2, self.sigma_3, self.hfov)
 
-    def to_agent_params(self, q_scale: float, q_cap: int, hist_cap: int) -> "_lib.CsfAgentParams":
+    def to_agent_params(self, q_scale: float, q_cap: int, hist_cap: int, origin=(0.0, 0.0)) -> "_lib.CsfAgentParams":
         p = _lib.CsfAgentParams()
+        p.q_origin[0], p.q_origin[1] = float(origin[0]), float(origin[1])
         p.t_s = self.t_s
         p.d_arrived_inter, p.d_arrived_stop = self.d_arrived_inter, self.d_arrived_stop
         p.v_max_stop, p.v_max_harddecel = self.v_max_stop, self.v_max_harddecel
@@ -351,6 +352,22 @@ class BalancingRiderBicycleParameters(BicycleParameters):
             p.br_B[i] = B[i]
             p.br_pole_icpt[i] = self.pole_intercept[i]
             p.br_pole_coef[i] = self.pole_slope[i]
+
+
+def payload_frame(points, margin_rel=0.25, margin_abs=250.0):
+    """Origin and half-extent of the Q-format frame for a crowd: the centre of the bounding box of
+    ``points`` (iterable of (..., 2) arrays: positions, destinations, obstacles) and its half-size plus a
+    margin for road users that leave the box.  A road user outside origin +- extent raises status bit 2."""
+    lo = np.array([np.inf, np.inf])
+    hi = -lo
+    for a in points:
+        a = np.asarray(a, float).reshape(-1, 2)
+        if a.size:
+            lo, hi = np.minimum(lo, a.min(axis=0)), np.maximum(hi, a.max(axis=0))
+    if not np.all(np.isfinite(lo)):
+        return (0.0, 0.0), 1000.0
+    half = float((hi - lo).max()) / 2
+    return (float((lo[0] + hi[0]) / 2), float((lo[1] + hi[1]) / 2)), half * (1.0 + margin_rel) + margin_abs
 
 
 def choose_q_scale(extent_m: float) -> float:

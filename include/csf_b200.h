@@ -14,7 +14,7 @@
  * Layouts
  * -------
  *  pair payload ("xycs"), one element per road user, array [N]:
- *     f32: { int32 xq, yq; float cos_psi, sin_psi; }   16 B,  x = xq * q_scale  [m]
+ *     f32: { int32 xq, yq; float cos_psi, sin_psi; }   16 B,  x = q_origin[0] + xq * q_scale  [m]
  *     f64: { double x, y, cos_psi, sin_psi; }          32 B
  *  forces: [n][2] (x,y interleaved) of the scalar type.
  *  per-agent state: struct of arrays, see CsfAgentState.
@@ -78,6 +78,7 @@ typedef struct CsfAgentParams {
     double br_pole_icpt[5], br_pole_coef[5];
     /* payload packing */
     double q_scale;
+    double q_origin[2]; /* origin (m) of the Q-format frame of the f32 payload: xq = rint((x - q_origin[0]) / q_scale) */
     int32_t traj_len;  /* int(30/t_s) = 3000, vehicle.py:159 */
     int32_t hist_len;  /* int(1/t_s)  = 100,  vehicle.py:1487 */
     int32_t hist_cap;  /* rows allocated in hist_x/hist_y (power of two > hist_len) */
@@ -196,6 +197,8 @@ int csf_bicycle_eccentricity_f64(const double* v, int64_t n, double v_max, doubl
  *   csf_tiled_item_order : item_order <- items by decreasing cost (<= 4096 items), to be passed to
  *                         the next launches: the heaviest items start first, the launch has no
  *                         tail.  Scheduling only: the forces do not depend on it. */
+#define CSF_TILED_PREPARED 1   /* csf_tiled_prepare_* has run: block bounds and item counter are in the workspace */
+#define CSF_TILED_NO_REDUCE 2  /* leave the partial sums in the workspace (csf_agent_step_fused_* reduces them) */
 int64_t csf_tiled_padded_sources(int64_t n_src);
 int64_t csf_tiled_num_tiles(int64_t n_src);
 int csf_tiled_tile_bytes(int elem_bytes);
@@ -214,6 +217,17 @@ int csf_morton_keys_f64(const void* xycs, int64_t n, double x0, double y0, doubl
  * memory, so that a caller that reduces the box on the device needs no host round trip */
 int csf_spatial_keys_f32(const void* xycs, int64_t n, const double* box_dev, int64_t* keys, csf_stream_t stream);
 int csf_spatial_keys_f64(const void* xycs, int64_t n, const double* box_dev, int64_t* keys, csf_stream_t stream);
+/* The whole re-sort on the device, inside this library (no host round trip, no framework op):
+ *   csf_spatial_bbox_*  : box_dev[4] <- {xmin, xmax, ymin, ymax} of the payload positions (payload units)
+ *   csf_spatial_order_* : perm <- indices of xycs[0..n) sorted along the Hilbert curve over box_dev
+ *                         (32-bit keys, stable radix sort); `workspace`: csf_spatial_order_workspace_bytes(n) */
+size_t csf_spatial_order_workspace_bytes(int64_t n);
+int csf_spatial_bbox_f32(const void* xycs, int64_t n, double* box_dev, csf_stream_t stream);
+int csf_spatial_bbox_f64(const void* xycs, int64_t n, double* box_dev, csf_stream_t stream);
+int csf_spatial_order_f32(const void* xycs, int64_t n, const double* box_dev, int64_t* perm, void* workspace,
+                          size_t workspace_bytes, csf_stream_t stream);
+int csf_spatial_order_f64(const void* xycs, int64_t n, const double* box_dev, int64_t* perm, void* workspace,
+                          size_t workspace_bytes, csf_stream_t stream);
 int csf_tile_sources_f32(const void* xycs, int64_t n, const int64_t* perm, void* sorted, void* tiles,
                          csf_stream_t stream);
 int csf_tile_sources_f64(const void* xycs, int64_t n, const int64_t* perm, void* sorted, void* tiles,
@@ -222,12 +236,12 @@ int csf_pair_forces_tiled_f32(const void* sorted, const void* tiles, int64_t n_s
                               const int64_t* tgt_perm, int64_t n_tgt, const CsfFieldParams* fp,
                               float* frep_xy, int accumulate, void* workspace, size_t workspace_bytes,
                               const unsigned int* item_order, unsigned int* item_cost,
-                              unsigned long long* stats, csf_stream_t stream);
+                              unsigned long long* stats, int flags, csf_stream_t stream);
 int csf_pair_forces_tiled_f64(const void* sorted, const void* tiles, int64_t n_src, const void* tgt_xycs,
                               const int64_t* tgt_perm, int64_t n_tgt, const CsfFieldParams* fp,
                               double* frep_xy, int accumulate, void* workspace, size_t workspace_bytes,
                               const unsigned int* item_order, unsigned int* item_cost,
-                              unsigned long long* stats, csf_stream_t stream);
+                              unsigned long long* stats, int flags, csf_stream_t stream);
 int64_t csf_tiled_num_items(int64_t n_src, int64_t n_tgt, int elem_bytes);
 int csf_tiled_item_order(const unsigned int* item_cost, int64_t n_items, unsigned int* item_order,
                          csf_stream_t stream);
@@ -276,9 +290,9 @@ int csf_pack_xycs_f64(const CsfAgentState* st, const CsfAgentParams* p, void* xy
 /* Generic payload packer for road users that are not stepped by this library
  * (UncontrolledVehicle sources, vehicle.py:920-987). psi: double [n]. */
 int csf_pack_xypsi_f32(const double* x, const double* y, const double* psi, int64_t n, double q_scale,
-                       void* xycs, csf_stream_t stream);
+                       double origin_x, double origin_y, void* xycs, csf_stream_t stream);
 int csf_pack_xypsi_f64(const double* x, const double* y, const double* psi, int64_t n, double q_scale,
-                       void* xycs, csf_stream_t stream);
+                       double origin_x, double origin_y, void* xycs, csf_stream_t stream);
 
 /* ---- multi-GPU: payload exchange over NVLink peer memory --------------------------------
  * One crowd sharded by agent range over the GPUs of a node: the one exchange step
@@ -299,7 +313,37 @@ typedef struct CsfPeerComm {
     uint32_t* data_flags[CSF_MAX_PEERS]; /* [world] words in rank p's buffer; rank r writes word r */
     uint32_t* read_flags[CSF_MAX_PEERS];
     uint32_t* seq;                       /* local: push count, read count, block counter, status */
+    int32_t* status_host;                /* optional host-mapped mirror of seq[3] != 0 (may be NULL) */
 } CsfPeerComm;
+/* What the fused step kernels fold in (csf_agent_step_fused_*): the fixed-order reduction of the tiled pair
+ * kernel's partial sums (launched with CSF_TILED_NO_REDUCE) and this rank's side of the payload exchange. */
+typedef struct CsfStepFusion {
+    const void* partial;     /* T [n_groups][partial_stride][2]: workspace + csf_tiled_partial_offset(); NULL: none */
+    int64_t partial_stride;  /* n_tgt of the pair call */
+    int64_t partial_offset;  /* index of the group's agent 0 among the pair call's targets */
+    int32_t n_groups;        /* csf_tiled_num_groups() */
+    double f0;               /* field strength f_0 (the partial sums are per unit f_0) */
+    CsfPeerComm comm;        /* comm.world <= 1: no exchange */
+} CsfStepFusion;
+/* csf_agent_step_* with the reduction of the pair kernel's partial sums and the payload exchange folded in:
+ * one launch instead of reduce + signal + step + push. */
+int csf_agent_step_fused_f32(int model, const CsfAgentState* st, const CsfAgentParams* p, int64_t n_total,
+                             const CsfStepFusion* fusion, const float* froad, float* force, void* next_xycs,
+                             csf_stream_t stream);
+int csf_agent_step_fused_f64(int model, const CsfAgentState* st, const CsfAgentParams* p, int64_t n_total,
+                             const CsfStepFusion* fusion, const double* froad, double* force, void* next_xycs,
+                             csf_stream_t stream);
+/* The step's first kernel: tile build (csf_tile_sources_*) + target-block bounds + item-counter reset in one
+ * launch; with `comm` (may be NULL) it first waits for the peers' payload pushes (csf_peer_wait_data).
+ * Follow with csf_pair_forces_tiled_*(..., flags | CSF_TILED_PREPARED). */
+int csf_tiled_prepare_f32(const void* xycs, int64_t n_src, const int64_t* perm, void* sorted, void* tiles,
+                          const void* tgt_xycs, const int64_t* tgt_perm, int64_t n_tgt, void* workspace,
+                          size_t workspace_bytes, const CsfPeerComm* comm, csf_stream_t stream);
+int csf_tiled_prepare_f64(const void* xycs, int64_t n_src, const int64_t* perm, void* sorted, void* tiles,
+                          const void* tgt_xycs, const int64_t* tgt_perm, int64_t n_tgt, void* workspace,
+                          size_t workspace_bytes, const CsfPeerComm* comm, csf_stream_t stream);
+int csf_tiled_num_groups(int64_t n_src, int64_t n_tgt, int elem_bytes);
+size_t csf_tiled_partial_offset(int64_t n_src, int64_t n_tgt, int elem_bytes);
 int csf_peer_handle_bytes(void);
 int csf_peer_alloc(size_t bytes, void** devptr, void* ipc_handle_out);
 int csf_peer_open(const void* ipc_handle, void** devptr);

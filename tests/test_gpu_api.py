@@ -220,7 +220,7 @@ def test_f32_per_step_error(model):
     W = oracle_world(model, s0, np.full(n, 5.0), q)
     A = W.groups[0]
     e64, g64 = make_engine(model, s0, 5.0, q, dtype=torch.float64)
-    e32, g32 = make_engine(model, s0, 5.0, q, dtype=torch.float32, q_scale=e64.q_scale)
+    e32, g32 = make_engine(model, s0, 5.0, q, dtype=torch.float32, q_scale=e64.q_scale, origin=e64.q_origin)
     fields = [f for f in _STATE_COLS + tuple(_FIELD_AXIS) if f not in ("destq", "dest_len", "vd_default")
               and getattr(g64, f) is not None]
     fp = co.field_params_array([A.p])[0]
@@ -229,7 +229,7 @@ def test_f32_per_step_error(model):
     ang = [2] + [c for c in (4, 5) if c < ns]               # psi, delta, theta: absolute, rad
     lin = [c for c in lin if c not in ang]
     worst = dict(f32_force=0.0, f32_state=0.0, f64_force=0.0, f64_state=0.0)
-    exempt = 0
+    exempt = exempt_steer = 0
     for step in range(steps):
         for name in fields:
             getattr(g32, name).copy_(getattr(g64, name).to(getattr(g32, name).dtype))
@@ -242,8 +242,12 @@ def test_f32_per_step_error(model):
         f64, s64 = e64.force.cpu().numpy(), g64.states_numpy()
         f32, s32 = e32.force.cpu().numpy().astype(float), g32.states_numpy()
 
+        # the total force is a sum of two terms of magnitude |F_dest| that may cancel: its error is judged
+        # against the terms (|F_rep| <= |F_dest| after the clip, intersection.py:841-848), at least 1
+        fscale = np.maximum(np.maximum(np.linalg.norm(fo, axis=1), np.linalg.norm(A.fdest, axis=1)), 1.0)
+
         def errs(f, s):
-            ef = _vec_rel(f, fo, 1.0)
+            ef = np.linalg.norm(f - fo, axis=1) / fscale
             es = _rel(s[:, lin], so[:, lin], 1.0).max(axis=1)
             for c in ang:
                 es = np.maximum(es, np.abs(np.angle(np.exp(1j * (s[:, c] - so[:, c])))))
@@ -255,17 +259,22 @@ def test_f32_per_step_error(model):
         assert ef64.max() < 1e-8 and es64.max() < 1e-8, (model, step, ef64.max(), es64.max())
         ef, es = errs(f32, s32)
         ok = margin > 1e-5
+        state_tol = 1e-4 + ef * fscale / np.maximum(np.linalg.norm(fo, axis=1), 1e-300)
         exempt += int((~ok).sum())
+        exempt_steer += int((ok & (es > 1e-4)).sum())          # agent-steps that needed the |dF| / |F| term
         worst["f32_force"] = max(worst["f32_force"], ef[ok].max())
-        worst["f32_state"] = max(worst["f32_state"], es[ok].max())
-        bad = ok & ((ef > 1e-4) | (es > 1e-4))
-        assert not bad.any(), (model, step, np.flatnonzero(bad)[:8], ef[bad][:8], es[bad][:8], margin[bad][:8])
+        worst["f32_state"] = max(worst["f32_state"], (es / state_tol * 1e-4)[ok].max())
+        bad = ok & ((ef > 1e-4) | (es > state_tol))
+        assert not bad.any(), (model, step, np.flatnonzero(bad)[:8], ef[bad][:8], es[bad][:8], margin[bad][:8],
+                               np.linalg.norm(fo, axis=1)[bad][:8])
     e32.check_status()
     e64.check_status()
     report(test="f32_per_step_vs_oracle", model=model, n=n, steps=steps, agent_steps=n * steps,
-           exempt_fov_boundary=exempt, **{k: float(v) for k, v in worst.items()})
+           exempt_fov_boundary=exempt, state_over_1e4_by_cancelled_force=exempt_steer,
+           **{k: float(v) for k, v in worst.items()})
     # a source within 1e-5 rad of the boundary of a 2.09 rad cone: ~n * 2 * 1e-5 / (2 pi) per target and step
     assert exempt <= max(3, int(20 * n * steps * n * 2e-5 / (2 * np.pi)))
+    assert exempt_steer <= n * steps // 50
 
 
 def test_graph_step_equals_kernel_by_kernel_step():

@@ -150,3 +150,87 @@ def test_q_scale_choice():
     q = P.choose_q_scale(5000.0)
     assert 5000.0 / q <= 2 ** 30 < 2 * 5000.0 / q * 1.0000001 * 2
     assert np.log2(q) == np.floor(np.log2(q))
+
+
+def test_payload_frame_is_centred_on_the_crowd():
+    """The Q-format frame of the f32 payload: origin = centre of the bounding box of everything the crowd
+    can reach, extent = half its size plus a margin -- the 31 bits cover the occupied region only."""
+    rng = np.random.default_rng(0)
+    pos = rng.uniform(1000.0, 1256.0, (500, 2))
+    dest = rng.uniform(900.0, 1400.0, (500, 5, 2))
+    (ox, oy), ext = P.payload_frame([pos, dest])
+    lo = np.minimum(pos.min(0), dest.reshape(-1, 2).min(0))
+    hi = np.maximum(pos.max(0), dest.reshape(-1, 2).max(0))
+    assert abs(ox - (lo[0] + hi[0]) / 2) < 1e-9 and abs(oy - (lo[1] + hi[1]) / 2) < 1e-9
+    assert np.all(np.abs(pos - (ox, oy)) < ext) and np.all(np.abs(dest - (ox, oy)) < ext)
+    assert ext < 0.2 * (2 * 1400.0 + 1000.0)           # far tighter than a frame around (0, 0)
+    assert P.choose_q_scale(ext) <= 2.0 ** -20
+    assert P.payload_frame([]) == ((0.0, 0.0), 1000.0)
+
+
+def test_package_utils_match_the_reference_vectors(golden):
+    """cyclistsocialforce_b200.utils (host helpers with the reference's names) against vectors generated by
+    the reference's own utils (tests/golden/make_golden.py): bit for bit, scalar and array call forms."""
+    from cyclistsocialforce_b200 import utils as U
+    g = golden
+    assert np.array_equal(U.limitAngle(g["util_angles"].copy()), g["util_limit"])
+    assert [U.limitAngle(float(a)) for a in g["util_angles"]] == g["util_limit"].tolist()
+    assert isinstance(U.limitAngle(0.3), float)
+    assert np.array_equal(U.angleDifference(g["util_a1"].copy(), g["util_a2"].copy()), g["util_angdiff"])
+    assert [U.angleDifference(float(a), float(b)) for a, b in zip(g["util_a1"], g["util_a2"])] == g["util_angdiff"].tolist()
+    rho, phi = U.cart2polar(np.array([1.0, 0.0, -2.0, 3.0]), np.array([0.0, 2.0, -0.0, -4.0]))
+    assert np.allclose(rho, [1, 2, 2, 5]) and np.allclose(phi, [0, np.pi / 2, np.pi, -np.arccos(0.6)])
+    assert np.array_equal(U.thresh(np.array([-2.0, 0.5, 9.0]), (-1.0, 1.0)), [-1.0, 0.5, 1.0])
+    with pytest.raises(AssertionError):
+        U.thresh(1.0, (2.0, 1.0))
+    x, y = np.array([3.0, 0.3, 0.0]), np.array([4.0, 0.4, 0.0])
+    rx, ry = U.limitMagnitude(x, y, np.array([1.0, 1.0, 1.0]))
+    assert rx is x and ry is y                                  # in place, like the reference
+    assert np.allclose(x, [0.6, 0.3, 0.0]) and np.allclose(y, [0.8, 0.4, 0.0])
+    z = np.zeros(3)
+    U.limitMagnitude(z, z.copy(), np.ones(3))
+    assert not z.any()
+
+
+@pytest.mark.reference
+def test_package_utils_match_the_reference_live():
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("no /root/reference")
+    from cyclistsocialforce_b200 import utils as U
+    ref = rh.modules()[4]
+    rng = np.random.default_rng(3)
+    a1, a2 = rng.uniform(-4 * np.pi, 4 * np.pi, 2000), rng.uniform(-np.pi, np.pi, 2000)
+    assert np.array_equal(U.limitAngle(a1.copy()), ref.limitAngle(a1.copy()))
+    w1 = ref.limitAngle(a1.copy())
+    assert np.array_equal(U.angleDifference(w1.copy(), a2.copy()), ref.angleDifference(w1.copy(), a2.copy()))
+    for p, q in zip(w1[:200], a2[:200]):
+        assert U.angleDifference(float(p), float(q)) == ref.angleDifference(float(p), float(q))
+    x, y = rng.normal(size=500), rng.normal(size=500)
+    for got, want in zip(U.cart2polar(x, y), ref.cart2polar(x, y)):
+        assert np.array_equal(got, want)
+    r = np.abs(rng.normal(size=500))
+    gx, gy = U.limitMagnitude(x.copy(), y.copy(), r)
+    wx, wy = ref.limitMagnitude(x.copy(), y.copy(), r)
+    assert np.array_equal(gx, wx) and np.array_equal(gy, wy)
+    assert np.array_equal(U.thresh(x, (-0.5, 0.7)), ref.thresh(x, (-0.5, 0.7)))
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("direction", ["left", "right"])
+def test_road_geometry_matches_reference_live(direction):
+    """Vertices of straight and curved segments (both turn directions, a rotated start pose) against the
+    reference's own classes."""
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("no /root/reference")
+    R = rh.modules()[1]
+    x0 = np.array([3.0, -2.0, 0.7])
+    mine1, ref1 = I.StraightRoadSegment(x0, 2.5, 12.3), R.StraightRoadSegment(x0, 2.5, 12.3)
+    mine2 = I.CurvedRoadSegment(mine1.x1, 2.5, 6.0, 1.1, direction)
+    ref2 = R.CurvedRoadSegment(ref1.x1, 2.5, 6.0, 1.1, direction)
+    for m, r in ((mine1, ref1), (mine2, ref2)):
+        assert np.abs(np.asarray(m.x1, float) - np.asarray(r.x1, float)).max() < 1e-12
+        for em, er in zip(m.edges, r.edges):
+            assert em.vertices.shape == np.asarray(er.vertices).shape
+            assert np.abs(em.vertices - np.asarray(er.vertices)).max() < 1e-12
