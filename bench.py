@@ -30,7 +30,7 @@ N_AGENTS = int(os.environ.get("CSF_BENCH_N", 65536))
 FLOP_PER_PAIR = 76.0          # 68 FP32 flops + 8 special-function results, dense convention
 BYTES_PER_AGENT_STEP = 124.0  # TwoDBicycle per-agent kernel, fp32 SoA
 SEED = 1
-METRIC = "agent-steps/sec, N=65,536 TwoDBicycle"
+METRIC = f"agent-steps/sec, N={N_AGENTS:,} TwoDBicycle"
 WORKLOAD = f"{N_AGENTS}-cyclist TwoDBicycle open-plane crowd (SURVEY 8d recipe, seed {SEED}, 4 m spacing)"
 
 
@@ -125,11 +125,25 @@ def run(args, out):
         # torchrun pins OMP_NUM_THREADS=1 for its children: the CPU arm uses every host thread
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
         r = cpu_oracle_run(args.steps, args.warmup)
+        cfg = {"workload": WORKLOAD + f"; CPU arm: a bounded sample of it -- {r.get('sample_agents')} of the "
+                           f"{N_AGENTS} agents are stepped per CPU step, each against all {N_AGENTS} sources (the "
+                           "full per-agent cost); value = sampled agent-steps / wall time, ms_per_step = measured "
+                           "time of one sample step",
+               "n_agents": N_AGENTS, "sample_agents": r.get("sample_agents"),
+               "ms_per_full_step_extrapolated": r.get("ms_per_full_step_extrapolated"),
+               "implementation": "C/OpenMP restatement of the reference's TwoDBicycle stepping path (oracle/csf_oracle_c.c),"
+                                 " every host thread; the reference's own Python is O(N^4) and cannot run N > ~200"}
+        if os.environ.get("CSF_BENCH_NUMPY_ORACLE", "1") != "0":
+            from oracle import cpu_port
+            try:        # the restated numpy oracle on a FULL 4,096-cyclist crowd (config 3), one core
+                cfg["restated_numpy_oracle_full_crowd"] = cpu_port.timed_numpy_oracle_full(4096, SEED, steps=2, warmup=1)
+            except Exception as e:      # noqa: BLE001
+                cfg["restated_numpy_oracle_full_crowd"] = {"error": str(e)[:200]}
         line = {
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "agent-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "n_agents": N_AGENTS},
+            "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": r["value"], "unit": "agent-steps/s", "cores": r["cores"],
                              "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
@@ -243,6 +257,16 @@ def run(args, out):
         if os.environ.get("CSF_BENCH_ROLES"):      # cycle accounting of a -DCSF_TILED_PROF build (tools/k1_roles.py)
             st_ = eng.pair_stats.cpu().numpy().astype(float)
             if st_[1] > 0:
+                n_it = int(lib.csf_tiled_num_items(N_AGENTS, n_local, 4))
+                tr = eng.pair_stats.cpu().numpy()[16:16 + 4 * n_it].reshape(-1, 4).astype(np.int64)
+                np.save(os.path.join(ROOT, "gpurun_out", "k1_item_trace.npy"), tr)
+                t0_ = tr[:, 0][tr[:, 0] > 0].min()
+                dur = (tr[:, 2] - tr[:, 0]) / 1e3
+                print("item trace: kernel span %.1f us; item (claim -> retire) us: mean %.1f median %.1f max %.1f; claim->publish "
+                      "mean %.1f; last claim at %.1f us, last retire at %.1f us" % (
+                          (tr[:, 2].max() - t0_) / 1e3, dur.mean(), np.median(dur), dur.max(),
+                          ((tr[:, 1] - tr[:, 0]) / 1e3).mean(), (tr[:, 0].max() - t0_) / 1e3, (tr[:, 2].max() - t0_) / 1e3),
+                      file=sys.stderr, flush=True)
                 print("roles: evaluate waiting %.1f%%; filter waiting for a stage %.1f%%, for a free slot %.1f%%; producer "
                       "waiting %.1f%%; buffers %d stages %d units %d" % (100 * st_[2] / st_[1], 100 * st_[4] / st_[3],
                       100 * st_[5] / st_[3], 100 * st_[7] / st_[6], st_[8], st_[9], st_[10]), file=sys.stderr, flush=True)

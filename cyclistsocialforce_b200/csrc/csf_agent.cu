@@ -160,33 +160,26 @@ template <typename T> __device__ void dest_force_direct(Agent<T>& a, const CsfAg
 }
 
 // ----------------------------------------------------------------------------------------
-// interpolating parametric cubic B-spline through m in {4,5,6} points
+// interpolating parametric cubic B-spline through M in {4,5,6} points
 // (scipy.interpolate.splprep(s=0)/splev == FITPACK parcur/fppara/splev/splder)
+//
+// M is a template parameter: every loop below unrolls with static indices, the knot vector
+// 0,0,0,0, u_2 .. u_{M-3}, 1,1,1,1 keeps its constant entries as constants, and the collocation system
+// is solved for the M - 2 interior coefficients only (c_0 and c_{M-1} are the end points): everything
+// lives in registers.  The callers switch on the run-time number of points.
 // ----------------------------------------------------------------------------------------
-template <typename T> struct Spline {
-    int m;
-    T t4, t5;       // interior knots (u_2, u_3) where present
-    T cx[6], cy[6]; // B-spline coefficients
+template <typename T, int M> struct SplineM {
+    T kn[M + 4];      // knots
+    T cx[M], cy[M];   // B-spline coefficients
 };
-template <typename T> __device__ __forceinline__ T knot(const Spline<T>& s, int i) {
-    if (i <= 3) return (T)0;
-    if (i >= s.m) return (T)1;
-    return i == 4 ? s.t4 : s.t5;
-}
-template <typename T> __device__ __forceinline__ T pick6(const T* c, int idx) {
-    T r = c[0];
-#pragma unroll
-    for (int q = 1; q < 6; ++q) r = (idx == q) ? c[q] : r;
-    return r;
-}
-// Cox-de Boor on knot interval l: cubic N3[0..3] (B_{l-3..l}), quadratic N2[0..2], linear N1[0..1]
-template <typename T>
-__device__ void bspline_basis(const Spline<T>& s, T u, int l, T* N3, T* N2, T* N1) {
+// Cox-de Boor on the six knots K[0..5] = t_{l-2} .. t_{l+3} around interval l: cubic N3[0..3]
+// (B_{l-3..l}), quadratic N2[0..2], linear N1[0..1]
+template <typename T> __device__ __forceinline__ void basis_local(const T* K, T u, T* N3, T* N2, T* N1) {
     T left[4], right[4], N[4];
 #pragma unroll
     for (int j = 1; j <= 3; ++j) {
-        left[j] = u - knot(s, l + 1 - j);
-        right[j] = knot(s, l + j) - u;
+        left[j] = u - K[3 - j];
+        right[j] = K[2 + j] - u;
     }
     N[0] = (T)1;
 #pragma unroll
@@ -205,96 +198,102 @@ __device__ void bspline_basis(const Spline<T>& s, T u, int l, T* N3, T* N2, T* N
 #pragma unroll
     for (int j = 0; j < 4; ++j) N3[j] = N[j];
 }
-template <typename T> __device__ __forceinline__ int spline_interval(const Spline<T>& s, T u) {
-    int l = 3;  // FITPACK splev: advance while u >= t[l+1] and l != m-1
-    if (l != s.m - 1 && u >= knot(s, 4)) l = 4;
-    if (l == 4 && l != s.m - 1 && u >= knot(s, 5)) l = 5;
-    return l;
-}
 // Fit: px,py = control points (relative coordinates); returns false on duplicate points.
-template <typename T> __device__ bool spline_fit(Spline<T>& s, const T* px, const T* py, int m) {
-    s.m = m;
-    T u[6];
+template <typename T, int M> __device__ __forceinline__ bool spline_fit(SplineM<T, M>& s, const T* px, const T* py) {
+    T u[M];
     u[0] = (T)0;
     bool ok = true;
 #pragma unroll
-    for (int k = 1; k < 6; ++k) {
-        if (k < m) {
-            const T dx = px[k] - px[k - 1], dy = py[k] - py[k - 1];
-            const T d = sqrt(dx * dx + dy * dy);
-            ok = ok && (d > (T)0);
-            u[k] = u[k - 1] + d;
-        } else u[k] = u[k - 1];
+    for (int k = 1; k < M; ++k) {                      // chord-length parameters
+        const T dx = px[k] - px[k - 1], dy = py[k] - py[k - 1];
+        const T d = sqrt(dx * dx + dy * dy);
+        ok = ok && (d > (T)0);
+        u[k] = u[k - 1] + d;
     }
-    const T tot = pick6(u, m - 1);
+    const T tot = u[M - 1];
 #pragma unroll
-    for (int k = 1; k < 6; ++k) u[k] = (k < m - 1) ? u[k] / tot : (T)1;
-    s.t4 = u[2];
-    s.t5 = u[3];
+    for (int k = 1; k < M - 1; ++k) u[k] = u[k] / tot;
+    u[M - 1] = (T)1;
+#pragma unroll
+    for (int i = 0; i < M + 4; ++i) s.kn[i] = i < 4 ? (T)0 : (i >= M ? (T)1 : u[i - 2]);
     if (!ok) return false;
-    // collocation system, dense 6x6 (rows/cols >= m are identity)
-    T A[6][6], bx[6], by[6];
+    // collocation at u_1 .. u_{M-2}; u_i lies in knot interval l = min(i + 2, M - 1), where the basis
+    // functions B_{l-3} .. B_l are the non-zero ones; columns 0 and M - 1 go to the right-hand side
+    constexpr int NI = M - 2;
+    T A[NI][NI], bx[NI], by[NI];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 1; i <= NI; ++i) {
+        const int l = i + 2 < M - 1 ? i + 2 : M - 1;
+        T N3[4], N2[3], N1[2];
+        basis_local(&s.kn[l - 2], u[i], N3, N2, N1);
+        T rx = px[i], ry = py[i];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) A[i][j] = (i == j) ? (T)1 : (T)0;
-        bx[i] = (i < m) ? px[i] : (T)0;
-        by[i] = (i < m) ? py[i] : (T)0;
-    }
+        for (int j = 0; j < NI; ++j) A[i - 1][j] = (T)0;
 #pragma unroll
-    for (int i = 1; i < 5; ++i) {
-        if (i <= m - 2) {
-            const int l = min(i + 2, m - 1);
-            T N3[4], N2[3], N1[2];
-            bspline_basis(s, u[i], l, N3, N2, N1);
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                T v = (T)0;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) v = (j == l - 3 + r) ? N3[r] : v;
-                A[i][j] = v;
-            }
+        for (int r = 0; r < 4; ++r) {
+            const int col = l - 3 + r;
+            if (col == 0) { rx -= N3[r] * px[0]; ry -= N3[r] * py[0]; }
+            else if (col == M - 1) { rx -= N3[r] * px[M - 1]; ry -= N3[r] * py[M - 1]; }
+            else A[i - 1][col - 1] = N3[r];
         }
+        bx[i - 1] = rx;
+        by[i - 1] = ry;
     }
     // Gaussian elimination without pivoting (B-spline collocation matrices are totally positive)
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
+    for (int k = 0; k < NI; ++k) {
         const T inv = (T)1 / A[k][k];
 #pragma unroll
-        for (int i = k + 1; i < 6; ++i) {
+        for (int i = k + 1; i < NI; ++i) {
             const T f = A[i][k] * inv;
 #pragma unroll
-            for (int j = k + 1; j < 6; ++j) A[i][j] -= f * A[k][j];
+            for (int j = k + 1; j < NI; ++j) A[i][j] -= f * A[k][j];
             bx[i] -= f * bx[k];
             by[i] -= f * by[k];
         }
     }
+    s.cx[0] = px[0]; s.cy[0] = py[0];
+    s.cx[M - 1] = px[M - 1]; s.cy[M - 1] = py[M - 1];
 #pragma unroll
-    for (int k = 5; k >= 0; --k) {
+    for (int k = NI - 1; k >= 0; --k) {
         T sx = bx[k], sy = by[k];
 #pragma unroll
-        for (int j = k + 1; j < 6; ++j) {
-            sx -= A[k][j] * s.cx[j];
-            sy -= A[k][j] * s.cy[j];
+        for (int j = k + 1; j < NI; ++j) {
+            sx -= A[k][j] * s.cx[j + 1];
+            sy -= A[k][j] * s.cy[j + 1];
         }
         const T inv = (T)1 / A[k][k];
-        s.cx[k] = sx * inv;
-        s.cy[k] = sy * inv;
+        s.cx[k + 1] = sx * inv;
+        s.cy[k + 1] = sy * inv;
     }
     return true;
 }
-// S(u) and optionally S'(u), S''(u)
-template <typename T>
-__device__ void spline_eval(const Spline<T>& s, T u, bool der, T& x, T& y, T& dx, T& dy, T& ddx, T& ddy) {
-    const int l = spline_interval(s, u);
-    T N3[4], N2[3], N1[2];
-    bspline_basis(s, u, l, N3, N2, N1);
-    T cxl[4], cyl[4];
+// S(u) and optionally S'(u), S''(u).  The knot interval of u is a run-time value in [3, M - 1]: the six
+// knots and four coefficients around it are picked with selects over that (static) range.
+template <typename T, int M>
+__device__ __forceinline__ void spline_eval(const SplineM<T, M>& s, T u, bool der, T& x, T& y, T& dx, T& dy, T& ddx,
+                                            T& ddy) {
+    int l = 3;  // FITPACK splev: advance while u >= t[l+1] and l != M-1
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        cxl[r] = pick6(s.cx, l - 3 + r);
-        cyl[r] = pick6(s.cy, l - 3 + r);
+    for (int ll = 4; ll <= M - 1; ++ll)
+        if (l == ll - 1 && u >= s.kn[ll]) l = ll;
+    T K[6], cxl[4], cyl[4];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) K[j] = s.kn[1 + j];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { cxl[r] = s.cx[r]; cyl[r] = s.cy[r]; }
+#pragma unroll
+    for (int ll = 4; ll <= M - 1; ++ll) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) K[j] = (l == ll) ? s.kn[ll - 2 + j] : K[j];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            cxl[r] = (l == ll) ? s.cx[ll - 3 + r] : cxl[r];
+            cyl[r] = (l == ll) ? s.cy[ll - 3 + r] : cyl[r];
+        }
     }
+    T N3[4], N2[3], N1[2];
+    basis_local(K, u, N3, N2, N1);
     x = y = (T)0;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -305,15 +304,55 @@ __device__ void spline_eval(const Spline<T>& s, T u, bool der, T& x, T& y, T& dx
     T d1x[3], d1y[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        const T w = (T)3 / (knot(s, l + 1 + r) - knot(s, l - 2 + r));
+        const T w = (T)3 / (K[3 + r] - K[r]);
         d1x[r] = w * (cxl[r + 1] - cxl[r]);
         d1y[r] = w * (cyl[r + 1] - cyl[r]);
     }
     dx = N2[0] * d1x[0] + N2[1] * d1x[1] + N2[2] * d1x[2];
     dy = N2[0] * d1y[0] + N2[1] * d1y[1] + N2[2] * d1y[2];
-    const T w0 = (T)2 / (knot(s, l + 1) - knot(s, l - 1)), w1 = (T)2 / (knot(s, l + 2) - knot(s, l));
+    const T w0 = (T)2 / (K[3] - K[1]), w1 = (T)2 / (K[4] - K[2]);
     ddx = N1[0] * (w0 * (d1x[1] - d1x[0])) + N1[1] * (w1 * (d1x[2] - d1x[1]));
     ddy = N1[0] * (w0 * (d1y[1] - d1y[0])) + N1[1] * (w1 * (d1y[2] - d1y[1]));
+}
+
+// The spline part of TwoDBicycle.calcDestinationForce (vehicle.py:1496-1553) for M control points:
+// returns 0 = force set, 1 = duplicate points (FITPACK would raise), 2 = look-ahead sample beyond the curve
+template <typename T, int M>
+__device__ __forceinline__ int spline_force(const T* px, const T* py, int cur, bool last, bool stop, T vd, T g,
+                                            T& fx, T& fy) {
+    SplineM<T, M> sp;
+    if (!spline_fit<T, M>(sp, px, py)) return 1;
+    const T step = (T)1 / (T)19;
+    int i_s = 1;
+    if (last) {  // argmin over the 20 samples  :1516-1520
+        T best = (T)0;
+        for (int j = 0; j < 20; ++j) {
+            const T u = (j == 19) ? (T)1 : (T)j * step;
+            T x, y, t0, t1, t2, t3;
+            spline_eval<T, M>(sp, u, false, x, y, t0, t1, t2, t3);
+            const T ex = x - px[cur], ey = y - py[cur];
+            const T d2 = ex * ex + ey * ey;
+            if (j == 0 || d2 < best) { best = d2; i_s = j; }
+        }
+    }
+    const int i_p = i_s + (stop ? 5 : 3);  // :1523-1526
+    if (i_p >= 20) return 2;
+    const T us = (i_s == 19) ? (T)1 : (T)i_s * step;
+    const T up = (i_p == 19) ? (T)1 : (T)i_p * step;
+    T sx, sy, dx, dy, ddx, ddy;
+    spline_eval<T, M>(sp, us, true, sx, sy, dx, dy, ddx, ddy);
+    T qx, qy, t0, t1, t2, t3;
+    spline_eval<T, M>(sp, up, false, qx, qy, t0, t1, t2, t3);
+    const T sp1 = sqrt(dx * dx + dy * dy);
+    const T R = sp1 * sp1 * sp1 / fabs(dx * ddy - dy * ddx);  // :1532-1537
+    const T thetacomf = (T)(10.0 * (CSF_TWO_PI / 360.0));
+    T v = fmax((T)2.5, sqrt(thetacomf * g * R));
+    v = fmin(v, vd);
+    const T ex = qx - sx, ey = qy - sy;
+    const T temp = v / sqrt(ex * ex + ey * ey);
+    fx = temp * ex;
+    fy = temp * ey;
+    return 0;
 }
 
 // TwoDBicycle.calcDestinationForce, vehicle.py:1443-1558
@@ -366,44 +405,13 @@ __device__ void dest_force_twod(Agent<T>& a, const CsfAgentParams& p, const CsfA
         m = 4;
         cur = 2;
     }
-    Spline<T> sp;
-    if (!spline_fit(sp, px, py, m)) {
-        a.flags |= 8;  // reference: FITPACK ValueError (duplicate points); here: direct approach
-        dest_force_direct(a, p, fx, fy);
-        return;
-    }
-    const T step = (T)1 / (T)19;
-    int i_s = 1;
-    T sx, sy, dx, dy, ddx, ddy;
-    if (last) {  // argmin over the 20 samples  :1516-1520
-        T best = (T)0;
-        for (int j = 0; j < 20; ++j) {
-            const T u = (j == 19) ? (T)1 : (T)j * step;
-            T x, y, t0, t1, t2, t3;
-            spline_eval(sp, u, false, x, y, t0, t1, t2, t3);
-            const T ex = x - px[cur], ey = y - py[cur];
-            const T d2 = ex * ex + ey * ey;
-            if (j == 0 || d2 < best) { best = d2; i_s = j; }
-        }
-    }
-    const int i_p = i_s + (stop ? 5 : 3);  // :1523-1526
-    if (i_p < 20) {
-        const T us = (i_s == 19) ? (T)1 : (T)i_s * step;
-        const T up = (i_p == 19) ? (T)1 : (T)i_p * step;
-        spline_eval(sp, us, true, sx, sy, dx, dy, ddx, ddy);
-        T qx, qy, t0, t1, t2, t3;
-        spline_eval(sp, up, false, qx, qy, t0, t1, t2, t3);
-        const T sp1 = sqrt(dx * dx + dy * dy);
-        const T R = sp1 * sp1 * sp1 / fabs(dx * ddy - dy * ddx);  // :1532-1537
-        const T thetacomf = (T)(10.0 * (CSF_TWO_PI / 360.0));
-        T v = fmax((T)2.5, sqrt(thetacomf * (T)p.g * R));
-        v = fmin(v, vd);
-        const T ex = qx - sx, ey = qy - sy;
-        const T temp = v / sqrt(ex * ex + ey * ey);
-        fx = temp * ex;
-        fy = temp * ey;
-    } else {
-        dest_force_direct(a, p, fx, fy);  // :1556
+    int rc;
+    if (m == 6) rc = spline_force<T, 6>(px, py, cur, last, stop, vd, (T)p.g, fx, fy);
+    else if (m == 5) rc = spline_force<T, 5>(px, py, cur, last, stop, vd, (T)p.g, fx, fy);
+    else rc = spline_force<T, 4>(px, py, cur, last, stop, vd, (T)p.g, fx, fy);
+    if (rc != 0) {
+        if (rc == 1) a.flags |= 8;  // reference: FITPACK ValueError (duplicate points); here: direct approach
+        dest_force_direct(a, p, fx, fy);  // (rc == 2: vehicle.py:1556)
     }
 }
 

@@ -38,31 +38,40 @@
 
 namespace {
 
-#ifndef CSF_TILED_FILTER_WARPS
-#define CSF_TILED_FILTER_WARPS 2
-#endif
-constexpr int kFW = CSF_TILED_FILTER_WARPS;   // filter warps per CTA
-#ifndef CSF_TILED_EVAL_WARPS
-#define CSF_TILED_EVAL_WARPS 6
-#endif
-constexpr int kEW = CSF_TILED_EVAL_WARPS;   // evaluate warps per CTA
+// Two shapes of CTA, same code (template parameters FW / EW = filter / evaluate warps):
+//   narrow  1 + 2 + 6 warps, three CTAs per SM  -- many items per CTA slot: the CTAs of an SM fill each
+//                                                  other's gaps at item boundaries;
+//   wide    1 + 4 + 22 warps, one CTA per SM    -- few items (a small crowd, a rank's shard of a crowd): a
+//                                                  CTA that has an SM to itself puts all of the SM's
+//                                                  evaluate warps on ONE item, whose latency is what
+//                                                  bounds such a launch.
 #ifndef CSF_TILED_MINB
 #define CSF_TILED_MINB 3
 #endif
-constexpr int kTThreads = (1 + kFW + kEW) * 32;
+constexpr int kNarrowFW = 2, kNarrowEW = 6, kWideFW = 4, kWideEW = 22;
 constexpr int kBT = 64;                  // targets per block
 constexpr int kTileS = 64;               // sources per tile (2 per lane)
 constexpr int kCT = 16;                  // tiles per chunk of the sorted copy = dynamic tiles per survivor buffer
 constexpr int kCS = kCT * kTileS;        // sources per chunk / survivor buffer
 constexpr int kST = 8;                   // tiles per shared-memory stage
 constexpr int kTMaxGroups = 64;
+#ifndef CSF_TILED_ITEMS_IN_FLIGHT
+#define CSF_TILED_ITEMS_IN_FLIGHT 2
+#endif
+constexpr int kItemsInFlight = CSF_TILED_ITEMS_IN_FLIGHT;   // items a CTA may hold (claimed, not yet evaluated)
 template <typename T> struct Stages { static constexpr int n = 4; };
-static_assert(kST % kFW == 0 && kBT % (kFW * 32) == 0, "filter warps split stages and target blocks evenly");
+static_assert(kST % kNarrowFW == 0 && kST % kWideFW == 0, "filter warps split stages evenly");
 // Capacity of the k-th survivor buffer of an item (slow start): the evaluate warps get their first
 // buffer of a new item after 256 survivors instead of 1024 -- the bubble at every item boundary is a
 // quarter as long -- and steady-state buffers are large, so that the fixed cost per (target, buffer)
 // stays small.  A fixed function of k: the order of every sum stays fixed.
-__device__ __forceinline__ int buffer_cap(int k) { return k == 0 ? 4 * kTileS : (k == 1 ? 8 * kTileS : kCS); }
+#ifndef CSF_TILED_SLOW_START
+#define CSF_TILED_SLOW_START 1
+#endif
+__device__ __forceinline__ int buffer_cap(int k) {
+    if (!CSF_TILED_SLOW_START) return kCS;
+    return k == 0 ? 4 * kTileS : (k == 1 ? 8 * kTileS : kCS);
+}
 
 template <typename T> struct Tile;
 template <> struct __align__(16) Tile<float> { int32_t cx, cy; float R; int32_t cnt; };
@@ -464,8 +473,8 @@ __device__ __forceinline__ void lobe_reaches2(const Tile<double>& blk, const Src
 }
 
 // named barrier 1 among the filter warps only
-__device__ __forceinline__ void filter_barrier() {
-    if (kFW > 1) asm volatile("bar.sync 1, %0;" ::"n"(kFW * 32) : "memory");
+template <int FW> __device__ __forceinline__ void filter_barrier() {
+    if (FW > 1) asm volatile("bar.sync 1, %0;" ::"n"(FW * 32) : "memory");
     else __syncwarp();
 }
 
@@ -482,6 +491,11 @@ enum { BUF_LAST = 1, BUF_EXIT = 2 };
 #ifndef CSF_TILED_PRODUCER_HINT_NS
 #define CSF_TILED_PRODUCER_HINT_NS 4000u
 #endif
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 #ifdef CSF_TILED_PROF
 #define PROF_T0(v) const long long v = clock64()
 #define PROF_ADD(acc, v) acc += clock64() - v
@@ -493,18 +507,18 @@ enum { BUF_LAST = 1, BUF_EXIT = 2 };
 #endif
 
 // ---- the tiled pair kernel ---------------------------------------------------------------------------
-// item -> (target block tb = item % n_tblocks, chunk group cg = item / n_tblocks); a group is
-// `group_chunks` consecutive chunks.  partial[cg][target][2].
+// item -> (target block tb = item % n_tblocks, part cg = item / n_tblocks of the block's near chunks);
+// partial[cg][target][2].
 // Stage protocol (producer -> filter warps): hdr[stage] = {item, n}: n = 1..kST tiles of the sorted copy
 // with their circle records; n == -1 closes the item, n == -2 ends the kernel.
 // Buffer protocol (filter -> evaluate warps): bdesc[slot] = {item, dynamic tiles, flags, target set}:
 // BUF_LAST = last buffer of the item (the evaluate warps write their sums), BUF_EXIT = leave.
-template <typename T, bool P2R>
-__global__ void __launch_bounds__(kTThreads, sizeof(T) == 4 ? CSF_TILED_MINB : 1)
+template <typename T, bool P2R, int FW, int EW>
+__global__ void __launch_bounds__((1 + FW + EW) * 32, (sizeof(T) == 4 && EW == kNarrowEW) ? CSF_TILED_MINB : 1)
 pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __restrict__ tiles, int64_t n_tiles,
                   const Xycs<T>* __restrict__ tgt, const int64_t* __restrict__ tgt_perm, int64_t n_tgt,
                   const Tile<T>* __restrict__ tblocks, PairConst<T> k, CullConst<T> cc, T* __restrict__ partial,
-                  int group_chunks, int n_groups, int n_tblocks, unsigned int* __restrict__ counter,
+                  int n_groups, int n_tblocks, unsigned int* __restrict__ counter,
                   const unsigned int* __restrict__ item_order, unsigned int* __restrict__ item_cost,
                   unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -526,21 +540,23 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
     T* lobe = reinterpret_cast<T*>(fmask + kStages * kST);                          // [kLobeBins] reach table
     T* bacc = lobe + kLobeBins;                                                     // [2 items][2 buffer parities][kBT][2] sums
     int* nextq = reinterpret_cast<int*>(bacc + 2 * 2 * kBT * 2);                    // [2] next target of the buffer in the slot
+    int* last_seen = nextq + 2;                                                     // evaluate warps that have left an item's last buffer, summed over items
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kFW);
+            mbar_init(&empty[s], FW);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&ready[s], 1);
-            mbar_init(&freeb[s], kEW);
+            mbar_init(&freeb[s], EW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < kLobeBins; i += blockDim.x) lobe[i] = cc.lobe[i];
     for (int i = threadIdx.x; i < 2 * 2 * kBT * 2; i += blockDim.x) bacc[i] = (T)0;
+    if (threadIdx.x == 0) *last_seen = 0;
     __syncthreads();
 
     const unsigned int n_items = (unsigned int)n_tblocks * (unsigned int)n_groups;
@@ -569,23 +585,54 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
             __syncwarp();
             PROF_ADD(pr_wait, w0);
         };
+        int fetched = 0;                                // items this CTA has claimed
         for (;;) {
+            // An item is claimed only when the last item but one has been evaluated completely: one item with
+            // the evaluate warps, one with the filter warps.  Without the limit the producer -- up to kStages
+            // stages ahead -- hoards the small items of a small crowd or shard while other CTAs run dry.
+            if (lane == 0 && fetched >= kItemsInFlight) {
+                const int want = EW * (fetched - kItemsInFlight + 1);
+                while (*reinterpret_cast<volatile int*>(last_seen) < want) __nanosleep(200);
+            }
+            __syncwarp();
             unsigned int item = 0;
             if (lane == 0) item = atomicAdd(counter, 1u);
             item = __shfl_sync(0xffffffffu, item, 0);
             if (item >= n_items) break;
+            ++fetched;
             if (item_order) item = item_order[item];        // heaviest items first (previous step's costs)
+#ifdef CSF_TILED_PROF
+            if (stats && lane == 0) { stats[16 + 4 * item] = globaltimer_ns(); stats[16 + 4 * item + 3] = blockIdx.x; }
+#endif
             const int tb = (int)(item % (unsigned int)n_tblocks), cg = (int)(item / (unsigned int)n_tblocks);
             const Tile<T> tbr = tblocks[tb];
-            const int64_t c_begin = (int64_t)cg * group_chunks, c_end = min(n_chunks, c_begin + group_chunks);
-            for (int64_t c0 = c_begin; c0 < c_end; c0 += 32) {
+            // The chunks that can be within d_cut of the block, in order, are dealt out evenly to the block's
+            // n_groups items: item cg streams entries [lo, hi) of that list.  (Splitting the chunk INDEX
+            // range instead would give one item nearly all of the work: the near chunks of a block are
+            // neighbours on the Hilbert curve.)
+            int lo = 0, hi = 0x7fffffff;
+            if (n_groups > 1) {
+                int n_near = 0;
+                for (int64_t c0 = 0; c0 < n_chunks; c0 += 32) {
+                    const int64_t c = c0 + lane;
+                    const bool near = c < n_chunks && circles_near(chunks[c], tbr, cc.dmax);
+                    n_near += __popc(__ballot_sync(0xffffffffu, near));
+                }
+                lo = (int)(((long long)n_near * cg) / n_groups);
+                hi = (int)(((long long)n_near * (cg + 1)) / n_groups);
+            }
+            int seen = 0;                               // near chunks passed so far
+            for (int64_t c0 = 0; c0 < n_chunks && seen < hi; c0 += 32) {
                 const int64_t c = c0 + lane;
                 bool near = false;
-                if (c < c_end) near = circles_near(chunks[c], tbr, cc.dmax);
+                if (c < n_chunks) near = circles_near(chunks[c], tbr, cc.dmax);
                 uint32_t m = __ballot_sync(0xffffffffu, near);
                 while (m) {
                     const int64_t ch = c0 + (__ffs(m) - 1);
                     m &= m - 1;
+                    const int ord = seen++;
+                    if (ord < lo) continue;
+                    if (ord >= hi) break;
                     const int64_t t0 = ch * kCT;
                     Tile<T> rec;
                     bool tn = false;
@@ -633,7 +680,7 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
 
     typedef decltype(SrcA<T>().x0) P;    // payload position type
 
-    if (warp <= kFW) {
+    if (warp <= FW) {
         // ===== filter warps =====
         // Per stage: (1) every source of the staged tiles is tested against the target block's circle
         // with the lobe test (lobe_reaches2): most sources near the block cannot matter for any of its
@@ -674,7 +721,7 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
             if (p_item >= 0) {
                 const int tb = p_item % n_tblocks, cg = p_item / n_tblocks;
                 T* a0 = bacc + (size_t)p_par * 2 * kBT * 2;
-                for (int q = ftid; q < kBT; q += kFW * 32) {
+                for (int q = ftid; q < kBT; q += FW * 32) {
                     const long long jj = bj[p_par * kBT + q];
                     const T sx = a0[q * 2] + a0[kBT * 2 + q * 2], sy = a0[q * 2 + 1] + a0[kBT * 2 + q * 2 + 1];
                     a0[q * 2] = a0[q * 2 + 1] = a0[kBT * 2 + q * 2] = a0[kBT * 2 + q * 2 + 1] = (T)0;
@@ -683,6 +730,9 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                         partial[((size_t)cg * n_tgt + (size_t)jj) * 2 + 1] = sy;
                     }
                 }
+#ifdef CSF_TILED_PROF
+                if (stats && ftid == 0) stats[16 + 4 * p_item + 2] = globaltimer_ns();
+#endif
                 if (slot) pend_item1 = -1; else pend_item0 = -1;
             }
         };
@@ -699,10 +749,10 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
             {   // pad the last dynamic tile with far-away sentinels (they contribute exactly 0)
                 Xycs<T> pad;
                 pad_entry(pad);
-                for (int kidx = count + ftid; kidx < n_dt * kTileS; kidx += kFW * 32)
+                for (int kidx = count + ftid; kidx < n_dt * kTileS; kidx += FW * 32)
                     write_entry(sb, kidx, pos_x(pad), pos_y(pad), pad.c, pad.s);
             }
-            for (int t = fw; t < n_dt; t += kFW) {            // circles of the dynamic tiles
+            for (int t = fw; t < n_dt; t += FW) {            // circles of the dynamic tiles
                 const int valid = min(kTileS, count - t * kTileS);
                 const SrcA<T> A = reinterpret_cast<const SrcA<T>*>(sb + (size_t)t * kTileB)[lane];
                 BBox<T> bb;
@@ -711,7 +761,7 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                 bb.warp_reduce();
                 if (lane == 0) dtile[slot * kCT + t] = bb.circle(valid);
             }
-            filter_barrier();
+            filter_barrier<FW>();
             if (ftid == 0) {
                 bdesc[slot] = make_int4(cur, n_dt, flags, par | ((kbuf & 1) << 1));
                 nextq[slot] = 0;
@@ -749,7 +799,7 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                 par = (int)(n_open++ & 1u);
                 const int tb = cur % n_tblocks;
                 blk = tblocks[tb];
-                for (int q = ftid; q < kBT; q += kFW * 32) {
+                for (int q = ftid; q < kBT; q += FW * 32) {
                     const int64_t t = (int64_t)tb * kBT + q;
                     long long myj = -1;
                     Xycs<T> e;
@@ -764,18 +814,21 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
             }
             if (n == -1) {
                 if (!have_slot) acquire();
-                filter_barrier();                             // targets / last appends have landed
+                filter_barrier<FW>();                             // targets / last appends have landed
                 publish(BUF_LAST);
                 if (item_cost && ftid == 0) item_cost[cur] = (unsigned int)surv;
+#ifdef CSF_TILED_PROF
+                if (stats && ftid == 0) stats[16 + 4 * cur + 1] = globaltimer_ns();
+#endif
             } else {
                 const unsigned char* base = stage_src + (size_t)stage * kST * kTileB;
                 uint2* fm = fmask + stage * kST;
                 // (1) filter this warp's tiles of the stage
-                constexpr int kTPW = kST / kFW;
+                constexpr int kTPW = kST / FW;
                 uint32_t mb0[kTPW], mb1[kTPW];
 #pragma unroll
                 for (int u = 0; u < kTPW; ++u) {
-                    const int t = fw + u * kFW;
+                    const int t = fw + u * FW;
                     mb0[u] = mb1[u] = 0;
                     if (t < n) {                              // warp-uniform
                         const int valid = (int)srec[stage * kST + t].cnt;
@@ -785,13 +838,13 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                         lobe_reaches2(blk, A, B, lobe, k.tiny, p0, p1);
                         mb0[u] = __ballot_sync(0xffffffffu, p0 && (lane < valid));
                         mb1[u] = __ballot_sync(0xffffffffu, p1 && (lane + 32 < valid));
-                        if (kFW > 1 && lane == 0) fm[t] = make_uint2(mb0[u], mb1[u]);
+                        if (FW > 1 && lane == 0) fm[t] = make_uint2(mb0[u], mb1[u]);
                     }
                 }
                 // (2) append in stream order: prefix over the stage's tiles (every filter warp computes it)
                 uint2 mm = make_uint2(0u, 0u);
-                if (kFW > 1) {
-                    filter_barrier();
+                if (FW > 1) {
+                    filter_barrier<FW>();
                     if (lane < n) mm = fm[lane];
                 } else {
 #pragma unroll
@@ -812,7 +865,7 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                 const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
                 for (int u = 0; u < kTPW; ++u) {
-                    const int t = fw + u * kFW;
+                    const int t = fw + u * FW;
                     if (t < n && (mb0[u] | mb1[u])) {
                         const int off = count + __shfl_sync(0xffffffffu, incl - c8, t);
                         const SrcA<T> A = reinterpret_cast<const SrcA<T>*>(base + (size_t)t * kTileB)[lane];
@@ -825,7 +878,7 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                 }
                 count += tot;
                 surv += tot;
-                filter_barrier();                             // the appends have landed, the stage has been read
+                filter_barrier<FW>();                             // the appends have landed, the stage has been read
                 if (count >= buffer_cap(kbuf)) publish(0);
             }
             if (lane == 0) mbar_arrive(&empty[stage]);
@@ -937,7 +990,10 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&freeb[slot]);
+        if (lane == 0) {
+            mbar_arrive(&freeb[slot]);
+            if (d.z & BUF_LAST) atomicAdd(last_seen, 1);
+        }
     }
     if (stats && n_eval && lane == 0) atomicAdd(stats, n_eval);
 #ifdef CSF_TILED_PROF
@@ -996,43 +1052,48 @@ template <typename T> size_t tiled_smem_bytes() {
            (size_t)(kStages * kST + 2 * kCT) * sizeof(Tile<T>) + (size_t)2 * kBT * sizeof(Xycs<T>) +
            (size_t)2 * kBT * sizeof(long long) + (size_t)(2 * kStages + 4) * sizeof(uint64_t) +
            (size_t)(kStages + 2) * sizeof(int4) + (size_t)kStages * kST * sizeof(uint2) +
-           (size_t)kLobeBins * sizeof(T) + (size_t)2 * 2 * kBT * 2 * sizeof(T) + 4 * sizeof(int);
+           (size_t)kLobeBins * sizeof(T) + (size_t)2 * 2 * kBT * 2 * sizeof(T) + 8 * sizeof(int);
 }
 
 // Resident CTAs per SM of the tiled kernel and the SM count, per device (the shared-memory attribute
 // is a per-device property of the function too).
 constexpr int kMaxDevices = 64;
-int g_tiled_ctas[2][kMaxDevices];
+int g_tiled_ctas[2][2][kMaxDevices];      // [f32 / f64][narrow / wide][device]
 int g_tiled_sms[kMaxDevices];
-template <typename T> int tiled_ctas(int* sm_count) {
+template <typename T, int FW, int EW> int tiled_shape_ctas() {
+    int best = 1 << 30;
+    const size_t smem = tiled_smem_bytes<T>();
+    {
+        auto kern = pair_tiled_kernel<T, false, FW, EW>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, (1 + FW + EW) * 32, smem);
+        best = nb < best ? nb : best;
+    }
+    {
+        auto kern = pair_tiled_kernel<T, true, FW, EW>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, (1 + FW + EW) * 32, smem);
+        best = nb < best ? nb : best;
+    }
+    return best < 1 ? 1 : best;
+}
+// resident CTAs per SM of the narrow (wide = false) or wide CTA shape on the current device
+template <typename T> int tiled_ctas(bool wide, int* sm_count) {
     const int idx = sizeof(T) == 4 ? 0 : 1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= kMaxDevices) dev = 0;
-    if (g_tiled_ctas[idx][dev] == 0) {
-        int best = 1 << 30;
-        const size_t smem = tiled_smem_bytes<T>();
-        {
-            auto kern = pair_tiled_kernel<T, false>;
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            int nb = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kTThreads, smem);
-            best = nb < best ? nb : best;
-        }
-        {
-            auto kern = pair_tiled_kernel<T, true>;
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            int nb = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kTThreads, smem);
-            best = nb < best ? nb : best;
-        }
+    if (g_tiled_ctas[idx][0][dev] == 0) {
+        g_tiled_ctas[idx][0][dev] = tiled_shape_ctas<T, kNarrowFW, kNarrowEW>();
+        g_tiled_ctas[idx][1][dev] = tiled_shape_ctas<T, kWideFW, kWideEW>();
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         g_tiled_sms[dev] = sms > 0 ? sms : 148;
-        g_tiled_ctas[idx][dev] = best < 1 ? 1 : best;
     }
     if (sm_count) *sm_count = g_tiled_sms[dev];
-    return g_tiled_ctas[idx][dev];
+    return g_tiled_ctas[idx][wide ? 1 : 0][dev];
 }
 
 int env_int(const char* name, int dflt) {
@@ -1041,33 +1102,36 @@ int env_int(const char* name, int dflt) {
 }
 
 // Work decomposition: target blocks of kBT targets; if there are too few blocks to keep every CTA slot
-// busy with several items, the chunk range of each block is split in groups.
-struct TiledPlan { int n_tblocks, n_groups, group_chunks, grid; int64_t n_tiles, n_chunks; };
+// busy, the list of chunks near a block is dealt out to several items, and below a few blocks per SM the
+// wide CTA shape is used (see the top of the file).
+struct TiledPlan { int n_tblocks, n_groups, grid; bool wide; int64_t n_tiles, n_chunks; };
 template <typename T> TiledPlan tiled_plan(int64_t n_src, int64_t n_tgt) {
-    static const int env_groups = env_int("CSF_TILED_GROUPS", 0), env_ipw = env_int("CSF_TILED_ITEMS_PER_SLOT", 4);
+    static const int env_groups = env_int("CSF_TILED_GROUPS", 0), env_ipw = env_int("CSF_TILED_ITEMS_PER_SLOT", 4),
+                     env_max = env_int("CSF_TILED_MAX_GROUPS", 16), env_wide = env_int("CSF_TILED_WIDE", -1),
+                     env_wide_below = env_int("CSF_TILED_WIDE_BELOW", 3);
     TiledPlan p;
     p.n_tiles = (n_src + kTileS - 1) / kTileS;
     p.n_chunks = (p.n_tiles + kCT - 1) / kCT;
-    int sms = 0;
-    const int64_t slots = (int64_t)tiled_ctas<T>(&sms) * sms;
-    const int64_t want = (int64_t)env_ipw * slots;
-    // 64 targets per block balance the lobe filter's cost (per block) against its selectivity (block
-    // radius).  Items must be plentiful -- a few per CTA slot -- because their cost follows the local
-    // density of the crowd (a jammed cluster costs several times the mean) and an item is the unit of
-    // dynamic scheduling: when there are too few blocks, the chunk range of each block is split over
-    // several items (each chunk is still filtered once per block).
     const int64_t tb = (n_tgt + kBT - 1) / kBT;
+    int sms = 0;
+    tiled_ctas<T>(false, &sms);
+    // fewer than env_wide_below target blocks per SM: item latency, not throughput, bounds the launch
+    p.wide = sizeof(T) == 4 && (env_wide >= 0 ? env_wide != 0 : tb < (int64_t)env_wide_below * sms);
+    const int64_t slots = (int64_t)tiled_ctas<T>(p.wide, &sms) * sms;
+    // 64 targets per block balance the lobe filter's cost (per block) against its selectivity (block
+    // radius).  Narrow shape: items must be plentiful -- a few per CTA slot -- because their cost follows
+    // the local density of the crowd and an item is the unit of dynamic scheduling.  Wide shape: one item
+    // per SM at a time; the chunks near a block are dealt out to several items only when there are fewer
+    // blocks than SMs.  (Each chunk is still filtered once per block either way.)
+    const int64_t want = p.wide ? slots : (int64_t)env_ipw * slots;
     int64_t groups = (want + tb - 1) / tb;
-    if (groups > 8) groups = 8;
+    if (groups > env_max) groups = env_max;
     if (env_groups >= 1) groups = env_groups;
     if (groups < 1) groups = 1;
     if (groups > kTMaxGroups) groups = kTMaxGroups;
     if (groups > p.n_chunks) groups = p.n_chunks;
-    const int64_t gc = (p.n_chunks + groups - 1) / groups;
-    groups = (p.n_chunks + gc - 1) / gc;
     p.n_tblocks = (int)tb;
     p.n_groups = (int)groups;
-    p.group_chunks = (int)gc;
     const int64_t items = tb * groups;
     p.grid = (int)(items < slots ? items : slots);
     return p;
@@ -1228,14 +1292,18 @@ int pair_tiled(const void* sorted, const void* tiles, int64_t n_src, const void*
             (const Xycs<T>*)tgt, tgt_perm, n_tgt, kBT, tblocks, pl.n_tblocks, counter);
         CSF_CHECK_LAUNCH("block_bounds_kernel");
     }
-    if (fp->p2r)
-        pair_tiled_kernel<T, true><<<pl.grid, kTThreads, smem, st>>>(
-            (const unsigned char*)sorted, (const Tile<T>*)tiles, pl.n_tiles, (const Xycs<T>*)tgt, tgt_perm, n_tgt,
-            tblocks, k, cc, partial, pl.group_chunks, pl.n_groups, pl.n_tblocks, counter, item_order, item_cost, stats);
-    else
-        pair_tiled_kernel<T, false><<<pl.grid, kTThreads, smem, st>>>(
-            (const unsigned char*)sorted, (const Tile<T>*)tiles, pl.n_tiles, (const Xycs<T>*)tgt, tgt_perm, n_tgt,
-            tblocks, k, cc, partial, pl.group_chunks, pl.n_groups, pl.n_tblocks, counter, item_order, item_cost, stats);
+#define CSF_TILED_LAUNCH(P2R_, FW_, EW_)                                                                             \
+    pair_tiled_kernel<T, P2R_, FW_, EW_><<<pl.grid, (1 + FW_ + EW_) * 32, smem, st>>>(                               \
+        (const unsigned char*)sorted, (const Tile<T>*)tiles, pl.n_tiles, (const Xycs<T>*)tgt, tgt_perm, n_tgt, tblocks, \
+        k, cc, partial, pl.n_groups, pl.n_tblocks, counter, item_order, item_cost, stats)
+    if (pl.wide) {
+        if (fp->p2r) CSF_TILED_LAUNCH(true, kWideFW, kWideEW);
+        else CSF_TILED_LAUNCH(false, kWideFW, kWideEW);
+    } else {
+        if (fp->p2r) CSF_TILED_LAUNCH(true, kNarrowFW, kNarrowEW);
+        else CSF_TILED_LAUNCH(false, kNarrowFW, kNarrowEW);
+    }
+#undef CSF_TILED_LAUNCH
     CSF_CHECK_LAUNCH("pair_tiled_kernel");
     if (flags & CSF_TILED_NO_REDUCE) return 0;          // the caller sums partial[group][target][2] * f_0 itself
     const int64_t n2 = n_tgt * 2;

@@ -485,7 +485,7 @@ class Engine:
                 wsb = max(wsb, int(self.lib.csf_pair_workspace_bytes(c, self.n_agents, 4 if self.f32 else 8)))
         self.tiled = (scenario_size is None and self.n_total > 1 and not self._ecc and
                       (pair_mode == "tiled" or (pair_mode == "auto" and self.n_total >= 2048)))
-        self.pair_stats = torch.zeros(16, dtype=torch.int64, device=self.device) if count_pairs else None
+        self.pair_stats = torch.zeros(16 + 4 * 16384, dtype=torch.int64, device=self.device) if count_pairs else None
         self._tiles = []
         self._pair_calls = 0
         if self.tiled:

@@ -41,6 +41,11 @@ static double angle_difference(double a1, double a2) {
 static double clampd(double x, double lo, double hi) { return fmax(fmin(x, hi), lo); }
 static double sgn(double x) { return (x > 0) - (x < 0); }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers and the OpenMP runtime of the process reads it once:
+ * the CPU baseline sets the thread count explicitly */
+void csf_c_set_num_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+}
 int csf_c_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -150,8 +150,11 @@ def test_demo_geometry_golden_f64(golden, model):
     assert np.array_equal(g.dest_ptr.cpu().numpy(), gd[f"demo_{model}_ptr"])
 
 
-@pytest.mark.parametrize("model", ["twod", BICYCLE_XFAIL])
+@pytest.mark.parametrize("model", ["twod", "invpendulum", BICYCLE_XFAIL])
 def test_stop_destinations_golden_f64(golden, model):
+    """Stop destinations (navigation machine go -> decelerating -> arrived, vehicle.py:354-457; for the
+    inverted pendulum also riding -> walking below v_max_walk, :1932-1950) against vectors generated by the
+    reference's own code."""
     gd = golden
     steps = gd[f"stop_{model}_steps"]
     eng, g = make_engine(model, gd["demo_s0"], gd["demo_vd"], gd["stop_dests"], dtype=torch.float64)
@@ -162,7 +165,12 @@ def test_stop_destinations_golden_f64(golden, model):
         if k in keep:
             S.append(g.states_numpy())
     eng.check_status()
-    assert np.abs(np.array(S) - gd[f"stop_{model}_s"]).max() < 1e-7
+    err = np.abs(np.array(S) - gd[f"stop_{model}_s"]).max()
+    report(test="stop_destinations_golden", model=model, steps=int(steps.max()), max_abs_state_err=float(err))
+    # the inverted pendulum's closed loop amplifies the 1e-15 difference between two matrix-exponential
+    # implementations (here: in-kernel Pade vs scipy's) along the way
+    assert err < (1e-6 if model == "invpendulum" else 1e-7)
+    assert np.array_equal(g.dest_ptr.cpu().numpy(), gd[f"stop_{model}_ptr"])
     znav = g.znav.cpu().numpy()
     assert np.array_equal(znav == 4, gd[f"stop_{model}_znav"][:, 2])
 

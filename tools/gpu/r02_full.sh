@@ -1,10 +1,10 @@
 #!/bin/bash
-# full GPU test suite + bench + emulated shard: bash tools/gpu/r02_full.sh <tag>
+# full GPU test suite + bench (+ ncu of the agent kernel): bash tools/gpu/r02_full.sh <tag> [ncu]
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 TAG=${1:-full}
 timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/${TAG}_pytest.log 2>&1
-echo "pytest rc=$?"; tail -25 gpurun_out/${TAG}_pytest.log | cut -c1-600
+echo "pytest rc=$?"; tail -12 gpurun_out/${TAG}_pytest.log | cut -c1-300
 show() { python - <<PY
 import json
 d=json.load(open("$1")); r=d["roofline"]; a=d["roofline_agent_kernel"]
@@ -13,9 +13,12 @@ PY
 }
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 echo "bench rc=$?"; tail -3 gpurun_out/${TAG}_bench.err; show gpurun_out/${TAG}_bench.json
-for G in 1 2 8; do
-CSF_TILED_GROUPS=$G CSF_BENCH_EMULATE_WORLD=8 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_shard_g$G.json 2> gpurun_out/${TAG}_shard_g$G.err
-show gpurun_out/${TAG}_shard_g$G.json
-done
-CSF_BENCH_N=1048576 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_1M.json 2> gpurun_out/${TAG}_bench_1M.err
-show gpurun_out/${TAG}_bench_1M.json
+CSF_BENCH_EMULATE_WORLD=8 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_shard8.json 2> gpurun_out/${TAG}_shard8.err
+show gpurun_out/${TAG}_shard8.json
+if [ "$2" = "ncu" ]; then
+  export CSF_BENCH_GRAPH=0
+  python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:agent_kernel -s 8 -c 1 -f -o gpurun_out/${TAG}_agent \
+      python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu.log 2>&1
+  echo "ncu rc=$?"
+fi
