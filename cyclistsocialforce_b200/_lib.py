@@ -61,6 +61,12 @@ class CsfAgentParams(C.Structure):
         ("br_A0", C.c_double * 25), ("br_A1", C.c_double * 25), ("br_A2", C.c_double * 25),
         ("br_B", C.c_double * 5),
         ("br_pole_icpt", C.c_double * 5), ("br_pole_coef", C.c_double * 5),
+        ("br_stochastic", C.c_int32), ("br_n_comp", C.c_int32), ("br_resample_thresh", C.c_double),
+        ("br_seed", C.c_uint64),
+        ("br_lam", C.c_double * 6), ("br_sc_mean", C.c_double * 6), ("br_sc_scale", C.c_double * 6),
+        ("br_log_a", C.c_double * 5), ("br_log_sign", C.c_double * 5),
+        ("br_w", C.c_double * 4), ("br_mu_g", C.c_double * 4), ("br_var_g", C.c_double * 4),
+        ("br_mu", (C.c_double * 5) * 4), ("br_slope", (C.c_double * 5) * 4), ("br_chol", (C.c_double * 15) * 4),
         ("q_scale", C.c_double), ("q_origin", C.c_double * 2),
         ("traj_len", C.c_int32), ("hist_len", C.c_int32), ("hist_cap", C.c_int32), ("q_cap", C.c_int32),
     ]
@@ -79,12 +85,24 @@ class CsfAgentState(C.Structure):
         ("hist_step", C.c_void_p),
         ("ip_x", C.c_void_p), ("ip_zrid", C.c_void_p), ("ip_delta_run", C.c_void_p),
         ("dyn_x", C.c_void_p), ("dyn_v", C.c_void_p), ("br_gains", C.c_void_p),
+        ("br_poles", C.c_void_p), ("br_vlast", C.c_void_p), ("br_draws", C.c_void_p), ("br_stream", C.c_void_p),
         ("status", C.c_void_p), ("status_host", C.c_void_p),
     ]
 
 
 _vp, _i64, _i32, _dbl, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_size_t
 _FP = C.POINTER(CsfFieldParams)
+MAX_COPY_SEGMENTS = 16
+
+
+class CsfCopySegment(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("bytes", C.c_int64)]
+
+
+class CsfCopySegments(C.Structure):
+    _fields_ = [("n", C.c_int32), ("pad_", C.c_int32), ("seg", CsfCopySegment * MAX_COPY_SEGMENTS)]
+
+
 _AP = C.POINTER(CsfAgentParams)
 _AS = C.POINTER(CsfAgentState)
 
@@ -137,10 +155,14 @@ SIGNATURES = {
     "csf_agent_step_f64": (C.c_int, [C.c_int, _AS, _AP, _i64, _vp, _vp, _vp, _vp, _vp]),
     "csf_agent_step_fused_f32": (C.c_int, [C.c_int, _AS, _AP, _i64, _vp, _vp, _vp, _vp, _vp]),
     "csf_agent_step_fused_f64": (C.c_int, [C.c_int, _AS, _AP, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "csf_br_init": (C.c_int, [_AS, _AP, _vp]),
     "csf_pack_xycs_f32": (C.c_int, [_AS, _AP, _vp, _vp]),
     "csf_pack_xycs_f64": (C.c_int, [_AS, _AP, _vp, _vp]),
     "csf_pack_xypsi_f32": (C.c_int, [_vp, _vp, _vp, _i64, _dbl, _dbl, _dbl, _vp, _vp]),
     "csf_pack_xypsi_f64": (C.c_int, [_vp, _vp, _vp, _i64, _dbl, _dbl, _dbl, _vp, _vp]),
+    "csf_copy_segments": (C.c_int, [C.POINTER(CsfCopySegments), _vp]),
+    "csf_sumo_pose_f32": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "csf_sumo_pose_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "csf_ffma_peak": (C.c_int, [_i64, _vp, C.POINTER(C.c_double), _vp]),
     "csf_peer_handle_bytes": (C.c_int, []),
     "csf_peer_alloc": (C.c_int, [_sz, C.POINTER(C.c_void_p), _vp]),

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcsf_b200.so")
-SOURCES = ["csf_pair.cu", "csf_pair_tiled.cu", "csf_agent.cu", "csf_peer.cu", "csf_order.cu"]
+SOURCES = ["csf_pair.cu", "csf_pair_tiled.cu", "csf_agent.cu", "csf_peer.cu", "csf_order.cu", "csf_traj.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

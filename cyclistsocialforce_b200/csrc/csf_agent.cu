@@ -90,11 +90,11 @@ template <typename T> __device__ __forceinline__ T dist_to(const Agent<T>& a, in
     T dx, dy;
     bool st;
     queue_entry(a, idx, dx, dy, st);
-    return sqrt(dx * dx + dy * dy);
+    return qsqrt(dx * dx + dy * dy);
 }
 
 // Vehicle.updateDestination, vehicle.py:545-594
-template <typename T> __device__ void update_destination(Agent<T>& a, const CsfAgentParams& p) {
+template <typename T> __device__ __forceinline__ void update_destination(Agent<T>& a, const CsfAgentParams& p) {
     const T dnext = dist_to(a, a.ptr);
     if (a.znav & 6) return;
     if (dnext <= (T)p.d_arrived_inter) a.ptr = min(a.ptr + 1, a.qlen - 1);
@@ -105,7 +105,7 @@ template <typename T> __device__ void update_destination(Agent<T>& a, const CsfA
 }
 
 // Vehicle.updateNavState, vehicle.py:354-457 -> v_d ; *ddest_out = distance to destination
-template <typename T> __device__ T update_nav_state(Agent<T>& a, const CsfAgentParams& p, bool stop, T* ddest_out) {
+template <typename T> __device__ __forceinline__ T update_nav_state(Agent<T>& a, const CsfAgentParams& p, bool stop, T* ddest_out) {
     const T k = (T)1.5;
     const bool z0 = a.znav & 1, z1 = a.znav & 2, z2 = a.znav & 4;
     const T vhd = (T)p.v_max_harddecel;
@@ -143,7 +143,7 @@ template <typename T> __device__ T update_nav_state(Agent<T>& a, const CsfAgentP
 }
 
 // Bicycle.calcDestinationForceField (vehicle.py:1168-1187) == calc_direct_approach_dest_force (:2096-2108)
-template <typename T> __device__ void dest_force_direct(Agent<T>& a, const CsfAgentParams& p, T& fx, T& fy) {
+template <typename T> __device__ __forceinline__ void dest_force_direct(Agent<T>& a, const CsfAgentParams& p, T& fx, T& fy) {
     update_destination(a, p);
     T rx, ry;
     bool stop;
@@ -187,7 +187,7 @@ template <typename T> __device__ __forceinline__ void basis_local(const T* K, T 
         T saved = (T)0;
 #pragma unroll
         for (int r = 0; r < j; ++r) {
-            const T temp = N[r] / (right[r + 1] + left[j - r]);
+            const T temp = qdiv(N[r], right[r + 1] + left[j - r]);
             N[r] = saved + right[r + 1] * temp;
             saved = left[j - r] * temp;
         }
@@ -206,13 +206,14 @@ template <typename T, int M> __device__ __forceinline__ bool spline_fit(SplineM<
 #pragma unroll
     for (int k = 1; k < M; ++k) {                      // chord-length parameters
         const T dx = px[k] - px[k - 1], dy = py[k] - py[k - 1];
-        const T d = sqrt(dx * dx + dy * dy);
+        const T d = qsqrt(dx * dx + dy * dy);
         ok = ok && (d > (T)0);
         u[k] = u[k - 1] + d;
     }
     const T tot = u[M - 1];
+    const T itot = qdiv((T)1, tot);
 #pragma unroll
-    for (int k = 1; k < M - 1; ++k) u[k] = u[k] / tot;
+    for (int k = 1; k < M - 1; ++k) u[k] = u[k] * itot;
     u[M - 1] = (T)1;
 #pragma unroll
     for (int i = 0; i < M + 4; ++i) s.kn[i] = i < 4 ? (T)0 : (i >= M ? (T)1 : u[i - 2]);
@@ -242,7 +243,7 @@ template <typename T, int M> __device__ __forceinline__ bool spline_fit(SplineM<
     // Gaussian elimination without pivoting (B-spline collocation matrices are totally positive)
 #pragma unroll
     for (int k = 0; k < NI; ++k) {
-        const T inv = (T)1 / A[k][k];
+        const T inv = qdiv((T)1, A[k][k]);
 #pragma unroll
         for (int i = k + 1; i < NI; ++i) {
             const T f = A[i][k] * inv;
@@ -262,7 +263,7 @@ template <typename T, int M> __device__ __forceinline__ bool spline_fit(SplineM<
             sx -= A[k][j] * s.cx[j + 1];
             sy -= A[k][j] * s.cy[j + 1];
         }
-        const T inv = (T)1 / A[k][k];
+        const T inv = qdiv((T)1, A[k][k]);
         s.cx[k + 1] = sx * inv;
         s.cy[k + 1] = sy * inv;
     }
@@ -304,13 +305,13 @@ __device__ __forceinline__ void spline_eval(const SplineM<T, M>& s, T u, bool de
     T d1x[3], d1y[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        const T w = (T)3 / (K[3 + r] - K[r]);
+        const T w = qdiv((T)3, K[3 + r] - K[r]);
         d1x[r] = w * (cxl[r + 1] - cxl[r]);
         d1y[r] = w * (cyl[r + 1] - cyl[r]);
     }
     dx = N2[0] * d1x[0] + N2[1] * d1x[1] + N2[2] * d1x[2];
     dy = N2[0] * d1y[0] + N2[1] * d1y[1] + N2[2] * d1y[2];
-    const T w0 = (T)2 / (K[3] - K[1]), w1 = (T)2 / (K[4] - K[2]);
+    const T w0 = qdiv((T)2, K[3] - K[1]), w1 = qdiv((T)2, K[4] - K[2]);
     ddx = N1[0] * (w0 * (d1x[1] - d1x[0])) + N1[1] * (w1 * (d1x[2] - d1x[1]));
     ddy = N1[0] * (w0 * (d1y[1] - d1y[0])) + N1[1] * (w1 * (d1y[2] - d1y[1]));
 }
@@ -343,13 +344,13 @@ __device__ __forceinline__ int spline_force(const T* px, const T* py, int cur, b
     spline_eval<T, M>(sp, us, true, sx, sy, dx, dy, ddx, ddy);
     T qx, qy, t0, t1, t2, t3;
     spline_eval<T, M>(sp, up, false, qx, qy, t0, t1, t2, t3);
-    const T sp1 = sqrt(dx * dx + dy * dy);
-    const T R = sp1 * sp1 * sp1 / fabs(dx * ddy - dy * ddx);  // :1532-1537
+    const T sp1 = qsqrt(dx * dx + dy * dy);
+    const T R = qdiv(sp1 * sp1 * sp1, fabs(dx * ddy - dy * ddx));  // :1532-1537
     const T thetacomf = (T)(10.0 * (CSF_TWO_PI / 360.0));
-    T v = fmax((T)2.5, sqrt(thetacomf * g * R));
+    T v = fmax((T)2.5, qsqrt(thetacomf * g * R));
     v = fmin(v, vd);
     const T ex = qx - sx, ey = qy - sy;
-    const T temp = v / sqrt(ex * ex + ey * ey);
+    const T temp = qdiv(v, qsqrt(ex * ex + ey * ey));
     fx = temp * ex;
     fy = temp * ey;
     return 0;
@@ -357,7 +358,7 @@ __device__ __forceinline__ int spline_force(const T* px, const T* py, int cur, b
 
 // TwoDBicycle.calcDestinationForce, vehicle.py:1443-1558
 template <typename T>
-__device__ void dest_force_twod(Agent<T>& a, const CsfAgentParams& p, const CsfAgentState& st, int64_t k, double pv_x,
+__device__ __forceinline__ void dest_force_twod(Agent<T>& a, const CsfAgentParams& p, const CsfAgentState& st, int64_t k, double pv_x,
                                 double pv_y, T& fx, T& fy) {
     update_destination(a, p);
     T drx, dry;
@@ -416,7 +417,7 @@ __device__ void dest_force_twod(Agent<T>& a, const CsfAgentParams& p, const CsfA
 }
 
 template <typename T, int MODEL>
-__device__ void destination_force(Agent<T>& a, const CsfAgentParams& p, const CsfAgentState& st, int64_t k, double pv_x,
+__device__ __forceinline__ void destination_force(Agent<T>& a, const CsfAgentParams& p, const CsfAgentState& st, int64_t k, double pv_x,
                                   double pv_y, T& fx, T& fy) {
     if (MODEL == CSF_MODEL_TWOD || MODEL == CSF_MODEL_INVPENDULUM) dest_force_twod(a, p, st, k, pv_x, pv_y, fx, fy);
     else if (MODEL == CSF_MODEL_BICYCLE) dest_force_direct(a, p, fx, fy);              // vehicle.py:1189-1194
@@ -432,7 +433,7 @@ __device__ void destination_force(Agent<T>& a, const CsfAgentParams& p, const Cs
 // ----------------------------------------------------------------------------------------
 // Bicycle.control + move, vehicle.py:1218-1272
 // ----------------------------------------------------------------------------------------
-template <typename T> __device__ void control_move(Agent<T>& a, const CsfAgentParams& p, T Fx, T Fy) {
+template <typename T> __device__ __forceinline__ void control_move(Agent<T>& a, const CsfAgentParams& p, T Fx, T Fy) {
     const T th = atan2(Fy, Fx);
     T vF = sqrt(Fx * Fx + Fy * Fy);
     const T dd = dist_to(a, a.ptr);
@@ -607,12 +608,10 @@ __device__ void invpend_yaw_step(const CsfAgentParams& p, double v, double psi_d
 __device__ void br_matrix(const CsfAgentParams& p, double v, double* A) {
     for (int i = 0; i < 25; ++i) A[i] = p.br_A0[i] + v * p.br_A1[i] + v * v * p.br_A2[i];
 }
-__device__ void br_gains(const CsfAgentParams& p, double v, double* K) {
+__device__ void br_gains(const CsfAgentParams& p, double v, const double* f /* pole features */, double* K) {
     constexpr int N = 5;
     double A[25], T1[25], T2[25], Phi[25];
     br_matrix(p, v, A);
-    double f[5];
-    for (int i = 0; i < 5; ++i) f[i] = p.br_pole_icpt[i] + p.br_pole_coef[i] * v;
     // phi(A) = (A - p0 I) (A^2 - 2 re1 A + |p1|^2 I) (A^2 - 2 re2 A + |p2|^2 I)
     double A2[25];
     mat_mul<N>(A, A, A2);
@@ -644,6 +643,129 @@ __device__ void br_gains(const CsfAgentParams& p, double v, double* K) {
         double s = 0.0;
         for (int i = 0; i < 5; ++i) s = fma(w[i], Phi[i * 5 + j], s);
         K[j] = s;
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// Stochastic rider behaviour: closed-loop poles drawn from the rider-behaviour model, a Gaussian mixture
+// over [speed, pole features] conditioned on the speed, in a Yeo-Johnson / log-shifted feature space
+// (parameters.py:1398-1402 -> controlbehavior.py:1414-1469 PoleModel.sample_poles, :1337-1412 sample,
+// :477-533 _get_conditional_gmm, :962-985 inverse_transform).  Counter-based random numbers
+// (Philox-4x32-10; key = seed, counter = road user, draw number): a road user's poles do not depend on how
+// the crowd is grouped or sharded, and the host oracle (oracle/pole_sampling.py) reproduces every draw.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t* out) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0;
+        c1 = l1;
+        c2 = h0 ^ c3 ^ k1;
+        c3 = l0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ double yj_forward(double x, double lam) {          // sklearn PowerTransformer
+    if (x >= 0.0) return fabs(lam) < 2.220446049250313e-16 ? log1p(x) : (pow(x + 1.0, lam) - 1.0) / lam;
+    return fabs(lam - 2.0) > 2.220446049250313e-16 ? -(pow(-x + 1.0, 2.0 - lam) - 1.0) / (2.0 - lam) : -log1p(-x);
+}
+__device__ __forceinline__ double yj_inverse(double y, double lam) {          // NaN outside the transform's range
+    if (y >= 0.0) return fabs(lam) < 2.220446049250313e-16 ? exp(y) - 1.0 : pow(y * lam + 1.0, 1.0 / lam) - 1.0;
+    return fabs(lam - 2.0) > 2.220446049250313e-16 ? 1.0 - pow(-(2.0 - lam) * y + 1.0, 1.0 / (2.0 - lam)) : 1.0 - exp(-y);
+}
+// pole features [p0_real, p1_real, p1_imag, p2_real, p2_imag] of road user `agent` at speed v; draws
+// *draws, *draws + 1, ... until the sample is inside the range of the inverse transform and stable.
+__device__ bool br_sample_poles(const CsfAgentParams& p, double v, unsigned long long agent, int* draws, double* f) {
+    const int nc = p.br_n_comp;
+    const double xt = (yj_forward(v, p.br_lam[0]) - p.br_sc_mean[0]) / p.br_sc_scale[0];
+    double w[4], wsum = 0.0;
+    for (int c = 0; c < 4; ++c) {
+        w[c] = 0.0;
+        if (c < nc) {
+            const double d = xt - p.br_mu_g[c];
+            w[c] = p.br_w[c] * exp(-0.5 * d * d / p.br_var_g[c]) / sqrt(CSF_TWO_PI * p.br_var_g[c]);
+            wsum += w[c];
+        }
+    }
+    bool any0 = false;
+    for (int c = 0; c < nc; ++c) { w[c] /= wsum; any0 = any0 || w[c] == 0.0; }
+    if (any0) {                                                  // controlbehavior.py:523-526
+        double s2 = 0.0;
+        for (int c = 0; c < nc; ++c) { if (w[c] == 0.0) w[c] = 2.220446049250313e-16 * nc; s2 += w[c]; }
+        for (int c = 0; c < nc; ++c) w[c] /= s2;
+    }
+    const uint32_t k0 = (uint32_t)(p.br_seed & 0xffffffffull), k1 = (uint32_t)(p.br_seed >> 32);
+    const uint32_t a_lo = (uint32_t)(agent & 0xffffffffull), a_hi = (uint32_t)(agent >> 32);
+    for (int t = 0; t < 1000; ++t) {
+        uint32_t r[8];
+        philox4x32_10(a_lo, (uint32_t)(*draws + t), 0u, a_hi, k0, k1, r);
+        philox4x32_10(a_lo, (uint32_t)(*draws + t), 1u, a_hi, k0, k1, r + 4);
+        double u[8], z[6];
+        for (int i = 0; i < 8; ++i) u[i] = ((double)r[i] + 0.5) * 2.3283064365386963e-10;
+        for (int i = 0; i < 3; ++i) {
+            const double rad = sqrt(-2.0 * log(u[1 + 2 * i]));
+            double sn, cs;
+            sincos(CSF_TWO_PI * u[2 + 2 * i], &sn, &cs);
+            z[2 * i] = rad * cs;
+            z[2 * i + 1] = rad * sn;
+        }
+        int comp = nc - 1;
+        double cum = 0.0;
+        for (int c = 0; c < nc; ++c) {
+            cum += w[c];
+            if (u[0] < cum) { comp = c; break; }
+        }
+        bool ok = true;
+        for (int i = 0; i < 5; ++i) {
+            double x = p.br_mu[comp][i] + p.br_slope[comp][i] * (xt - p.br_mu_g[comp]);
+            for (int j = 0; j <= i; ++j) x += p.br_chol[comp][i * (i + 1) / 2 + j] * z[j];
+            double y = yj_inverse(x * p.br_sc_scale[1 + i] + p.br_sc_mean[1 + i], p.br_lam[1 + i]);
+            if (p.br_log_sign[i] != 0.0) y = (exp(y) + p.br_log_a[i]) / p.br_log_sign[i];
+            f[i] = y;
+            ok = ok && isfinite(y);
+        }
+        ok = ok && f[0] <= 0.0 && f[1] <= 0.0 && f[3] <= 0.0;
+        if (ok) { *draws += t + 1; return true; }
+    }
+    *draws += 1000;
+    return false;
+}
+// poles of a BalancingRider agent for the speed v: the regression of the component mean, or -- stochastic
+// behaviour -- the agent's current sample, re-drawn when the speed has moved by more than the threshold
+// since the last draw (update_control_params, parameters.py:1376-1411)
+__device__ void br_poles_for(const CsfAgentParams& p, const CsfAgentState& st, int64_t k, double v, double* f, int* flags) {
+    if (!p.br_stochastic) {
+        for (int i = 0; i < 5; ++i) f[i] = p.br_pole_icpt[i] + p.br_pole_coef[i] * v;
+        return;
+    }
+    if (fabs(v - st.br_vlast[k]) > p.br_resample_thresh) {
+        int draws = st.br_draws[k];
+        if (!br_sample_poles(p, v, (unsigned long long)st.br_stream[k], &draws, f)) *flags |= 16;
+        st.br_draws[k] = draws;
+        st.br_vlast[k] = v;
+        for (int i = 0; i < 5; ++i) st.br_poles[(size_t)i * st.n + k] = f[i];
+    } else {
+        for (int i = 0; i < 5; ++i) f[i] = st.br_poles[(size_t)i * st.n + k];
+    }
+}
+// gains of every agent for its current speed (BalancingRiderDynamics.__init__ -> _get_gains(v),
+// dynamics.py:305-306, :602-615): also draws the first poles of a stochastic rider
+__global__ void br_init_kernel(CsfAgentState st, CsfAgentParams p) {
+    const int64_t k = st.first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= st.first + st.count) return;
+    double f[5], g[5];
+    int flags = 0;
+    const double v = st.dyn_v[k];
+    br_poles_for(p, st, k, v, f, &flags);
+    br_gains(p, v, f, g);
+    for (int r = 0; r < 5; ++r) st.br_gains[(size_t)r * st.n + k] = g[r];
+    if (flags && st.status != nullptr) {
+        atomicOr(st.status, flags);
+        if (st.status_host != nullptr) *reinterpret_cast<volatile int32_t*>(st.status_host) = 1;
     }
 }
 
@@ -823,7 +945,9 @@ __device__ __forceinline__ bool agent_body(const CsfAgentState& st, const CsfAge
             double g[5], xb[5];
             for (int r = 0; r < 5; ++r) xb[r] = st.dyn_x[(size_t)r * st.n + k];
             if (v != vold) {  // :680-681
-                br_gains(p, vbar, g);
+                double pf[5];
+                br_poles_for(p, st, k, vbar, pf, &a.flags);
+                br_gains(p, vbar, pf, g);
                 for (int r = 0; r < 5; ++r) st.br_gains[(size_t)r * st.n + k] = g[r];
             } else
                 for (int r = 0; r < 5; ++r) g[r] = st.br_gains[(size_t)r * st.n + k];
@@ -1034,6 +1158,12 @@ int csf_agent_step_fused_f64(int model, const CsfAgentState* st, const CsfAgentP
                              csf_stream_t s) {
     return launch_agent<double, MODE_STEP>(model, st, p, n_total, nullptr, froad, force, nullptr, next_xycs,
                                            (cudaStream_t)s, fusion);
+}
+int csf_br_init(const CsfAgentState* st, const CsfAgentParams* p, csf_stream_t s) {
+    if (st->count <= 0) return 0;
+    br_init_kernel<<<(unsigned)((st->count + 63) / 64), 64, 0, (cudaStream_t)s>>>(*st, *p);
+    CSF_CHECK_LAUNCH("br_init_kernel");
+    return 0;
 }
 int csf_pack_xycs_f32(const CsfAgentState* st, const CsfAgentParams* p, void* xycs, csf_stream_t s) {
     if (st->count <= 0) return 0;

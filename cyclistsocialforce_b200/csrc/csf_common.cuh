@@ -41,11 +41,22 @@ template <> struct M<double> {
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
 };
 
+// Division and square root of the per-agent kernels: IEEE in the f64 verification build; in the f32
+// production build the single-instruction MUFU approximations (relative error <= 2^-22, far inside the
+// 1e-4 per-step budget) -- an IEEE float division is ~10 instructions with a slow path, and the per-agent
+// kernel is bound by instruction fetch and issue latency, not by bandwidth.
+__device__ __forceinline__ float qdiv(float a, float b) { return a * M<float>::rcp(b); }
+__device__ __forceinline__ double qdiv(double a, double b) { return a / b; }
+__device__ __forceinline__ float qsqrt(float a) { return M<float>::sqrt(a); }
+__device__ __forceinline__ double qsqrt(double a) { return ::sqrt(a); }
+
 // ---- angles (reference utils.py) --------------------------------------------------
 // limitAngle, utils.py:124-139: wrap to (-pi, pi]
+__device__ __forceinline__ float periods(float th) { return floorf(th * (float)(1.0 / CSF_TWO_PI)); }
+__device__ __forceinline__ double periods(double th) { return floor(th / CSF_TWO_PI); }
 template <typename T> __device__ __forceinline__ T limit_angle(T th) {
     const T tp = (T)CSF_TWO_PI, pi = (T)CSF_PI;
-    th = floor(th / tp) * (-tp) + th;
+    th = periods(th) * (-tp) + th;
     if (th > pi) th -= tp;
     else if (th < -pi) th += tp;
     return th;

@@ -28,7 +28,7 @@ _STATE_COLS = ("x", "y", "psi", "v", "delta", "theta", "deltadot", "thetadot")
 # per-agent device fields and the axis the agent index runs along (churn: AgentGroup.select / concat)
 _FIELD_AXIS = dict(vd_default=0, step_i=0, destq=0, dest_len=0, dest_ptr=0, znav=0, znav_v0=0, znav_d0=0, znav_d1=0,
                    prev_x=0, prev_y=0, hist_x=1, hist_y=1, hist_step=0, ip_x=1, ip_zrid=0, ip_delta_run=0,
-                   dyn_x=1, dyn_v=0, br_gains=1)
+                   dyn_x=1, dyn_v=0, br_gains=1, br_poles=1, br_vlast=0, br_draws=0, br_stream=0)
 HIST_CAP = 128     # smallest ring of past positions (rows); sized per group from t_s, see hist_capacity()
 
 
@@ -59,7 +59,7 @@ class AgentGroup:
     queue convention, vehicle.py:183-185)."""
 
     def __init__(self, model, s0, params, vd_default=None, destqueues=None, dtype=torch.float32,
-                 device="cuda", q_cap=None):
+                 device="cuda", q_cap=None, stream_ids=None):
         assert model in N_STATES and model != "uncontrolled"
         _lib.load()
         if not torch.cuda.is_available():
@@ -120,6 +120,7 @@ class AgentGroup:
             self.hist_x = self.hist_y = self.hist_step = None
         self.ip_x = self.ip_zrid = self.ip_delta_run = None
         self.dyn_x = self.dyn_v = self.br_gains = None
+        self.br_poles = self.br_vlast = self.br_draws = self.br_stream = None
         if model == "invpendulum":
             # vehicle.py:1728-1736
             self.ip_x = t64(np.stack([s0[:, 4], z, s0[:, 5], z, s0[:, 2]]))
@@ -131,7 +132,17 @@ class AgentGroup:
             # dynamics.py:361-399 (CSF frame -> bike frame) and :305-306
             self.dyn_x = t64(np.stack([s0[:, 5], -s0[:, 4], s0[:, 7], -s0[:, 6], -s0[:, 2]]))
             self.dyn_v = t64(s0[:, 3])
-            self.br_gains = t64(self._initial_br_gains(s0[:, 3]))
+            self.br_poles = torch.zeros((5, n), dtype=f64, device=dev)
+            self.br_vlast = torch.full((n,), -10000.0, dtype=f64, device=dev)     # parameters.py:1311
+            self.br_draws = torch.zeros(n, dtype=i32, device=dev)
+            # the random stream of a rider is keyed by this number (default: its index in the group); it
+            # travels with the rider through select / concat, so churn does not re-key anybody
+            ids = np.arange(n, dtype=np.int64) if stream_ids is None else np.asarray(stream_ids, dtype=np.int64).reshape(n)
+            self.br_stream = torch.as_tensor(ids, dtype=torch.int64, device=dev)
+            if getattr(params, "stochastic_control_behavior", False):
+                self.br_gains = torch.zeros((5, n), dtype=f64, device=dev)       # drawn + designed on the device below
+            else:
+                self.br_gains = t64(self._initial_br_gains(s0[:, 3]))
         elif model == "planarpoint":
             self.dyn_x = t64(s0[:, 2][None, :])
             self.dyn_v = t64(s0[:, 3])
@@ -139,6 +150,18 @@ class AgentGroup:
         self.payload_offset = 0
         self._cstate = None
         self._cparams = None
+        if model == "balancingrider" and getattr(params, "stochastic_control_behavior", False):
+            self.init_stochastic_gains()
+
+    def init_stochastic_gains(self):
+        """First poles and gains of stochastic riders (BalancingRiderDynamics.__init__ -> _get_gains,
+        dynamics.py:305-306): drawn on the device, every rider from its own stream (``br_stream``)."""
+        self._cstate = None
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().csf_br_init(C.byref(self.cstate()), C.byref(self.cparams(1.0)),
+                                               C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                       "csf_br_init")
+        self._cstate = None
 
     def _init_status(self):
         """Device status word + its mirror in pinned (host-mapped) memory: the kernels raise the mirror
@@ -254,7 +277,8 @@ class AgentGroup:
             for name in ("x", "y", "psi", "v", "delta", "theta", "deltadot", "thetadot", "vd_default",
                          "step_i", "destq", "dest_len", "dest_ptr", "znav", "znav_v0", "znav_d0",
                          "znav_d1", "prev_x", "prev_y", "hist_x", "hist_y", "hist_step", "ip_x",
-                         "ip_zrid", "ip_delta_run", "dyn_x", "dyn_v", "br_gains", "status"):
+                         "ip_zrid", "ip_delta_run", "dyn_x", "dyn_v", "br_gains", "br_poles", "br_vlast", "br_draws",
+                         "br_stream", "status"):
                 t = getattr(self, name)
                 setattr(s, name, t.data_ptr() if t is not None else None)
             s.status_host = self.status_host.data_ptr()     # (UVA: pinned host memory is device-addressable)
@@ -313,7 +337,8 @@ class AgentGroup:
 
     _RECORD_FIELDS = ("x", "y", "psi", "v", "delta", "theta", "deltadot", "thetadot", "step_i", "dest_ptr",
                       "znav", "znav_v0", "znav_d0", "znav_d1", "prev_x", "prev_y", "hist_x", "hist_y",
-                      "hist_step", "ip_x", "ip_zrid", "ip_delta_run", "dyn_x", "dyn_v", "br_gains")
+                      "hist_step", "ip_x", "ip_zrid", "ip_delta_run", "dyn_x", "dyn_v", "br_gains", "br_poles", "br_vlast",
+                      "br_draws", "br_stream")
 
     def export_records(self):
         """Full per-agent device state as host dicts (kept by vehicles across re-binding)."""

@@ -163,24 +163,36 @@ class SocialForceIntersection:
 
     Extra keyword arguments of this implementation (all optional):
       dtype        torch.float32 (production build, default) or torch.float64 (verification)
-      record_traj  keep the per-vehicle ``traj`` / ``trajF`` / ``F`` histories on the host
-                   (one device->host copy per step); default: on for <= 64 road users.
+      record_traj  keep the per-vehicle ``traj`` / ``trajF`` / ``F`` histories on the host; default: on for
+                   <= 64 road users (one device->host copy per step).  ``record_traj=True`` on a larger
+                   crowd records through a device ring that the host drains a chunk of steps at a time
+                   (trajstream.TrajectoryStream: one launch per step, one copy per chunk); the per-vehicle
+                   arrays are filled in when ``vehicle.traj`` is read or ``flush_trajectories()`` is called.
+      sumo_client  a traci-like object (``.vehicle.moveToXY``); with ``activate_sumo_cosimulation=True``
+                   every step ends with a batched position update (one kernel + one device->host copy,
+                   then the client calls; reference :660-688).  Without a client ``traci`` is imported.
     """
 
     def __init__(self, vehicleList, id="", priority_rule="unregulated", animate=False, axes=None,
                  activate_sumo_cosimulation=False, net=None, road_elements=(), bicycle_drawing_kwargs=None,
-                 dtype=torch.float32, record_traj=None, device="cuda", _private=False):
+                 dtype=torch.float32, record_traj=None, device="cuda", sumo_client=None, _private=False):
         if animate:
             raise NotImplementedError("matplotlib animation is outside the accelerated stepping path")
-        if activate_sumo_cosimulation:
-            raise NotImplementedError("SUMO/TraCI co-simulation stays host-side and is out of scope here")
+        if activate_sumo_cosimulation and sumo_client is None:
+            try:
+                import traci as sumo_client          # noqa: F811  (the reference's client, if installed)
+            except ImportError as e:
+                raise ImportError("activate_sumo_cosimulation=True needs the SUMO python client (traci) or a "
+                                  "sumo_client object with .vehicle.moveToXY") from e
+        self._sumo = sumo_client if activate_sumo_cosimulation else None
         assert isinstance(id, str), "Intersection ID has to be a string."
         assert priority_rule in ("p2r", "unregulated"), "Priority rule has to be one of ('p2r','unregulated')"
         self.id = id
         self.priority_rule = priority_rule
         self.animate = False
         self.ax = axes
-        self.activate_sumo_cosimulation = False
+        self.activate_sumo_cosimulation = bool(activate_sumo_cosimulation)
+        self._traj_stream = None
         self.road_elements = list(road_elements)
         self.is_first_step = True
         self.hist_n_vecs = []
@@ -209,7 +221,8 @@ class SocialForceIntersection:
         for (model, _), vs in order.items():
             s0 = np.stack([v._s for v in vs])
             g = AgentGroup(model, s0, vs[0].params, vd_default=[v.params.v_desired_default for v in vs],
-                           destqueues=[v._destqueue for v in vs], dtype=self.dtype, device=self.device)
+                           destqueues=[v._destqueue for v in vs], dtype=self.dtype, device=self.device,
+                           stream_ids=[v._stream_id for v in vs])
             for k, v in enumerate(vs):
                 if v._record is not None:
                     g.import_record(k, v._record)
@@ -242,6 +255,12 @@ class SocialForceIntersection:
         self._invalidate()
         rt = self._record_traj_opt
         self.record_traj = (self.n_bikes <= 64) if rt is None else bool(rt)
+        self.flush_trajectories()                 # (records of the previous binding, if any)
+        self._traj_stream = None
+        if self.record_traj and self.n_bikes > 64 and self._engine is not None:
+            from .trajstream import TrajectoryStream
+            self._traj_stream = TrajectoryStream(self._engine)
+            self._traj_groups = list(self._groups)
 
     # ---- churn without a host round trip of the crowd (reference :458-539, :576-634) -------------------
     def _device_add(self, user):
@@ -257,7 +276,7 @@ class SocialForceIntersection:
             return False
         one = AgentGroup(user.MODEL, np.asarray(user._s, float)[None, :], g.params,
                          vd_default=[user.params.v_desired_default], destqueues=[user._destqueue],
-                         dtype=self.dtype, device=self.device)
+                         dtype=self.dtype, device=self.device, stream_ids=[user._stream_id])
         if user._record is not None:
             one.import_record(0, user._record)
         new = AgentGroup.concat(g, one)
@@ -356,10 +375,54 @@ class SocialForceIntersection:
         return self._xypsi()[:, 2:3]
 
     def update_road_user_positions(self):
-        """reference :660-688: state -> pair payload (device side)."""
+        """reference :660-688: state -> pair payload (device side); with SUMO co-simulation the positions go
+        to the client -- one kernel and one device->host copy per model group, then one ``moveToXY`` per
+        road user from the batch."""
         if self._engine is not None:
             self._sync_obstacles()
             self._engine.pack()
+            if self._sumo is not None:
+                self._push_to_sumo()
+
+    def _push_to_sumo(self):
+        from .trajstream import sumo_poses
+        for g in self._groups:
+            poses = sumo_poses(g)
+            for v in self.vehicles:
+                if v._group is g:
+                    x, y, ang = poses[v._k]
+                    self._sumo.vehicle.moveToXY(v.id, "", -1, float(x), float(y), angle=float(ang), keepRoute=6)
+
+    def flush_trajectories(self):
+        """Move everything the trajectory stream has recorded into the vehicles' ``traj`` / ``trajF`` /
+        ``F`` histories (crowds of more than 64 road users with ``record_traj=True``)."""
+        ts = getattr(self, "_traj_stream", None)
+        if ts is None:
+            return
+        chunks = ts.drain()
+        if not chunks:
+            return
+        by_group = {id(g): [v for v in self.vehicles if v._group is g] for g in self._traj_groups}
+        step_now = {id(g): g.step_i.cpu().numpy() for g in self._traj_groups}
+        total = sum(c["steps"] for c in chunks)
+        done = 0
+        for c in chunks:
+            k = c["steps"]
+            for gi, g in enumerate(self._traj_groups):
+                cols = c["groups"][gi]
+                names = [n for n in ("x", "y", "psi", "v", "delta", "theta", "deltadot", "thetadot") if n in cols]
+                S = np.stack([cols[n].astype(float) for n in names], axis=1)            # (k, n_states, n)
+                off = g.payload_offset - self._engine.global_offset
+                for v in by_group[id(g)]:
+                    L = v._traj.shape[1]
+                    last = int(step_now[id(g)][v._k]) - (total - done - k)                # step index of row k-1
+                    idx = (np.arange(last - k + 1, last + 1)) % L
+                    v._traj[:, idx] = S[:, :v._traj.shape[0], v._k].T
+                    f = c["force"][:, off + v._k, :].astype(float)
+                    v.F.extend(np.hypot(f[:, 0], f[:, 1]).tolist())
+                    if v.trajF is not None:
+                        v.trajF[:, idx] = f.T
+            done += k
 
     def _sync_obstacles(self):
         if self._obstacles_dirty:
@@ -434,8 +497,12 @@ class SocialForceIntersection:
                 for v in o.vehicles:
                     v.step()
             self._invalidate()
-            if self.record_traj:
+            if self._traj_stream is not None:
+                self._traj_stream.append()
+            elif self.record_traj:
                 self._record_histories()
+            if self._sumo is not None:
+                self._push_to_sumo()
         self.hist_n_vecs.append(self.n_bikes)
 
     def _record_histories(self):

@@ -287,7 +287,12 @@ class BalancingRiderBicycleParameters(BicycleParameters):
     The rider-behaviour ("pole") models ship as the linear pole-vs-speed regressions the
     reference derives at construction (``PoleModel.get_component_mean_function``,
     controlbehavior.py:1601-1650); they were extracted with tests/golden/make_golden.py.
-    Stochastic sampling (``stochastic_control_behavior=True``) is not implemented.
+    ``stochastic_control_behavior=True``: every rider draws its closed-loop poles from the model -- a
+    Gaussian mixture over [speed, pole features] conditioned on the speed -- and re-draws them whenever its
+    speed has moved by more than ``controlparam_resampling_speedthresh`` (reference :1398-1402,
+    controlbehavior.py:1414-1469).  The draws happen on the device with a counter-based generator
+    (``controlparam_seed``; csrc/csf_agent.cu ``br_sample_poles``); the model's numbers ship as
+    data/pole_models.json (tests/golden/make_polemodels.py re-serialises the reference's YAML files).
     """
 
     #: features [p0_real, p1_real, p1_imag, p2_real, p2_imag]: (intercept, slope) per model/component
@@ -313,7 +318,7 @@ class BalancingRiderBicycleParameters(BicycleParameters):
                  controlparam_filename="BR1_ImRe5GivenV_pole-model-params.yaml",
                  stochastic_control_behavior=False, controlparam_resampling_speedthresh=0.8333,
                  controlparam_polemodel_component=0, p_dist_roll=0.00, p_dist_steer=0.00,
-                 T_dist_roll=9000, T_dist_steer=1000, **kwargs):
+                 T_dist_roll=9000, T_dist_steer=1000, controlparam_seed=0, **kwargs):
         if bicycleParameterDict is None:
             bicycleParameterDict = wc.balanceassistv1_with_averagerider
         self.bike = dict(bicycleParameterDict)
@@ -321,16 +326,31 @@ class BalancingRiderBicycleParameters(BicycleParameters):
         super().__init__(**kwargs)
         self.m = self.bike["mB"] + self.bike["mF"] + self.bike["mH"] + self.bike["mR"]
         self.g = self.bike["g"]
-        if stochastic_control_behavior:
-            raise NotImplementedError("stochastic_control_behavior is not implemented on the GPU path")
         if p_dist_roll > 0 or p_dist_steer:
             raise Warning("Support for steer and roll torque disturbance removed!")  # dynamics.py:317-318
         if poles is not None or gains is not None:
             raise NotImplementedError("fixed poles/gains are not implemented; use a pole model")
-        self.stochastic_control_behavior = False
+        self.stochastic_control_behavior = bool(stochastic_control_behavior)
         self.controlparam_filename = controlparam_filename
         self.controlparam_polemodel_component = controlparam_polemodel_component
-        key = (controlparam_filename, controlparam_polemodel_component)
+        self.controlparam_resampling_speedthresh = float(controlparam_resampling_speedthresh)
+        self.controlparam_seed = int(controlparam_seed)
+        self.polemodel = None
+        if self.stochastic_control_behavior:
+            models = load_pole_models()
+            if controlparam_filename not in models:
+                raise FileNotFoundError(
+                    f"Couldn't find Balancing Rider Control Behavior model {controlparam_filename}. "
+                    f"Available models are: {sorted(models)}")
+            self.polemodel = models[controlparam_filename]
+            n_comp = len(self.polemodel["weights"])
+            if controlparam_polemodel_component >= n_comp:                    # reference :1369-1373
+                raise ValueError(f"Balancing Rider Control Behavior model {controlparam_filename} has only {n_comp} "
+                                 f"components but controlparam_polemodel_component is set to "
+                                 f"{controlparam_polemodel_component}!")
+            if self.polemodel["index_given"] != 0 or len(self.polemodel["features"]) != 6 or n_comp > 4:
+                raise NotImplementedError("pole model layout not supported by the device sampler")
+        key = (controlparam_filename, controlparam_polemodel_component if not self.stochastic_control_behavior else 0)
         if key not in self.POLE_REGRESSIONS:
             raise FileNotFoundError(
                 f"Couldn't find Balancing Rider Control Behavior model {key}. "
@@ -352,6 +372,46 @@ class BalancingRiderBicycleParameters(BicycleParameters):
             p.br_B[i] = B[i]
             p.br_pole_icpt[i] = self.pole_intercept[i]
             p.br_pole_coef[i] = self.pole_slope[i]
+        p.br_stochastic = 1 if self.stochastic_control_behavior else 0
+        if self.stochastic_control_behavior:
+            m = self.polemodel
+            cov, mu, w = np.array(m["covariances"]), np.array(m["means"]), np.array(m["weights"])
+            p.br_n_comp = len(w)
+            p.br_resample_thresh = self.controlparam_resampling_speedthresh
+            p.br_seed = self.controlparam_seed & 0xFFFFFFFFFFFFFFFF
+            for i in range(6):
+                p.br_lam[i], p.br_sc_mean[i], p.br_sc_scale[i] = m["lambdas"][i], m["scaler_mean"][i], m["scaler_scale"][i]
+            logf = list(m["log_features"])
+            for i in range(5):                       # pole feature i = model feature i + 1
+                j = logf.index(i + 1) if (i + 1) in logf else -1
+                p.br_log_a[i] = m["log_a"][j] if j >= 0 else 0.0
+                p.br_log_sign[i] = m["log_sign"][j] if j >= 0 else 0.0
+            for c in range(len(w)):
+                # Gaussian component conditioned on the speed (feature 0): mean moves linearly with it, the
+                # covariance is the Schur complement (controlbehavior.py:477-533)
+                var_g, cg = cov[c, 0, 0], cov[c, 1:, 0]
+                L = np.linalg.cholesky(cov[c, 1:, 1:] - np.outer(cg, cg) / var_g)
+                p.br_w[c], p.br_mu_g[c], p.br_var_g[c] = w[c], mu[c, 0], var_g
+                for i in range(5):
+                    p.br_mu[c][i] = mu[c, 1 + i]
+                    p.br_slope[c][i] = cg[i] / var_g
+                    for j in range(i + 1):
+                        p.br_chol[c][i * (i + 1) // 2 + j] = L[i, j]
+
+
+_POLE_MODELS = None
+
+
+def load_pole_models():
+    """The rider-behaviour models packaged with the reference (data/balancingriderparams/*.yaml), as
+    re-serialised numbers: data/pole_models.json."""
+    global _POLE_MODELS
+    if _POLE_MODELS is None:
+        import json
+        import os
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "pole_models.json")) as f:
+            _POLE_MODELS = json.load(f)
+    return _POLE_MODELS
 
 
 def payload_frame(points, margin_rel=0.25, margin_abs=250.0):

@@ -35,6 +35,7 @@ class Vehicle:
     REQUIRED_PARAMS = ("d_arrived_inter", "hfov")
     N_STATES = 4
     STATE_NAMES = ["x[m]", "y[m]", "psi[rad]", "v[m/s]"]
+    _n_created = 0
 
     def __init__(self, s0, id="unknown", route=(), saveForces=False, params=None, dest_force_func=None,
                  rep_force_func=None, uncontrolled=False, uncontrolled_traj=()):
@@ -80,6 +81,9 @@ class Vehicle:
         self._group = None     # engine.AgentGroup
         self._k = -1
         self._record = None    # full per-agent device record kept across re-binding
+        # key of this road user's random stream (stochastic rider behaviour): its serial number in the process
+        self._stream_id = Vehicle._n_created
+        Vehicle._n_created += 1
 
     # ---- state views -------------------------------------------------------------------------
     def _bound(self):
@@ -135,6 +139,8 @@ class Vehicle:
 
     @property
     def traj(self):
+        if self._owner is not None:
+            self._owner.flush_trajectories()          # (no-op unless a trajectory stream is recording)
         return self._traj
 
     # ---- destinations --------------------------------------------------------------------------

@@ -76,6 +76,19 @@ typedef struct CsfAgentParams {
      * steer-torque column br_B, pole(v) = icpt + coef*v (parameters.py:1403-1411) */
     double br_A0[25], br_A1[25], br_A2[25], br_B[5];
     double br_pole_icpt[5], br_pole_coef[5];
+    /* stochastic rider behaviour (parameters.py:1398-1402, controlbehavior.py:1337-1469): the rider-behaviour
+     * model = Gaussian mixture over [speed, p0_real, p1_real, p1_imag, p2_real, p2_imag] in a transformed
+     * feature space; per component c: weight, mean / variance of the speed, the pole features' mean at the
+     * speed's mean, their slope against the speed, and the lower Cholesky factor (row-major, packed) of their
+     * conditional covariance.  Feature transforms: Yeo-Johnson lambda + standard scaler per feature (index 0
+     * = speed), log shift x = sign * (exp(y) + a) per pole feature (sign 0: none). */
+    int32_t br_stochastic, br_n_comp;
+    double br_resample_thresh;
+    uint64_t br_seed;
+    double br_lam[6], br_sc_mean[6], br_sc_scale[6];
+    double br_log_a[5], br_log_sign[5];
+    double br_w[4], br_mu_g[4], br_var_g[4];
+    double br_mu[4][5], br_slope[4][5], br_chol[4][15];
     /* payload packing */
     double q_scale;
     double q_origin[2]; /* origin (m) of the Q-format frame of the f32 payload: xq = rint((x - q_origin[0]) / q_scale) */
@@ -126,8 +139,16 @@ typedef struct CsfAgentState {
                              * planarpoint: [1][n] psi (unwrapped).  Positions live in x/y. */
     double* dyn_v;          /* [n] */
     double* br_gains;       /* [5][n] */
+    /* stochastic rider behaviour: the agent's current pole features, the speed they were drawn at, and
+     * the number of random draws it has consumed (NULL unless CsfAgentParams.br_stochastic) */
+    double* br_poles;       /* [5][n] */
+    double* br_vlast;       /* [n] */
+    int32_t* br_draws;      /* [n] */
+    int64_t* br_stream;     /* [n] key of the rider's random stream (counter-based generator: the draws of a
+                             * rider depend on (seed, br_stream, draw number) only, not on grouping or sharding) */
     /* device-side status word: bit0 non-finite force/state seen, bit1 invalid nav state,
-     * bit2 payload position out of Q range, bit3 degenerate spline (duplicate points) */
+     * bit2 payload position out of Q range, bit3 degenerate spline (duplicate points),
+     * bit4 no valid pole sample in 1000 draws (stochastic rider behaviour) */
     int32_t* status;        /* [1] */
     /* optional mirror in host-mapped (pinned) memory: set to 1 whenever `status` gets a bit, so that the
      * host can poll every step without a copy or a synchronisation; may be NULL */
@@ -285,6 +306,9 @@ int csf_agent_step_f64(int model, const CsfAgentState* st, const CsfAgentParams*
                        csf_stream_t stream);
 /* Build the pair payload from the current state (update_road_user_positions,
  * intersection.py:660-677). */
+/* Gains of every BalancingRider agent for its current speed (what BalancingRiderDynamics.__init__ computes,
+ * dynamics.py:305-306, :602-615); with br_stochastic it also draws the agents' first poles. */
+int csf_br_init(const CsfAgentState* st, const CsfAgentParams* p, csf_stream_t stream);
 int csf_pack_xycs_f32(const CsfAgentState* st, const CsfAgentParams* p, void* xycs, csf_stream_t stream);
 int csf_pack_xycs_f64(const CsfAgentState* st, const CsfAgentParams* p, void* xycs, csf_stream_t stream);
 /* Generic payload packer for road users that are not stepped by this library
@@ -353,6 +377,29 @@ int csf_peer_wait_data(const CsfPeerComm* comm, csf_stream_t stream);
 int csf_peer_signal_read(const CsfPeerComm* comm, csf_stream_t stream);
 int csf_peer_push(const CsfPeerComm* comm, int64_t first_elem, int64_t n_elem, int elem_bytes,
                   csf_stream_t stream);
+
+/* ---- trajectory stream and host bridge -------------------------------------------
+ * Replaces the per-vehicle history writes of the reference (vehicle.py:320-325 `traj[:, i] = s`,
+ * :1407-1413, `trajF`) and the per-vehicle traci.vehicle.moveToXY loop (intersection.py:660-688):
+ *   csf_copy_segments : up to CSF_MAX_COPY_SEGMENTS contiguous device-to-device copies in one launch (the
+ *                       state columns of every model group + the total forces -> one slot of a device ring
+ *                       that the host drains a chunk of steps at a time); lengths are multiples of 4 bytes;
+ *   csf_sumo_pose_*   : out[i] = {x, y, SUMO angle in degrees} (utils.py:119-121 angleSFMtoSUMO) for a
+ *                       batched moveToXY after ONE device-to-host copy per step. */
+#define CSF_MAX_COPY_SEGMENTS 16
+typedef struct CsfCopySegment {
+    const void* src;
+    void* dst;
+    int64_t bytes;
+} CsfCopySegment;
+typedef struct CsfCopySegments {
+    int32_t n;
+    int32_t pad_;
+    CsfCopySegment seg[CSF_MAX_COPY_SEGMENTS];
+} CsfCopySegments;
+int csf_copy_segments(const CsfCopySegments* segs, csf_stream_t stream);
+int csf_sumo_pose_f32(const double* x, const double* y, const void* psi, int64_t n, double* out, csf_stream_t stream);
+int csf_sumo_pose_f64(const double* x, const double* y, const void* psi, int64_t n, double* out, csf_stream_t stream);
 
 /* ---- measurement helper: sustained FP32 FFMA throughput of this device ------------
  * Runs `iters` dependent-chain FFMA rounds on every SM; returns flops executed

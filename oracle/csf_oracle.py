@@ -401,6 +401,11 @@ def balancingrider_poles(pole_model, v):
     return np.array(poles)
 
 
+def ps_poles(f):
+    """[p0_real, p1_real, p1_imag, p2_real, p2_imag] -> the five closed-loop poles (controlbehavior.py:65-89)."""
+    return np.array([f[0] + 0j, f[1] + 1j * f[2], f[1] - 1j * f[2], f[3] + 1j * f[4], f[3] - 1j * f[4]])
+
+
 def place_gain(A, B, poles):
     """ct.place == scipy.signal.place_poles(method='YT').gain_matrix (dynamics.py:1209)."""
     import scipy.signal
@@ -457,7 +462,12 @@ class Agents:
             self.x = np.stack([s[:, 5], -s[:, 4], s[:, 7], -s[:, 6], -s[:, 2], s[:, 0], -s[:, 1]],
                               axis=1)
             self.v = s[:, 3].copy()
-            self.gains = np.stack([self._br_gains(float(v)) for v in self.v])
+            # stochastic rider behaviour (parameters.py:1311, :1398-1402): per-rider pole features, the
+            # speed they were drawn at and the number of draws consumed from the rider's random stream
+            self.br_feats = np.zeros((self.n, 5))
+            self.br_vlast = np.full(self.n, -10000.0)
+            self.br_draws = np.zeros(self.n, int)
+            self.gains = np.stack([self._br_gains(float(v), k) for k, v in enumerate(self.v)])
         if model == "planarpoint":
             self.x = np.stack([self.s[:, 2], self.s[:, 0], self.s[:, 1]], axis=1)   # dynamics.py:987-991
             self.v = self.s[:, 3].copy()
@@ -718,9 +728,20 @@ class Agents:
             self.x[k] = (s[4], 0, s[5], 0, s[2])
         self._record(k)
 
-    def _br_gains(self, v):
-        """BalancingRiderDynamics._get_gains, dynamics.py:602-615."""
+    def _br_gains(self, v, k=0):
+        """BalancingRiderDynamics._get_gains, dynamics.py:602-615 (update_control_params(v), then place)."""
         A, B = balancingrider_matrices(self.p.bike, v)
+        if getattr(self.p, "stochastic", False):
+            # parameters.py:1398-1402: new, independent poles when the speed has moved by more than the
+            # threshold since the last draw; otherwise the rider keeps its poles
+            if abs(v - self.br_vlast[k]) > self.p.resample_thresh:
+                from . import pole_sampling as ps
+                m = ps.load_model(self.p.pole_model_file)
+                f, used = ps.sample_features(m, v, self.p.seed, self.p.agent_offset + k, int(self.br_draws[k]))
+                self.br_feats[k] = f
+                self.br_draws[k] += used
+                self.br_vlast[k] = v
+            return place_gain(A, B, ps_poles(self.br_feats[k]))
         return place_gain(A, B, balancingrider_poles(self.p.pole_model, v))
 
     def step_balancingrider(self, k, Fx, Fy):
@@ -732,7 +753,7 @@ class Agents:
         v = thresh(self.v[k] + p.t_s * a, p.v_max_riding)
         vbar = (v + self.s[k, 3]) / 2
         if v != self.v[k]:
-            self.gains[k] = self._br_gains(vbar)
+            self.gains[k] = self._br_gains(vbar, k)
         g = self.gains[k]
         x = self.x[k]
         psi_F = limit_angle(math.atan2(-Fy, Fx))                      # :661-671
