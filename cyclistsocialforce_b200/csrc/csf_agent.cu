@@ -459,191 +459,207 @@ template <typename T> __device__ __forceinline__ void control_move(Agent<T>& a, 
 }
 
 // ----------------------------------------------------------------------------------------
-// small dense double-precision linear algebra (per-agent, local arrays)
+// small dense double-precision linear algebra (per-agent; every loop unrolled, so the arrays live in
+// registers -- no local memory)
 // ----------------------------------------------------------------------------------------
-template <int N> __device__ void mat_mul(const double* A, const double* B, double* C) {
-    for (int i = 0; i < N; ++i)
-        for (int j = 0; j < N; ++j) {
-            double s = 0.0;
-            for (int k = 0; k < N; ++k) s = fma(A[i * N + k], B[k * N + j], s);
-            C[i * N + j] = s;
-        }
-}
-// E = exp(M) for the 6x6 augmented matrix [[A_c t, B_c t],[0,0]]: degree-13 Pade approximant with
-// scaling and squaring (Higham 2005, the algorithm behind scipy.linalg.expm that the reference
-// reaches through control.forced_response, vehicle.py:1835-1842).
-__device__ void expm6(const double* Min, double* E) {
-    constexpr int N = 6;
-    const double b[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800.,
-                          129060195264000.,   10559470521600.,    670442572800.,     33522128640.,
-                          1323241920.,        40840800.,          960960.,           16380.,
-                          182.,               1.};
-    double nrm = 0.0;
-    for (int j = 0; j < N; ++j) {
-        double c = 0.0;
-        for (int i = 0; i < N; ++i) c += fabs(Min[i * N + j]);
-        nrm = fmax(nrm, c);
-    }
-    int s = 0;
-    double sc = 1.0;
-    while (nrm * sc > 5.371920351148152 && s < 60) { sc *= 0.5; ++s; }
-    double A[N * N], A2[N * N], A4[N * N], A6[N * N], U[N * N], V[N * N], W[N * N];
-    for (int i = 0; i < N * N; ++i) A[i] = Min[i] * sc;
-    mat_mul<N>(A, A, A2);
-    mat_mul<N>(A2, A2, A4);
-    mat_mul<N>(A4, A2, A6);
-    for (int i = 0; i < N * N; ++i) W[i] = b[13] * A6[i] + b[11] * A4[i] + b[9] * A2[i];
-    mat_mul<N>(A6, W, V);  // V as scratch
-    for (int i = 0; i < N * N; ++i)
-        W[i] = V[i] + b[7] * A6[i] + b[5] * A4[i] + b[3] * A2[i] + ((i % (N + 1) == 0) ? b[1] : 0.0);
-    mat_mul<N>(A, W, U);
-    for (int i = 0; i < N * N; ++i) W[i] = b[12] * A6[i] + b[10] * A4[i] + b[8] * A2[i];
-    mat_mul<N>(A6, W, V);
-    for (int i = 0; i < N * N; ++i)
-        V[i] += b[6] * A6[i] + b[4] * A4[i] + b[2] * A2[i] + ((i % (N + 1) == 0) ? b[0] : 0.0);
-    // solve (V - U) R = (V + U): P := V - U, Q := V + U (in A2, A4), partial pivoting
-    double* P = A2;
-    double* Q = A4;
-    for (int i = 0; i < N * N; ++i) { P[i] = V[i] - U[i]; Q[i] = V[i] + U[i]; }
-    for (int k = 0; k < N; ++k) {
-        int piv = k;
-        double best = fabs(P[k * N + k]);
-        for (int i = k + 1; i < N; ++i)
-            if (fabs(P[i * N + k]) > best) { best = fabs(P[i * N + k]); piv = i; }
-        if (piv != k)
-            for (int j = 0; j < N; ++j) {
-                double t = P[k * N + j]; P[k * N + j] = P[piv * N + j]; P[piv * N + j] = t;
-                t = Q[k * N + j]; Q[k * N + j] = Q[piv * N + j]; Q[piv * N + j] = t;
-            }
-        const double inv = 1.0 / P[k * N + k];
-        for (int i = k + 1; i < N; ++i) {
-            const double f = P[i * N + k] * inv;
-            for (int j = k; j < N; ++j) P[i * N + j] -= f * P[k * N + j];
-            for (int j = 0; j < N; ++j) Q[i * N + j] -= f * Q[k * N + j];
-        }
-    }
-    for (int k = N - 1; k >= 0; --k) {
-        const double inv = 1.0 / P[k * N + k];
-        for (int j = 0; j < N; ++j) {
-            double t = Q[k * N + j];
-            for (int i = k + 1; i < N; ++i) t -= P[k * N + i] * E[i * N + j];
-            E[k * N + j] = t * inv;
-        }
-    }
-    for (int q = 0; q < s; ++q) {
-        mat_mul<N>(E, E, W);
-        for (int i = 0; i < N * N; ++i) E[i] = W[i];
-    }
-}
-// solve A x = b (5x5, partial pivoting), A destroyed
-__device__ void solve5(double* A, double* b, double* x) {
+// solve A x = b (5x5, partial pivoting by predicated row swaps), A and b destroyed
+__device__ __forceinline__ void solve5(double (&A)[5][5], double (&b)[5], double (&x)[5]) {
     constexpr int N = 5;
+#pragma unroll
     for (int k = 0; k < N; ++k) {
-        int piv = k;
-        double best = fabs(A[k * N + k]);
-        for (int i = k + 1; i < N; ++i)
-            if (fabs(A[i * N + k]) > best) { best = fabs(A[i * N + k]); piv = i; }
-        if (piv != k) {
-            for (int j = 0; j < N; ++j) { double t = A[k * N + j]; A[k * N + j] = A[piv * N + j]; A[piv * N + j] = t; }
-            double t = b[k]; b[k] = b[piv]; b[piv] = t;
-        }
-        const double inv = 1.0 / A[k * N + k];
+        // bring the largest |A[i][k]|, i >= k, to row k: compare-and-swap with every later row (the first
+        // of several equal candidates stays, as in the reference's LAPACK pivoting)
+#pragma unroll
         for (int i = k + 1; i < N; ++i) {
-            const double f = A[i * N + k] * inv;
-            for (int j = k; j < N; ++j) A[i * N + j] -= f * A[k * N + j];
-            b[i] -= f * b[k];
+            const bool sw = fabs(A[i][k]) > fabs(A[k][k]);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const double u = A[k][j], w = A[i][j];
+                A[k][j] = sw ? w : u;
+                A[i][j] = sw ? u : w;
+            }
+            const double u = b[k], w = b[i];
+            b[k] = sw ? w : u;
+            b[i] = sw ? u : w;
+        }
+        const double inv = 1.0 / A[k][k];
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+            const double f = A[i][k] * inv;
+#pragma unroll
+            for (int j = k + 1; j < N; ++j) A[i][j] = fma(-f, A[k][j], A[i][j]);
+            b[i] = fma(-f, b[k], b[i]);
         }
     }
+#pragma unroll
     for (int k = N - 1; k >= 0; --k) {
-        double s = b[k];
-        for (int j = k + 1; j < N; ++j) s -= A[k * N + j] * x[j];
-        x[k] = s / A[k * N + k];
+        double t = b[k];
+#pragma unroll
+        for (int j = k + 1; j < N; ++j) t = fma(-A[k][j], x[j], t);
+        x[k] = t / A[k][k];
     }
 }
 
 // ----------------------------------------------------------------------------------------
 // InvPendulumBicycle, vehicle.py:1738-1950 (dynamics in double in both builds)
 // ----------------------------------------------------------------------------------------
-__device__ void invpend_yaw_step(const CsfAgentParams& p, double v, double psi_d, double* x /*[5]*/) {
+// floor(log2 |a|) of a finite non-zero double, as an integer (0 for a == 0)
+__device__ __forceinline__ int exp2_of(double a) { return a == 0.0 ? 0 : ilogb(a); }
+
+// x+ = [I 0] exp(M) [x; psi_d],  M = [[A_c t_s, B_c t_s], [0, 0]]  -- what ct.forced_response returns for a
+// constant input over one sample (vehicle.py:1835-1842).  The reference forms the full matrix exponential
+// (scipy's Pade-13 scaling-and-squaring); only its ACTION on one vector is needed, and M has 12 non-zero
+// entries.  |M|_1 is 50...400 (steer-torque gains over a small steering inertia) although its spectral
+// radius is below 1: M is badly scaled, not large.  A diagonal similarity by powers of two -- exact in
+// floating point -- brings |D^-1 M D|_1 to 2...4; then  exp(M) y = D (T_24(D^-1 M D / n))^n D^-1 y  with the
+// degree-24 Taylor polynomial in Horner form and n = 1, 2, 4 ... sub-steps so that the norm per sub-step is
+// at most 2 (truncation 2^25/25! < 3e-18).  ~16 FMAs per term, everything in registers; agrees with
+// scipy.linalg.expm to 1e-15 relative (tests: invpendulum crowds against the oracle).
+__device__ __forceinline__ void invpend_yaw_step(const CsfAgentParams& p, double v, double psi_d, double (&x)[5]) {
     // open loop (:1738-1768) with time-varying K, K tau_2, tau_3 (parameters.py:1850-1855)
     const double l = p.l;
     const double K_tau_2 = (v * p.l_2) / (p.g * l), K = (v * v) / (p.g * l), tau_3 = l / v;
     const double iv = 1.0 / v;
     const double vd[4] = {1.0, iv, iv * iv, iv * iv * iv};
     double kx[5], ku = 0.0;
+#pragma unroll
     for (int r = 0; r < 5; ++r) {
         kx[r] = 0.0;
+#pragma unroll
         for (int c = 0; c < 4; ++c) kx[r] += p.kx_table[r][c] * vd[c];
     }
+#pragma unroll
     for (int c = 0; c < 4; ++c) ku += p.ku_table[c] * vd[c];
     const double bI = 1.0 / p.i_steer;
     const double ts = p.t_s;
-    double Mx[36];
-    for (int i = 0; i < 36; ++i) Mx[i] = 0.0;
     // A_c = A - B K_x ; B_c = K_u B  (rows scaled by t_s)
-    Mx[0 * 6 + 1] = ts;
-    for (int c = 0; c < 5; ++c) Mx[1 * 6 + c] = -bI * kx[c] * ts;
-    Mx[1 * 6 + 1] += (-p.c_steer * bI) * ts;
-    Mx[1 * 6 + 5] = ku * bI * ts;
-    Mx[2 * 6 + 3] = ts;
-    Mx[3 * 6 + 0] = -K / p.tau_1_squared * ts;
-    Mx[3 * 6 + 1] = -K_tau_2 / p.tau_1_squared * ts;
-    Mx[3 * 6 + 2] = 1.0 / p.tau_1_squared * ts;
-    Mx[4 * 6 + 0] = 1.0 / tau_3 * ts;
-    double E[36];
-    expm6(Mx, E);
-    double xn[5];
-    for (int r = 0; r < 5; ++r) {
-        double s = E[r * 6 + 5] * psi_d;
-        for (int c = 0; c < 5; ++c) s = fma(E[r * 6 + c], x[c], s);
-        xn[r] = s;
+    double m01 = ts, m23 = ts;
+    double m1[6];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) m1[c] = -bI * kx[c] * ts;
+    m1[1] += (-p.c_steer * bI) * ts;
+    m1[5] = ku * bI * ts;
+    double m30 = -K / p.tau_1_squared * ts, m31 = -K_tau_2 / p.tau_1_squared * ts, m32 = 1.0 / p.tau_1_squared * ts;
+    double m40 = 1.0 / tau_3 * ts;
+    // balancing exponents e_i (d_i = 2^e_i, d_0 = 1): equalise the magnitudes of the entry pairs (0,1)/(1,0),
+    // (3,1)/(1,3), (3,2)/(2,3), (4,0)/(1,4); the input column gets magnitude ~1
+    const int e1 = (exp2_of(m1[0]) - exp2_of(m01)) >> 1;
+    const int e3 = e1 + ((exp2_of(m31) - exp2_of(m1[3])) >> 1);
+    const int e2 = e3 - ((exp2_of(m32) - exp2_of(m23)) >> 1);
+    const int e4 = (e1 + exp2_of(m40) - exp2_of(m1[4])) >> 1;
+    const int e5 = e1 - exp2_of(m1[5]);
+    const int e[6] = {0, e1, e2, e3, e4, e5};
+    m01 = scalbn(m01, e[1] - e[0]);
+    m23 = scalbn(m23, e[3] - e[2]);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) m1[c] = scalbn(m1[c], e[c] - e[1]);
+    m30 = scalbn(m30, e[0] - e[3]);
+    m31 = scalbn(m31, e[1] - e[3]);
+    m32 = scalbn(m32, e[2] - e[3]);
+    m40 = scalbn(m40, e[0] - e[4]);
+    // 1-norm of the balanced matrix -> sub-steps
+    double nrm = fabs(m1[0]) + fabs(m30) + fabs(m40);
+    nrm = fmax(nrm, fabs(m01) + fabs(m1[1]) + fabs(m31));
+    nrm = fmax(nrm, fabs(m1[2]) + fabs(m32));
+    nrm = fmax(nrm, fabs(m1[3]) + fabs(m23));
+    nrm = fmax(nrm, fmax(fabs(m1[4]), fabs(m1[5])));
+    int ns = 1, sh = 0;
+    while (nrm > 2.0 * ns && sh < 20) { ns <<= 1; ++sh; }
+    m01 = scalbn(m01, -sh);
+    m23 = scalbn(m23, -sh);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) m1[c] = scalbn(m1[c], -sh);
+    m30 = scalbn(m30, -sh);
+    m31 = scalbn(m31, -sh);
+    m32 = scalbn(m32, -sh);
+    m40 = scalbn(m40, -sh);
+    double y[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) y[r] = scalbn(x[r], -e[r]);
+    const double c15 = m1[5] * scalbn(psi_d, -e[5]);       // the input is constant over the step
+    for (int q = 0; q < ns; ++q) {
+        double r0 = y[0], r1 = y[1], r2 = y[2], r3 = y[3], r4 = y[4];
+#pragma unroll
+        for (int kk = 24; kk >= 1; --kk) {
+            const double ik = 1.0 / (double)kk;              // (compile-time constant: the loop is unrolled)
+            const double t0 = m01 * r1;
+            const double t1 = fma(m1[0], r0, fma(m1[1], r1, fma(m1[2], r2, fma(m1[3], r3, fma(m1[4], r4, c15)))));
+            const double t2 = m23 * r3;
+            const double t3 = fma(m30, r0, fma(m31, r1, m32 * r2));
+            const double t4 = m40 * r0;
+            r0 = fma(t0, ik, y[0]);
+            r1 = fma(t1, ik, y[1]);
+            r2 = fma(t2, ik, y[2]);
+            r3 = fma(t3, ik, y[3]);
+            r4 = fma(t4, ik, y[4]);
+        }
+        y[0] = r0; y[1] = r1; y[2] = r2; y[3] = r3; y[4] = r4;
     }
-    for (int r = 0; r < 5; ++r) x[r] = xn[r];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) x[r] = scalbn(y[r], e[r]);
 }
 
 // ----------------------------------------------------------------------------------------
 // BalancingRiderBicycle gain design: Ackermann's formula == ct.place for a single input
-// (dynamics.py:602-615, :1205-1209).  K = e_n^T C^-1 phi(A)
+// (dynamics.py:602-615, :1205-1209).  K = e_n^T C^-1 phi(A), evaluated as a ROW VECTOR pushed through the
+// factors of phi -- five vector-matrix products instead of matrix-matrix products; A (25 doubles) and a
+// few 5-vectors, all in registers.
 // ----------------------------------------------------------------------------------------
-__device__ void br_matrix(const CsfAgentParams& p, double v, double* A) {
-    for (int i = 0; i < 25; ++i) A[i] = p.br_A0[i] + v * p.br_A1[i] + v * v * p.br_A2[i];
+__device__ __forceinline__ void br_matrix(const CsfAgentParams& p, double v, double (&A)[5][5]) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) A[i][j] = fma(v * v, p.br_A2[i * 5 + j], fma(v, p.br_A1[i * 5 + j], p.br_A0[i * 5 + j]));
 }
-__device__ void br_gains(const CsfAgentParams& p, double v, const double* f /* pole features */, double* K) {
-    constexpr int N = 5;
-    double A[25], T1[25], T2[25], Phi[25];
-    br_matrix(p, v, A);
-    // phi(A) = (A - p0 I) (A^2 - 2 re1 A + |p1|^2 I) (A^2 - 2 re2 A + |p2|^2 I)
-    double A2[25];
-    mat_mul<N>(A, A, A2);
-    for (int i = 0; i < 25; ++i) Phi[i] = A[i] - ((i % 6 == 0) ? f[0] : 0.0);
-    for (int q = 0; q < 2; ++q) {
-        const double re = f[1 + 2 * q], im = f[2 + 2 * q];
-        for (int i = 0; i < 25; ++i) T1[i] = A2[i] - 2.0 * re * A[i] + ((i % 6 == 0) ? (re * re + im * im) : 0.0);
-        mat_mul<N>(Phi, T1, T2);
-        for (int i = 0; i < 25; ++i) Phi[i] = T2[i];
+// w^T A
+__device__ __forceinline__ void vec_mat5(const double (&w)[5], const double (&A)[5][5], double (&out)[5]) {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) t = fma(w[i], A[i][j], t);
+        out[j] = t;
     }
-    // controllability matrix columns b, Ab, ..., A^4 b
-    double C[25], col[5], nxt[5];
+}
+__device__ __forceinline__ void br_gains(const CsfAgentParams& p, double v, const double* f /* pole features */, double* K) {
+    double A[5][5];
+    br_matrix(p, v, A);
+    // controllability matrix C = [b, Ab, ..., A^4 b]; w^T = e_5^T C^-1  <=>  C^T w = e_5
+    double Ct[5][5], col[5], nxt[5];
+#pragma unroll
     for (int i = 0; i < 5; ++i) col[i] = p.br_B[i];
+#pragma unroll
     for (int c = 0; c < 5; ++c) {
-        for (int i = 0; i < 5; ++i) C[i * 5 + c] = col[i];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) Ct[c][i] = col[i];
+#pragma unroll
         for (int i = 0; i < 5; ++i) {
-            double s = 0.0;
-            for (int j = 0; j < 5; ++j) s = fma(A[i * 5 + j], col[j], s);
-            nxt[i] = s;
+            double t = 0.0;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) t = fma(A[i][j], col[j], t);
+            nxt[i] = t;
         }
+#pragma unroll
         for (int i = 0; i < 5; ++i) col[i] = nxt[i];
     }
-    // w^T = e_5^T C^-1  <=>  C^T w = e_5
-    double Ct[25], e[5] = {0, 0, 0, 0, 1}, w[5];
-    for (int i = 0; i < 5; ++i)
-        for (int j = 0; j < 5; ++j) Ct[i * 5 + j] = C[j * 5 + i];
+    double e[5] = {0, 0, 0, 0, 1}, w[5];
     solve5(Ct, e, w);
-    for (int j = 0; j < 5; ++j) {
-        double s = 0.0;
-        for (int i = 0; i < 5; ++i) s = fma(w[i], Phi[i * 5 + j], s);
-        K[j] = s;
+    // K = w^T (A - p0 I) (A^2 - 2 re1 A + |p1|^2 I) (A^2 - 2 re2 A + |p2|^2 I)
+    double u[5], u2[5];
+    vec_mat5(w, A, u);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) w[j] = fma(-f[0], w[j], u[j]);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const double re = f[1 + 2 * q], im = f[2 + 2 * q];
+        vec_mat5(w, A, u);
+        vec_mat5(u, A, u2);
+        const double m2 = fma(re, re, im * im);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) w[j] = fma(m2, w[j], fma(-2.0 * re, u[j], u2[j]));
     }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) K[j] = w[j];
 }
 
 // ----------------------------------------------------------------------------------------
@@ -953,16 +969,17 @@ __device__ __forceinline__ bool agent_body(const CsfAgentState& st, const CsfAge
                 for (int r = 0; r < 5; ++r) g[r] = st.br_gains[(size_t)r * st.n + k];
             const double psi_F = limit_angle(atan2(-(double)Fy, (double)Fx));  // :661-671
             const double psi_c = xb[4] + angle_difference(xb[4], psi_F);
-            double A[25], L[25], rhs[5], xn[5];
+            double A[5][5], L[5][5], rhs[5], xn[5];
             br_matrix(p, vbar, A);
             const double h = p.t_s;
-            for (int i = 0; i < 5; ++i)
-                for (int j = 0; j < 5; ++j) A[i * 5 + j] -= p.br_B[i] * g[j];  // A_c
+#pragma unroll
             for (int i = 0; i < 5; ++i) {
                 double s = h * p.br_B[i] * g[4] * psi_c;
+#pragma unroll
                 for (int j = 0; j < 5; ++j) {
-                    L[i * 5 + j] = ((i == j) ? 1.0 : 0.0) - 0.5 * h * A[i * 5 + j];
-                    s += (((i == j) ? 1.0 : 0.0) + 0.5 * h * A[i * 5 + j]) * xb[j];
+                    const double ac = A[i][j] - p.br_B[i] * g[j];          // A_c
+                    L[i][j] = ((i == j) ? 1.0 : 0.0) - 0.5 * h * ac;
+                    s += (((i == j) ? 1.0 : 0.0) + 0.5 * h * ac) * xb[j];
                 }
                 rhs[i] = s;
             }

@@ -508,7 +508,10 @@ class Engine:
         if self.n_total > 1 and scenario_size is None:
             for s, c, _, _ in self.classes:
                 wsb = max(wsb, int(self.lib.csf_pair_workspace_bytes(c, self.n_agents, 4 if self.f32 else 8)))
-        self.tiled = (scenario_size is None and self.n_total > 1 and not self._ecc and
+        # tiled + culled kernel for every class with the TwoD field; Bicycle-field (v0.1) classes of a mixed
+        # crowd go through their dense kernel and add to the same sums
+        self.tiled = (scenario_size is None and self.n_total > 1 and
+                      any(fp.field_kind == 0 for _, _, _, fp in self.classes) and
                       (pair_mode == "tiled" or (pair_mode == "auto" and self.n_total >= 2048)))
         self.pair_stats = torch.zeros(16 + 4 * 16384, dtype=torch.int64, device=self.device) if count_pairs else None
         self._tiles = []

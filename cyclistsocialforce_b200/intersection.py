@@ -175,7 +175,8 @@ class SocialForceIntersection:
 
     def __init__(self, vehicleList, id="", priority_rule="unregulated", animate=False, axes=None,
                  activate_sumo_cosimulation=False, net=None, road_elements=(), bicycle_drawing_kwargs=None,
-                 dtype=torch.float32, record_traj=None, device="cuda", sumo_client=None, _private=False):
+                 dtype=torch.float32, record_traj=None, device="cuda", sumo_client=None, traj_chunk_steps=None,
+                 _private=False):
         if animate:
             raise NotImplementedError("matplotlib animation is outside the accelerated stepping path")
         if activate_sumo_cosimulation and sumo_client is None:
@@ -193,6 +194,7 @@ class SocialForceIntersection:
         self.ax = axes
         self.activate_sumo_cosimulation = bool(activate_sumo_cosimulation)
         self._traj_stream = None
+        self._traj_chunk_steps = traj_chunk_steps
         self.road_elements = list(road_elements)
         self.is_first_step = True
         self.hist_n_vecs = []
@@ -259,7 +261,7 @@ class SocialForceIntersection:
         self._traj_stream = None
         if self.record_traj and self.n_bikes > 64 and self._engine is not None:
             from .trajstream import TrajectoryStream
-            self._traj_stream = TrajectoryStream(self._engine)
+            self._traj_stream = TrajectoryStream(self._engine, chunk_steps=self._traj_chunk_steps)
             self._traj_groups = list(self._groups)
 
     # ---- churn without a host round trip of the crowd (reference :458-539, :576-634) -------------------
@@ -434,6 +436,7 @@ class SocialForceIntersection:
     # ---- road users --------------------------------------------------------------------------------------
     def add_road_user(self, user):
         """reference :458-539."""
+        self.flush_trajectories()                 # (before the device groups are re-bound)
         self.vehicles.append(user)
         if not self._device_add(user):
             self._rebuild()
@@ -443,6 +446,7 @@ class SocialForceIntersection:
 
     def remove_road_user(self, i):
         """reference :576-616."""
+        self.flush_trajectories()
         v = self.vehicles.pop(i)
         if not self._device_remove([v]):
             self.vehicles.insert(i, v)
@@ -454,6 +458,7 @@ class SocialForceIntersection:
 
     def remove_road_users_by_id(self, ids):
         """reference :618-634."""
+        self.flush_trajectories()
         gone = [v for v in self.vehicles if v.id in ids]
         keep = [v for v in self.vehicles if v.id not in ids]
         self.vehicles = keep

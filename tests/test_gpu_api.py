@@ -120,6 +120,63 @@ def test_add_and_remove_road_users():
     assert [v.i for v in ins.vehicles] == [55] * 12
 
 
+@pytest.mark.parametrize("cls_name,model", [("TwoDBicycle", "twod"), ("InvPendulumBicycle", "invpendulum")])
+def test_churn_against_the_oracle(cls_name, model):
+    """add_road_user / remove_road_user / remove_road_users_by_id (reference intersection.py:458-539,
+    :576-634) in the middle of a run, against the ORACLE doing the same list operations on per-vehicle
+    state (the reference's vehicles own their state): the road users that stay keep their navigation
+    machine, history and dynamic state; a road user that joins starts from its constructor state."""
+    import cyclistsocialforce_b200.vehicle as V
+    cls = getattr(V, cls_name)
+    ns = cls.N_STATES
+    n = 14
+    s0, q = co.synthetic_crowd(n + 2, seed=6, spacing=3.0, n_states=ns)
+
+    def mk(k):
+        b = cls(tuple(s0[k]), id=f"v{k}")
+        b.setDestinations(q[k, :, 0], q[k, :, 1])
+        return b
+
+    def mk_oracle(k):
+        A = co.Agents(model, s0[k:k + 1])
+        A.set_destinations(0, q[k, :, 0], q[k, :, 1])
+        A.tag = f"v{k}"
+        return A
+
+    ins = SocialForceIntersection([mk(k) for k in range(n)], dtype=torch.float64)
+    W = co.World([mk_oracle(k) for k in range(n)])
+
+    def check(tag):
+        got = {v.id: v.s for v in ins.vehicles}
+        assert [v.id for v in ins.vehicles] == [g.tag for g in W.groups], tag
+        for g in W.groups:
+            assert np.abs(got[g.tag] - g.s[0]).max() < 1e-8, (tag, g.tag, np.abs(got[g.tag] - g.s[0]).max())
+
+    def run(k):
+        for _ in range(k):
+            ins.step()
+            W.step()
+
+    run(12)
+    check("before churn")
+    ins.remove_road_user(3)                                  # reference :576-616 pops index 3
+    W.groups.pop(3)
+    run(9)
+    check("after remove_road_user")
+    ins.add_road_user(mk(n))                                 # a fresh road user in the middle of the crowd
+    W.groups.append(mk_oracle(n))
+    run(11)
+    check("after add_road_user")
+    ins.remove_road_users_by_id(["v0", "v7", f"v{n}"])       # :618-634
+    W.groups = [g for g in W.groups if g.tag not in ("v0", "v7", f"v{n}")]
+    ins.add_road_user(mk(n + 1))
+    W.groups.append(mk_oracle(n + 1))
+    run(15)
+    check("after remove_road_users_by_id + add")
+    assert ins.n_bikes == n - 2 and ins.hist_n_vecs[-1] == n - 2
+    ins.check_status()
+
+
 def test_vehicle_hooks_match_oracle():
     """Vehicle.calcRepulsiveForce / calcDestinationForce / step used on their own."""
     b = TwoDBicycle((1.0, 2.0, 0.4, 5.0, 0.0), id="solo")

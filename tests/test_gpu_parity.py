@@ -374,3 +374,39 @@ def test_tiled_clusters_with_gaps(dtype):
     assert err.max() < (F64_TOL if dtype == torch.float64 else F32_TOL)
     assert _vec_rel(res["tiled"][0], res["dense"][0], 1e-3).max() < (1e-10 if dtype == torch.float64 else 2e-5)
     assert np.abs(res["tiled"][1] - res["dense"][1]).max() < (1e-9 if dtype == torch.float64 else 2e-3)
+
+
+def test_mixed_crowd_with_v01_bicycles_keeps_the_tiled_kernel():
+    """A crowd that contains ``Bicycle`` (v0.1 elliptic field, vehicle.py:1054-1147) road users next to
+    TwoD-field ones: the TwoD-field classes still go through the tiled + culled kernel, the Bicycle class
+    through its dense kernel, both into the same sums -- equal to the all-dense engine and to the oracle."""
+    from cyclistsocialforce_b200 import parameters as P
+    from cyclistsocialforce_b200.engine import AgentGroup, Engine
+    from cyclistsocialforce_b200.synthetic import queues_with_start
+    n, nb = 2300, 180
+    s0, q = co.synthetic_crowd(n, seed=13, spacing=3.0)
+    s0[:nb, 3] = np.linspace(1.0, 9.0, nb)                     # speed-dependent eccentricity
+    res = {}
+    for mode in ("dense", "tiled"):
+        gb = AgentGroup("bicycle", s0[:nb], P.BicycleParameters(), destqueues=list(queues_with_start(s0[:nb], q[:nb])),
+                        dtype=torch.float64)
+        gt = AgentGroup("twod", s0[nb:], P.InvPendulumBicycleParameters(),
+                        destqueues=list(queues_with_start(s0[nb:], q[nb:])), dtype=torch.float64)
+        eng = Engine([gb, gt], dtype=torch.float64, pair_mode=mode)
+        assert eng.tiled == (mode == "tiled")
+        for _ in range(3):
+            eng.step()
+        res[mode] = (np.vstack([gb.states_numpy(), gt.states_numpy()]), eng.force.cpu().numpy())
+    assert np.abs(res["dense"][0] - res["tiled"][0]).max() < 1e-10
+    assert np.abs(res["dense"][1] - res["tiled"][1]).max() < 1e-10
+    Ab = co.Agents("bicycle", s0[:nb])
+    At = co.Agents("twod", s0[nb:])
+    for k in range(nb):
+        Ab.set_destinations(k, q[k, :, 0], q[k, :, 1])
+    for k in range(n - nb):
+        At.set_destinations(k, q[nb + k, :, 0], q[nb + k, :, 1])
+    W = co.World([Ab, At])
+    for _ in range(3):
+        W.step()
+    ref = np.vstack([Ab.s, At.s])
+    assert np.abs(res["tiled"][0] - ref).max() < 1e-9

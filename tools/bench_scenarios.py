@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--model", default="invpendulum")
+    ap.add_argument("--no-graph", action="store_true", help="kernel-by-kernel launches (for ncu)")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     lr = int(os.environ.get("LOCAL_RANK", 0))
@@ -52,7 +53,7 @@ def main():
     params = dict(twod=P.InvPendulumBicycleParameters, invpendulum=P.InvPendulumBicycleParameters,
                   planarpoint=P.PlanarPointBicycleParameters, balancingrider=P.BalancingRiderBicycleParameters)[a.model]()
     g = AgentGroup(a.model, s0, params, destqueues=list(q), dtype=torch.float32, device=dev)
-    eng = Engine([g], dtype=torch.float32, device=dev, scenario_size=a.per, extent=2000.0, graph=True)
+    eng = Engine([g], dtype=torch.float32, device=dev, scenario_size=a.per, extent=2000.0, graph=not a.no_graph)
     for _ in range(a.warmup):
         eng.step()
     torch.cuda.synchronize(dev)
