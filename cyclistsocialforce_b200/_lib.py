@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcsf_b200.so")
+# (CSF_B200_LIB: another build of the same library, for tuning experiments -- tools/gpu/*.sh)
+LIB_PATH = os.environ.get("CSF_B200_LIB") or os.path.join(HERE, "libcsf_b200.so")
 
 MODEL_IDS = dict(twod=0, invpendulum=1, balancingrider=2, planarpoint=3, bicycle=4)
 
@@ -61,7 +62,8 @@ class CsfAgentParams(C.Structure):
         ("br_A0", C.c_double * 25), ("br_A1", C.c_double * 25), ("br_A2", C.c_double * 25),
         ("br_B", C.c_double * 5),
         ("br_pole_icpt", C.c_double * 5), ("br_pole_coef", C.c_double * 5),
-        ("br_stochastic", C.c_int32), ("br_n_comp", C.c_int32), ("br_resample_thresh", C.c_double),
+        ("br_stochastic", C.c_int32), ("br_n_comp", C.c_int32), ("br_fixed_gains", C.c_int32), ("br_pad_", C.c_int32),
+        ("br_resample_thresh", C.c_double),
         ("br_seed", C.c_uint64),
         ("br_lam", C.c_double * 6), ("br_sc_mean", C.c_double * 6), ("br_sc_scale", C.c_double * 6),
         ("br_log_a", C.c_double * 5), ("br_log_sign", C.c_double * 5),

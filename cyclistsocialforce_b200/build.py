@@ -38,7 +38,13 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, out: str | None = None, defines: str | None = None,
+          sources=None) -> str:
+    """``out`` / ``defines`` / ``sources``: a variant build next to the product library (tuning experiments):
+    the listed sources are compiled with the extra defines into objects of their own, the rest is linked
+    from the product build's objects."""
+    if out is not None:
+        return _build_variant(out, defines or "", sources or ["csf_pair_tiled.cu"])
     if not force and not needs_build():
         return LIB
     nvcc = _nvcc()
@@ -64,6 +70,32 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("link failed:\n" + r.stdout)
     os.replace(LIB + ".tmp", LIB)
     return LIB
+
+
+def _build_variant(out, defines, sources):
+    build()                                           # the product objects must exist
+    nvcc = _nvcc()
+    tag = os.path.splitext(os.path.basename(out))[0]
+    objs = []
+    for src in SOURCES:
+        if src in sources:
+            obj = os.path.join(CSRC, src.replace(".cu", f".{tag}.o"))
+            cmd = [nvcc, *NVCC_FLAGS, *defines.split(), "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c",
+                   os.path.join(CSRC, src), "-o", obj]
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout)
+            objs.append(obj)
+        else:
+            objs.append(os.path.join(CSRC, src.replace(".cu", ".o")))
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout)
+    for o in objs:
+        if f".{tag}.o" in o:
+            os.remove(o)
+    return out
 
 
 if __name__ == "__main__":

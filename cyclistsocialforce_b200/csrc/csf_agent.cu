@@ -960,7 +960,7 @@ __device__ __forceinline__ bool agent_body(const CsfAgentState& st, const CsfAge
             const double vbar = 0.5 * (v + vold);  // vehicle.s[3] == dynamics.v in the reference
             double g[5], xb[5];
             for (int r = 0; r < 5; ++r) xb[r] = st.dyn_x[(size_t)r * st.n + k];
-            if (v != vold) {  // :680-681
+            if (v != vold && !p.br_fixed_gains) {  // :680-681 (fixed gains: dynamics.py:606-607)
                 double pf[5];
                 br_poles_for(p, st, k, vbar, pf, &a.flags);
                 br_gains(p, vbar, pf, g);

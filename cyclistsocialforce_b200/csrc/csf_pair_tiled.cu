@@ -15,16 +15,17 @@
 //   producer (1 warp)  fetches items from an atomic counter, tests chunk and tile circles against
 //                      the block circle and streams the tiles that can be within d_cut of the block
 //                      into a ring of shared-memory stages (8 tiles each) with 1-D TMA bulk copies;
-//   filter   (2 warps) take the stages, drop every source whose field cannot reach the block circle
+//   filter   (2 warps; 4 in the wide shape) take the stages, drop every source whose field cannot reach the block circle
 //                      (lobe test, packed FP32x2) and append the survivors, in stream order, to one
 //                      of two survivor buffers (16 dynamic tiles of 64, with bounding circles); they
 //                      also load the block's targets, ordered by heading so that every evaluate warp
 //                      owns targets looking in all directions (its work per buffer is then even);
-//   evaluate (6 warps) own the targets r = w, w + 6, ... of the block: per survivor buffer a warp
-//                      tests its targets' view cones against the 16 circles (two targets per
-//                      ballot), evaluates the surviving tiles two sources per lane (pair_eval2, which
-//                      still applies the exact per-pair mask), and keeps the running sums of target
-//                      i in lanes i and 16 + i.  The buffer is handed back when all six are done.
+//   evaluate (11 warps; 22 in the wide shape) take the block's targets two at a time from a shared
+//                      counter: per survivor buffer a warp tests the two targets' view cones against the 16
+//                      circles (one ballot), evaluates the surviving tiles two sources per lane
+//                      (pair_eval2, which still applies the exact per-pair mask), reduces both force
+//                      components with one butterfly and adds them to the target's accumulator.  The
+//                      buffer is handed back when all evaluate warps are done with it.
 // While the evaluate warps work on one buffer the filter warps fill the other, and the producer is
 // stages ahead of both.  Culled pairs contribute exactly 0 (mask) or < 2^-cutoff_log2 f_0 (f32), so
 // the result equals the dense kernel's up to the order of summation and that bound.  Every sum has
@@ -39,16 +40,28 @@
 namespace {
 
 // Two shapes of CTA, same code (template parameters FW / EW = filter / evaluate warps):
-//   narrow  1 + 2 + 6 warps, three CTAs per SM  -- many items per CTA slot: the CTAs of an SM fill each
-//                                                  other's gaps at item boundaries;
+//   narrow  1 + 2 + 11 warps, two CTAs per SM   -- several items per CTA slot: the CTAs of an SM fill each
+//                                                  other's gaps at item boundaries.  (Measured on B200,
+//                                                  N = 65,536 / a half / an eighth of it, K1 in us:
+//                                                  1+2+6 x3: 305 / 186 / 70;  1+2+11 x2: 306 / 174 / 69;
+//                                                  1+4+11 x2: 303 / 174 / 68;  1+2+12 x2 (64 registers, spills):
+//                                                  314 / 178 / 70;  1+1+6 x3: 324 / 205 / 69 -- 22 evaluate
+//                                                  warps per SM at 72 registers instead of 18 change little:
+//                                                  the kernel sits on a plateau that the shape does not move);
 //   wide    1 + 4 + 22 warps, one CTA per SM    -- few items (a small crowd, a rank's shard of a crowd): a
 //                                                  CTA that has an SM to itself puts all of the SM's
 //                                                  evaluate warps on ONE item, whose latency is what
 //                                                  bounds such a launch.
 #ifndef CSF_TILED_MINB
-#define CSF_TILED_MINB 3
+#define CSF_TILED_MINB 2
 #endif
-constexpr int kNarrowFW = 2, kNarrowEW = 6, kWideFW = 4, kWideEW = 22;
+#ifndef CSF_NARROW_FW
+#define CSF_NARROW_FW 2
+#endif
+#ifndef CSF_NARROW_EW
+#define CSF_NARROW_EW 11
+#endif
+constexpr int kNarrowFW = CSF_NARROW_FW, kNarrowEW = CSF_NARROW_EW, kWideFW = 4, kWideEW = 22;
 constexpr int kBT = 64;                  // targets per block
 constexpr int kTileS = 64;               // sources per tile (2 per lane)
 constexpr int kCT = 16;                  // tiles per chunk of the sorted copy = dynamic tiles per survivor buffer

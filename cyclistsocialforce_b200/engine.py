@@ -139,10 +139,11 @@ class AgentGroup:
             # travels with the rider through select / concat, so churn does not re-key anybody
             ids = np.arange(n, dtype=np.int64) if stream_ids is None else np.asarray(stream_ids, dtype=np.int64).reshape(n)
             self.br_stream = torch.as_tensor(ids, dtype=torch.int64, device=dev)
-            if getattr(params, "stochastic_control_behavior", False):
-                self.br_gains = torch.zeros((5, n), dtype=f64, device=dev)       # drawn + designed on the device below
+            fixed = getattr(params, "gains", None)
+            if fixed is not None:                      # parameters `gains=`: never re-designed (dynamics.py:606-607)
+                self.br_gains = t64(np.repeat(np.asarray(fixed, float).reshape(5, 1), n, axis=1))
             else:
-                self.br_gains = t64(self._initial_br_gains(s0[:, 3]))
+                self.br_gains = torch.zeros((5, n), dtype=f64, device=dev)       # designed on the device below
         elif model == "planarpoint":
             self.dyn_x = t64(s0[:, 2][None, :])
             self.dyn_v = t64(s0[:, 3])
@@ -150,12 +151,14 @@ class AgentGroup:
         self.payload_offset = 0
         self._cstate = None
         self._cparams = None
-        if model == "balancingrider" and getattr(params, "stochastic_control_behavior", False):
-            self.init_stochastic_gains()
+        if model == "balancingrider" and getattr(params, "gains", None) is None:
+            self.init_gains()
 
-    def init_stochastic_gains(self):
-        """First poles and gains of stochastic riders (BalancingRiderDynamics.__init__ -> _get_gains,
-        dynamics.py:305-306): drawn on the device, every rider from its own stream (``br_stream``)."""
+    def init_gains(self):
+        """First gains of every BalancingRider (BalancingRiderDynamics.__init__ -> _get_gains(v),
+        dynamics.py:305-306, :602-615), on the device: poles from the pole model's regression, the fixed poles,
+        or -- stochastic riders -- the first draw of every rider's own stream (``br_stream``); then the
+        same Ackermann design the step kernel uses."""
         self._cstate = None
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().csf_br_init(C.byref(self.cstate()), C.byref(self.cparams(1.0)),
@@ -245,27 +248,6 @@ class AgentGroup:
                 fields[name] = torch.cat([ta, tb], dim=ax).contiguous()
         return AgentGroup._from_fields(a, a.n + b.n, cols, fields, np.concatenate([ha, hb]),
                                        np.concatenate([a.dest_len_host, b.dest_len_host]), q_cap)
-
-    def _initial_br_gains(self, v0):
-        """BalancingRiderDynamics.__init__ -> _get_gains(v) (dynamics.py:305-306, :602-615):
-        host-side Ackermann, same closed form as the kernel."""
-        from . import whipplecarvallo as wc
-        A0, A1, A2, B = wc.speed_polynomial_state_matrices(self.params.bike)
-        out = np.zeros((5, len(v0)))
-        cache = {}
-        for k, v in enumerate(v0):
-            v = float(v)
-            if v not in cache:
-                A = A0 + v * A1 + v * v * A2
-                poles = self.params.poles_at(v)
-                phi = np.eye(5, dtype=complex)
-                for pl in poles:
-                    phi = phi @ (A - pl * np.eye(5))
-                ctrb = np.stack([np.linalg.matrix_power(A, i) @ B for i in range(5)], axis=1)
-                w = np.linalg.solve(ctrb.T, np.array([0, 0, 0, 0, 1.0]))
-                cache[v] = np.real(w @ phi)
-            out[:, k] = cache[v]
-        return out
 
     # ---- C structs ------------------------------------------------------------------------
     def cstate(self):
@@ -413,15 +395,18 @@ class Engine:
     def __init__(self, groups, obstacles=None, priority_rule="unregulated", road_edges=(),
                  dtype=torch.float32, device="cuda", q_scale=None, extent=None, origin=None, scenario_size=None,
                  n_global=None, global_offset=0, exchange=None, pair_mode="auto", resort_every=64,
-                 count_pairs=False, graph=False):
+                 count_pairs=False, graph=False, global_classes=None):
         """``q_scale`` / ``extent`` / ``origin``: the Q-format frame of the f32 payload -- positions are
         stored as int32 multiples of ``q_scale`` (default: the finest power of two that fits ``extent``
         into 2^30 units) relative to ``origin`` (default with ``extent``/``q_scale``: (0, 0); with neither:
         frame fitted to the crowd, see ``parameters.payload_frame``).
         ``n_global`` / ``global_offset`` / ``exchange``: agent-range sharding of one crowd over
         several GPUs -- this engine owns agents [global_offset, global_offset + n) of an
-        ``n_global``-agent crowd with homogeneous field parameters; ``exchange(payload)`` is
-        called after every step to all-gather the pair payload (see distributed.py).
+        ``n_global``-agent crowd; ``exchange(payload)`` is called after every step to all-gather the pair
+        payload (see distributed.py).  The field parameters of the whole crowd are those of this engine's
+        first group unless ``global_classes`` = [(first, count, params), ...] names the parameter set of
+        every contiguous range of the GLOBAL numbering (the same list on every rank: a source's field
+        parameters are not part of the exchanged payload, so every rank has to know them up front).
         ``graph=True``: ``step()`` replays a CUDA graph of the step's kernel sequence (captured at the
         first call; the periodic re-sort of the spatial order and the exchange stay outside it)."""
         self.lib = _lib.load()
@@ -487,9 +472,24 @@ class Engine:
         # source classes: contiguous payload ranges with identical field parameters
         self.classes = []
         if n_global is not None:
-            g0 = self.groups[0]
-            self.classes.append((0, self.n_total, g0.params.field_key(),
-                                 g0.params.to_field_params(self.q_scale, self.p2r)))
+            if any(g.model == "bicycle" for g in self.groups):
+                raise NotImplementedError("v0.1 Bicycle-field sources in a sharded crowd: their eccentricity "
+                                          "depends on the speed, which is not part of the exchanged payload")
+            if global_classes is None:
+                global_classes = [(0, self.n_total, self.groups[0].params)]
+            covered = 0
+            for first, count, par in global_classes:
+                if int(first) != covered or count <= 0:
+                    raise ValueError("global_classes must tile [0, n_global) with contiguous ranges")
+                covered += int(count)
+                key = par.field_key()
+                if self.classes and self.classes[-1][2] == key:
+                    s0_, c0_, k0_, fp0_ = self.classes[-1]
+                    self.classes[-1] = (s0_, c0_ + int(count), k0_, fp0_)
+                else:
+                    self.classes.append((int(first), int(count), key, par.to_field_params(self.q_scale, self.p2r)))
+            if covered != self.n_total:
+                raise ValueError("global_classes must tile [0, n_global) with contiguous ranges")
         for g in (self.groups + self.obstacles if n_global is None else []):
             kind = 1 if g.model == "bicycle" else 0      # v0.1 elliptic field (vehicle.py:1107-1147)
             key = g.params.field_key(kind)

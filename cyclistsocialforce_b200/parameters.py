@@ -328,8 +328,18 @@ class BalancingRiderBicycleParameters(BicycleParameters):
         self.g = self.bike["g"]
         if p_dist_roll > 0 or p_dist_steer:
             raise Warning("Support for steer and roll torque disturbance removed!")  # dynamics.py:317-318
-        if poles is not None or gains is not None:
-            raise NotImplementedError("fixed poles/gains are not implemented; use a pole model")
+        # fixed control parameters (reference :1306-1314): the pole model is ignored; ``gains`` wins over
+        # ``poles`` (dynamics.py:606-607 returns params.gains before it ever looks at the poles)
+        self.controlparam_fix = poles is not None or gains is not None
+        self.poles = None if poles is None else np.asarray(poles, dtype=complex).reshape(-1)
+        self.gains = None if gains is None else np.asarray(gains, dtype=float).reshape(-1)
+        if self.gains is not None and self.gains.shape != (5,):
+            raise ValueError("gains: the five full-state feedback gains K_x (the last one is also the input gain)")
+        fixed_features = None
+        if self.poles is not None:
+            fixed_features = _pole_features(self.poles)
+        if self.controlparam_fix:
+            stochastic_control_behavior = False
         self.stochastic_control_behavior = bool(stochastic_control_behavior)
         self.controlparam_filename = controlparam_filename
         self.controlparam_polemodel_component = controlparam_polemodel_component
@@ -351,11 +361,15 @@ class BalancingRiderBicycleParameters(BicycleParameters):
             if self.polemodel["index_given"] != 0 or len(self.polemodel["features"]) != 6 or n_comp > 4:
                 raise NotImplementedError("pole model layout not supported by the device sampler")
         key = (controlparam_filename, controlparam_polemodel_component if not self.stochastic_control_behavior else 0)
-        if key not in self.POLE_REGRESSIONS:
-            raise FileNotFoundError(
-                f"Couldn't find Balancing Rider Control Behavior model {key}. "
-                f"Available models are: {sorted(self.POLE_REGRESSIONS)}")
-        self.pole_intercept, self.pole_slope = self.POLE_REGRESSIONS[key]
+        if self.controlparam_fix:
+            f = fixed_features if fixed_features is not None else (-1.0, -2.0, 1.0, -3.0, 1.0)   # (unused with gains)
+            self.pole_intercept, self.pole_slope = tuple(f), (0.0,) * 5
+        else:
+            if key not in self.POLE_REGRESSIONS:
+                raise FileNotFoundError(
+                    f"Couldn't find Balancing Rider Control Behavior model {key}. "
+                    f"Available models are: {sorted(self.POLE_REGRESSIONS)}")
+            self.pole_intercept, self.pole_slope = self.POLE_REGRESSIONS[key]
         self.p_dist_roll, self.p_dist_steer = p_dist_roll, p_dist_steer
         self.T_dist_roll, self.T_dist_steer = T_dist_roll, T_dist_steer
 
@@ -373,6 +387,7 @@ class BalancingRiderBicycleParameters(BicycleParameters):
             p.br_pole_icpt[i] = self.pole_intercept[i]
             p.br_pole_coef[i] = self.pole_slope[i]
         p.br_stochastic = 1 if self.stochastic_control_behavior else 0
+        p.br_fixed_gains = 1 if self.gains is not None else 0
         if self.stochastic_control_behavior:
             m = self.polemodel
             cov, mu, w = np.array(m["covariances"]), np.array(m["means"]), np.array(m["weights"])
@@ -397,6 +412,27 @@ class BalancingRiderBicycleParameters(BicycleParameters):
                     p.br_slope[c][i] = cg[i] / var_g
                     for j in range(i + 1):
                         p.br_chol[c][i * (i + 1) // 2 + j] = L[i, j]
+
+
+def _pole_features(poles):
+    """Five closed-loop poles (one real, two complex-conjugate pairs, any order) -> the features
+    [p0_real, p1_real, p1_imag, p2_real, p2_imag] the gain design works with."""
+    poles = np.asarray(poles, dtype=complex).reshape(-1)
+    if poles.shape != (5,):
+        raise ValueError("poles: five closed-loop poles (one real, two complex-conjugate pairs)")
+    real = [z for z in poles if abs(z.imag) < 1e-14]
+    upper = sorted([z for z in poles if z.imag >= 1e-14], key=lambda z: (z.real, z.imag), reverse=True)
+    lower = [z for z in poles if z.imag <= -1e-14]
+    if len(real) == 5 or len(real) == 3:
+        # real pairs: (A - a)(A - b) = A^2 - (a + b) A + a b  ==  re = (a + b)/2, im^2 = a b - re^2 < 0 is not
+        # representable with a real imaginary part
+        raise NotImplementedError("fixed poles: one real pole and two complex-conjugate pairs are supported")
+    if len(real) != 1 or len(upper) != 2 or len(lower) != 2:
+        raise ValueError("poles must be one real pole and two complex-conjugate pairs")
+    for z in upper:
+        if min(abs(z.conjugate() - w) for w in lower) > 1e-9 * max(1.0, abs(z)):
+            raise ValueError("poles must come in complex-conjugate pairs")
+    return (float(real[0].real), float(upper[0].real), float(upper[0].imag), float(upper[1].real), float(upper[1].imag))
 
 
 _POLE_MODELS = None

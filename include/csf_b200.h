@@ -83,6 +83,7 @@ typedef struct CsfAgentParams {
      * conditional covariance.  Feature transforms: Yeo-Johnson lambda + standard scaler per feature (index 0
      * = speed), log shift x = sign * (exp(y) + a) per pole feature (sign 0: none). */
     int32_t br_stochastic, br_n_comp;
+    int32_t br_fixed_gains, br_pad_;   /* br_fixed_gains: the gains never change (parameters `gains=`, dynamics.py:606-607) */
     double br_resample_thresh;
     uint64_t br_seed;
     double br_lam[6], br_sc_mean[6], br_sc_scale[6];

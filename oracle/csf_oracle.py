@@ -730,7 +730,11 @@ class Agents:
 
     def _br_gains(self, v, k=0):
         """BalancingRiderDynamics._get_gains, dynamics.py:602-615 (update_control_params(v), then place)."""
+        if getattr(self.p, "fixed_gains", None) is not None:       # dynamics.py:606-607
+            return np.asarray(self.p.fixed_gains, float)
         A, B = balancingrider_matrices(self.p.bike, v)
+        if getattr(self.p, "fixed_poles", None) is not None:       # parameters.py:1311-1314: controlparam_fix
+            return place_gain(A, B, np.asarray(self.p.fixed_poles, complex))
         if getattr(self.p, "stochastic", False):
             # parameters.py:1398-1402: new, independent poles when the speed has moved by more than the
             # threshold since the last draw; otherwise the rider keeps its poles

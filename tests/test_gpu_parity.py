@@ -410,3 +410,68 @@ def test_mixed_crowd_with_v01_bicycles_keeps_the_tiled_kernel():
         W.step()
     ref = np.vstack([Ab.s, At.s])
     assert np.abs(res["tiled"][0] - ref).max() < 1e-9
+
+
+def _lockstep(engines, bounds, steps):
+    """Step several shard engines that live in ONE process (one GPU) in lock step: after every step each
+    engine's own payload rows are copied into the others' payload buffers -- what the exchange does across
+    GPUs (distributed.PayloadExchange / PeerExchange), so the sharded code path runs on a one-GPU box."""
+    for _ in range(steps):
+        for e in engines:
+            e.step()
+        for i, e in enumerate(engines):
+            lo, hi = bounds[i]
+            for o in engines:
+                if o is not e:
+                    o.payload[lo:hi].copy_(e.payload[lo:hi])
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_sharded_engines_in_one_process_equal_the_single_crowd(dtype):
+    """Agent-range sharding (n_global / global_offset) with HETEROGENEOUS field parameters (two parameter
+    classes, global_classes): three shard engines stepped in lock step on one GPU reproduce the unsharded
+    crowd -- f64 to 1e-10; f32 within the summation-order noise."""
+    from cyclistsocialforce_b200 import parameters as P
+    from cyclistsocialforce_b200.engine import AgentGroup, Engine
+    from cyclistsocialforce_b200.synthetic import queues_with_start
+    n, na = 2600, 1000
+    s0, q = co.synthetic_crowd(n, seed=19, spacing=3.0)
+    pa = lambda: P.InvPendulumBicycleParameters()
+    pb = lambda: P.InvPendulumBicycleParameters(hfov=1.1 * np.pi, f_0=5.0, sigma_1=4.0)
+    origin, extent = P.payload_frame([s0[:, :2], q[..., :2]])
+    queues = list(queues_with_start(s0, q))
+
+    def groups(lo, hi):
+        out = []
+        if lo < na:
+            out.append(AgentGroup("twod", s0[lo:min(hi, na)], pa(), destqueues=queues[lo:min(hi, na)], dtype=dtype))
+        if hi > na:
+            out.append(AgentGroup("twod", s0[max(lo, na):hi], pb(), destqueues=queues[max(lo, na):hi], dtype=dtype))
+        return out
+
+    single = Engine(groups(0, n), dtype=dtype, extent=extent, origin=origin, resort_every=4)
+    bounds = [(0, 700), (700, 1800), (1800, n)]            # the middle shard straddles the class boundary
+    classes = [(0, na, pa()), (na, n - na, pb())]
+    shards = [Engine(groups(lo, hi), dtype=dtype, extent=extent, origin=origin, n_global=n, global_offset=lo,
+                     global_classes=classes, resort_every=4) for lo, hi in bounds]
+    for i, e in enumerate(shards):                         # initial exchange
+        lo, hi = bounds[i]
+        for o in shards:
+            if o is not e:
+                o.payload[lo:hi].copy_(e.payload[lo:hi])
+    steps = 10
+    for _ in range(steps):
+        single.step()
+    _lockstep(shards, bounds, steps)
+    ref = np.vstack([g.states_numpy() for g in single.groups])
+    got = np.vstack([g.states_numpy() for e in shards for g in e.groups])
+    d = np.abs(got - ref).max(axis=1)
+    if dtype == torch.float64:
+        assert d.max() < 1e-10
+    else:
+        assert np.median(d) < 1e-6 and (d > 1e-4).mean() < 0.01, (np.median(d), d.max())
+    for e in shards + [single]:
+        e.check_status()
+    with pytest.raises(ValueError):
+        Engine(groups(0, 700), dtype=dtype, extent=extent, origin=origin, n_global=n, global_offset=0,
+               global_classes=[(0, na, pa())])

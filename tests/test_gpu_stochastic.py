@@ -145,3 +145,36 @@ def test_facade_stochastic_riders():
     for _ in range(5):
         ins.step()
     assert np.all(np.isfinite(np.array([b.s for b in ins.vehicles])))
+
+
+@pytest.mark.parametrize("kind", ["poles", "gains"])
+def test_fixed_poles_and_fixed_gains(kind):
+    """BalancingRiderBicycleParameters(poles=...) / (gains=...) (reference parameters.py:1306-1314,
+    dynamics.py:602-615): the pole model is ignored; with fixed poles the gains are still re-designed for
+    every new speed, with fixed gains never."""
+    n, steps = 20, 15
+    s0, q = co.synthetic_crowd(n, seed=41, spacing=4.0, n_states=8)
+    s0[:, 3] = np.linspace(3.0, 6.0, n)
+    poles = np.array([-9.0, -1.1 + 2.0j, -1.1 - 2.0j, -1.7 + 6.5j, -1.7 - 6.5j])
+    gains = np.array([-13.1, 1.1, -6.7, -0.11, -11.4])
+    if kind == "poles":
+        par = P.BalancingRiderBicycleParameters(poles=poles)
+        op = co.default_params("balancingrider", fixed_poles=poles)
+    else:
+        par = P.BalancingRiderBicycleParameters(gains=gains)
+        op = co.default_params("balancingrider", fixed_gains=gains)
+    A = co.Agents("balancingrider", s0, params=op, v_desired=np.full(n, 5.0))
+    for k in range(n):
+        A.set_destinations(k, q[k, :, 0], q[k, :, 1])
+    W = co.World([A])
+    g = AgentGroup("balancingrider", s0, par, vd_default=5.0, destqueues=list(queues_with_start(s0, q)),
+                   dtype=torch.float64)
+    eng = Engine([g], dtype=torch.float64)
+    assert np.abs(g.br_gains.cpu().numpy().T - A.gains).max() < 1e-7 * np.abs(A.gains).max()
+    for k in range(steps):
+        W.step()
+        eng.step()
+        assert np.abs(g.states_numpy() - A.s).max() < 1e-8, k
+    if kind == "gains":
+        assert np.array_equal(g.br_gains.cpu().numpy().T, np.tile(gains, (n, 1)))
+    eng.check_status()

@@ -116,3 +116,20 @@ def test_oracle_agents_resample_on_speed_change():
     assert A.br_draws[0] == d0 and np.array_equal(A.br_feats[0], f0) and A.br_vlast[0] == 4.0
     A._br_gains(4.6, 0)
     assert A.br_draws[0] > d0 and not np.array_equal(A.br_feats[0], f0) and A.br_vlast[0] == 4.6
+
+
+def test_fixed_poles_and_gains_parameters():
+    """poles= / gains= (reference parameters.py:1306-1314): features of the fixed poles, flag for fixed gains."""
+    from cyclistsocialforce_b200 import parameters as P
+    par = P.BalancingRiderBicycleParameters(poles=[-1.7 - 6.5j, -9.0, -1.1 + 2.0j, -1.7 + 6.5j, -1.1 - 2.0j])
+    assert par.controlparam_fix and not par.stochastic_control_behavior
+    assert par.pole_intercept == (-9.0, -1.1, 2.0, -1.7, 6.5) and par.pole_slope == (0.0,) * 5
+    assert [complex(z) for z in par.poles_at(3.3)] == [-9 + 0j, -1.1 + 2j, -1.1 - 2j, -1.7 + 6.5j, -1.7 - 6.5j]
+    c = par.to_agent_params(1.0, 8, 128)
+    assert c.br_fixed_gains == 0 and c.br_stochastic == 0 and list(c.br_pole_coef) == [0.0] * 5
+    g = P.BalancingRiderBicycleParameters(gains=(-13.0, 1.0, -6.0, -0.1, -11.0), stochastic_control_behavior=True)
+    assert g.to_agent_params(1.0, 8, 128).br_fixed_gains == 1 and not g.stochastic_control_behavior
+    with pytest.raises(ValueError):
+        P.BalancingRiderBicycleParameters(poles=[-1, -2 + 1j, -2 - 1j, -3 + 1j, -3 - 2j])
+    with pytest.raises(ValueError):
+        P.BalancingRiderBicycleParameters(gains=(1.0, 2.0))
