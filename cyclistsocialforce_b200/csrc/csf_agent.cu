@@ -503,8 +503,17 @@ __device__ __forceinline__ void solve5(double (&A)[5][5], double (&b)[5], double
 // ----------------------------------------------------------------------------------------
 // InvPendulumBicycle, vehicle.py:1738-1950 (dynamics in double in both builds)
 // ----------------------------------------------------------------------------------------
-// floor(log2 |a|) of a finite non-zero double, as an integer (0 for a == 0)
-__device__ __forceinline__ int exp2_of(double a) { return a == 0.0 ? 0 : ilogb(a); }
+__constant__ double kInvK[25] = {0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11,
+                                 1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21,
+                                 1.0 / 22, 1.0 / 23, 1.0 / 24};
+// floor(log2 |a|) of a finite, normal, non-zero double from its exponent field (0 for a == 0), and 2^e as a
+// double built the same way (|e| < 1022): scaling by a power of two is then one exact multiplication --
+// ilogb / scalbn are library calls with dozens of instructions each
+__device__ __forceinline__ int exp2_of(double a) {
+    const int ex = (__double2hiint(a) >> 20) & 0x7ff;
+    return ex == 0 ? 0 : ex - 1023;
+}
+__device__ __forceinline__ double pow2(int e) { return __hiloint2double((1023 + e) << 20, 0); }
 
 // x+ = [I 0] exp(M) [x; psi_d],  M = [[A_c t_s, B_c t_s], [0, 0]]  -- what ct.forced_response returns for a
 // constant input over one sample (vehicle.py:1835-1842).  The reference forms the full matrix exponential
@@ -549,14 +558,14 @@ __device__ __forceinline__ void invpend_yaw_step(const CsfAgentParams& p, double
     const int e4 = (e1 + exp2_of(m40) - exp2_of(m1[4])) >> 1;
     const int e5 = e1 - exp2_of(m1[5]);
     const int e[6] = {0, e1, e2, e3, e4, e5};
-    m01 = scalbn(m01, e[1] - e[0]);
-    m23 = scalbn(m23, e[3] - e[2]);
+    m01 *= pow2(e[1] - e[0]);
+    m23 *= pow2(e[3] - e[2]);
 #pragma unroll
-    for (int c = 0; c < 6; ++c) m1[c] = scalbn(m1[c], e[c] - e[1]);
-    m30 = scalbn(m30, e[0] - e[3]);
-    m31 = scalbn(m31, e[1] - e[3]);
-    m32 = scalbn(m32, e[2] - e[3]);
-    m40 = scalbn(m40, e[0] - e[4]);
+    for (int c = 0; c < 6; ++c) m1[c] *= pow2(e[c] - e[1]);
+    m30 *= pow2(e[0] - e[3]);
+    m31 *= pow2(e[1] - e[3]);
+    m32 *= pow2(e[2] - e[3]);
+    m40 *= pow2(e[0] - e[4]);
     // 1-norm of the balanced matrix -> sub-steps
     double nrm = fabs(m1[0]) + fabs(m30) + fabs(m40);
     nrm = fmax(nrm, fabs(m01) + fabs(m1[1]) + fabs(m31));
@@ -565,23 +574,25 @@ __device__ __forceinline__ void invpend_yaw_step(const CsfAgentParams& p, double
     nrm = fmax(nrm, fmax(fabs(m1[4]), fabs(m1[5])));
     int ns = 1, sh = 0;
     while (nrm > 2.0 * ns && sh < 20) { ns <<= 1; ++sh; }
-    m01 = scalbn(m01, -sh);
-    m23 = scalbn(m23, -sh);
+    const double isub = pow2(-sh);
+    m01 *= isub;
+    m23 *= isub;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) m1[c] = scalbn(m1[c], -sh);
-    m30 = scalbn(m30, -sh);
-    m31 = scalbn(m31, -sh);
-    m32 = scalbn(m32, -sh);
-    m40 = scalbn(m40, -sh);
+    for (int c = 0; c < 6; ++c) m1[c] *= isub;
+    m30 *= isub;
+    m31 *= isub;
+    m32 *= isub;
+    m40 *= isub;
     double y[5];
 #pragma unroll
-    for (int r = 0; r < 5; ++r) y[r] = scalbn(x[r], -e[r]);
-    const double c15 = m1[5] * scalbn(psi_d, -e[5]);       // the input is constant over the step
+    for (int r = 0; r < 5; ++r) y[r] = x[r] * pow2(-e[r]);
+    const double c15 = m1[5] * (psi_d * pow2(-e[5]));       // the input is constant over the step
     for (int q = 0; q < ns; ++q) {
         double r0 = y[0], r1 = y[1], r2 = y[2], r3 = y[3], r4 = y[4];
-#pragma unroll
+#pragma unroll 4
         for (int kk = 24; kk >= 1; --kk) {
-            const double ik = 1.0 / (double)kk;              // (compile-time constant: the loop is unrolled)
+            const double ik = kInvK[kk];                     // (rolled: the unrolled loop is 400 instructions that
+                                                             //  every SM fetches once per launch)
             const double t0 = m01 * r1;
             const double t1 = fma(m1[0], r0, fma(m1[1], r1, fma(m1[2], r2, fma(m1[3], r3, fma(m1[4], r4, c15)))));
             const double t2 = m23 * r3;
@@ -596,7 +607,7 @@ __device__ __forceinline__ void invpend_yaw_step(const CsfAgentParams& p, double
         y[0] = r0; y[1] = r1; y[2] = r2; y[3] = r3; y[4] = r4;
     }
 #pragma unroll
-    for (int r = 0; r < 5; ++r) x[r] = scalbn(y[r], e[r]);
+    for (int r = 0; r < 5; ++r) x[r] = y[r] * pow2(e[r]);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -826,6 +837,27 @@ __device__ __forceinline__ bool agent_body(const CsfAgentState& st, const CsfAge
         pv_y = st.prev_y[k];
         hist_step = st.hist_step[k];
     }
+    // dynamic state of the richer models (K3 needs it ~2,000 instructions from here: fetched now)
+    int pre_zr = 0, pre_run = 0;
+    double pre_x[5] = {0, 0, 0, 0, 0}, pre_g[5] = {0, 0, 0, 0, 0}, pre_v = 0.0;
+    if (MODE != MODE_FORCES) {
+        if (MODEL == CSF_MODEL_INVPENDULUM) {
+            pre_zr = st.ip_zrid[k];
+            pre_run = st.ip_delta_run[k];
+#pragma unroll
+            for (int r = 0; r < 5; ++r) pre_x[r] = st.ip_x[(size_t)r * st.n + k];
+        } else if (MODEL == CSF_MODEL_BALANCINGRIDER) {
+            pre_v = st.dyn_v[k];
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                pre_x[r] = st.dyn_x[(size_t)r * st.n + k];
+                pre_g[r] = st.br_gains[(size_t)r * st.n + k];
+            }
+        } else if (MODEL == CSF_MODEL_PLANARPOINT) {
+            pre_v = st.dyn_v[k];
+            pre_x[0] = st.dyn_x[k];
+        }
+    }
     T frx0 = (T)0, fry0 = (T)0, fox = (T)0, foy = (T)0;
     const bool fused_rep = MODE == MODE_STEP && fu.partial != nullptr;
     const bool have_rep = MODE != MODE_ADVANCE && n_total > 1 && (frep != nullptr || fused_rep);
@@ -892,15 +924,16 @@ __device__ __forceinline__ bool agent_body(const CsfAgentState& st, const CsfAge
             } else control_move(a, p, Fx, Fy);
         } else if (MODEL == CSF_MODEL_INVPENDULUM) {
             // updateRidingState, vehicle.py:1932-1950
-            int zr = st.ip_zrid[k];
-            const int run = st.ip_delta_run[k];
+            int zr = pre_zr;
+            const int run = pre_run;
             const bool cvwalk = a.v < (T)p.v_max_walk;
             const bool cdelta = run >= min(a.i, p.hist_len) + 1;
             const bool ride = !cvwalk && (((zr & 2) && cdelta) || (zr & 1));
             zr = ride ? 1 : 2;
             st.ip_zrid[k] = zr;
             double xs[5];
-            for (int r = 0; r < 5; ++r) xs[r] = st.ip_x[(size_t)r * st.n + k];
+#pragma unroll
+            for (int r = 0; r < 5; ++r) xs[r] = pre_x[r];
             if (a.znav & 4) {  // :1898-1899
                 a.v = (T)0; a.delta = (T)0; a.theta = (T)0;
             } else if (ride) {
@@ -933,14 +966,14 @@ __device__ __forceinline__ bool agent_body(const CsfAgentState& st, const CsfAge
         } else if (MODEL == CSF_MODEL_PLANARPOINT) {
             // PlanarPointDynamics.step, dynamics.py:1051-1079 (closed-form implicit midpoint)
             wrap = false;
-            const double vold = st.dyn_v[k];
+            const double vold = pre_v;
             const double vdF = sqrt((double)Fx * Fx + (double)Fy * Fy);
             const double acc = clampT(p.k_p_v * (vdF - vold), p.a_max[0], p.a_max[1]);
             const double v = clampT(vold + p.t_s * acc, p.v_max_riding[0], p.v_max_riding[1]);
             const double vbar = 0.5 * (v + vold);  // vehicle.s[3] == dynamics.v in the reference
             const double psi_c = limit_angle(atan2((double)Fy, (double)Fx));  // dynamics.py:112-121
             const double h = p.t_s, kp = p.k_psi;
-            const double ps = st.dyn_x[k];
+            const double ps = pre_x[0];
             const double pn = ((1.0 - h * kp / 2) * ps + h * kp * psi_c) / (1.0 + h * kp / 2);
             double sn, cs;
             sincos(0.5 * (ps + pn), &sn, &cs);
@@ -953,20 +986,22 @@ __device__ __forceinline__ bool agent_body(const CsfAgentState& st, const CsfAge
         } else if (MODEL == CSF_MODEL_BALANCINGRIDER) {
             // BalancingRiderDynamics.step, dynamics.py:674-705 (closed-form implicit midpoint)
             wrap = false;
-            const double vold = st.dyn_v[k];
+            const double vold = pre_v;
             const double vdF = sqrt((double)Fx * Fx + (double)Fy * Fy);
             const double acc = clampT(p.k_p_v * (vdF - vold), p.a_max[0], p.a_max[1]);
             const double v = clampT(vold + p.t_s * acc, p.v_max_riding[0], p.v_max_riding[1]);
             const double vbar = 0.5 * (v + vold);  // vehicle.s[3] == dynamics.v in the reference
             double g[5], xb[5];
-            for (int r = 0; r < 5; ++r) xb[r] = st.dyn_x[(size_t)r * st.n + k];
+#pragma unroll
+            for (int r = 0; r < 5; ++r) xb[r] = pre_x[r];
             if (v != vold && !p.br_fixed_gains) {  // :680-681 (fixed gains: dynamics.py:606-607)
                 double pf[5];
                 br_poles_for(p, st, k, vbar, pf, &a.flags);
                 br_gains(p, vbar, pf, g);
                 for (int r = 0; r < 5; ++r) st.br_gains[(size_t)r * st.n + k] = g[r];
             } else
-                for (int r = 0; r < 5; ++r) g[r] = st.br_gains[(size_t)r * st.n + k];
+#pragma unroll
+                for (int r = 0; r < 5; ++r) g[r] = pre_g[r];
             const double psi_F = limit_angle(atan2(-(double)Fy, (double)Fx));  // :661-671
             const double psi_c = xb[4] + angle_difference(xb[4], psi_F);
             double A[5][5], L[5][5], rhs[5], xn[5];

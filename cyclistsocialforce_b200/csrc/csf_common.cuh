@@ -53,7 +53,7 @@ __device__ __forceinline__ double qsqrt(double a) { return ::sqrt(a); }
 // ---- angles (reference utils.py) --------------------------------------------------
 // limitAngle, utils.py:124-139: wrap to (-pi, pi]
 __device__ __forceinline__ float periods(float th) { return floorf(th * (float)(1.0 / CSF_TWO_PI)); }
-__device__ __forceinline__ double periods(double th) { return floor(th / CSF_TWO_PI); }
+__device__ __forceinline__ double periods(double th) { return floor(th * (1.0 / CSF_TWO_PI)); }   // (the fold below absorbs a last-bit difference at multiples of 2 pi)
 template <typename T> __device__ __forceinline__ T limit_angle(T th) {
     const T tp = (T)CSF_TWO_PI, pi = (T)CSF_PI;
     th = periods(th) * (-tp) + th;
