@@ -81,9 +81,15 @@ static_assert(kST % kNarrowFW == 0 && kST % kWideFW == 0, "filter warps split st
 #ifndef CSF_TILED_SLOW_START
 #define CSF_TILED_SLOW_START 1
 #endif
+#ifndef CSF_TILED_CAP0
+#define CSF_TILED_CAP0 4
+#endif
+#ifndef CSF_TILED_CAP1
+#define CSF_TILED_CAP1 8
+#endif
 __device__ __forceinline__ int buffer_cap(int k) {
     if (!CSF_TILED_SLOW_START) return kCS;
-    return k == 0 ? 4 * kTileS : (k == 1 ? 8 * kTileS : kCS);
+    return k == 0 ? CSF_TILED_CAP0 * kTileS : (k == 1 ? CSF_TILED_CAP1 * kTileS : kCS);
 }
 
 template <typename T> struct Tile;
@@ -1119,7 +1125,7 @@ int env_int(const char* name, int dflt) {
 // wide CTA shape is used (see the top of the file).
 struct TiledPlan { int n_tblocks, n_groups, grid; bool wide; int64_t n_tiles, n_chunks; };
 template <typename T> TiledPlan tiled_plan(int64_t n_src, int64_t n_tgt) {
-    static const int env_groups = env_int("CSF_TILED_GROUPS", 0), env_ipw = env_int("CSF_TILED_ITEMS_PER_SLOT", 4),
+    static const int env_groups = env_int("CSF_TILED_GROUPS", 0), env_ipw = env_int("CSF_TILED_ITEMS_PER_SLOT", 3),
                      env_max = env_int("CSF_TILED_MAX_GROUPS", 16), env_wide = env_int("CSF_TILED_WIDE", -1),
                      env_wide_below = env_int("CSF_TILED_WIDE_BELOW", 3);
     TiledPlan p;
@@ -1133,7 +1139,10 @@ template <typename T> TiledPlan tiled_plan(int64_t n_src, int64_t n_tgt) {
     const int64_t slots = (int64_t)tiled_ctas<T>(p.wide, &sms) * sms;
     // 64 targets per block balance the lobe filter's cost (per block) against its selectivity (block
     // radius).  Narrow shape: items must be plentiful -- a few per CTA slot -- because their cost follows
-    // the local density of the crowd and an item is the unit of dynamic scheduling.  Wide shape: one item
+    // the local density of the crowd and an item is the unit of dynamic scheduling; but every split of a
+    // block's chunk list halves the survivors per item, hence the tiles per (target, buffer) unit, whose
+    // fixed cost (cull, reductions) is a fifth of the evaluate warps' instructions.  Measured at N = 65,536
+    // with 296 CTA slots (K1, us): 1,024 items 291, 2,048 items 308, 3,072 items 318 -- three items per slot.  Wide shape: one item
     // per SM at a time; the chunks near a block are dealt out to several items only when there are fewer
     // blocks than SMs.  (Each chunk is still filtered once per block either way.)
     const int64_t want = p.wide ? slots : (int64_t)env_ipw * slots;

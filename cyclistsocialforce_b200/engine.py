@@ -395,7 +395,7 @@ class Engine:
     def __init__(self, groups, obstacles=None, priority_rule="unregulated", road_edges=(),
                  dtype=torch.float32, device="cuda", q_scale=None, extent=None, origin=None, scenario_size=None,
                  n_global=None, global_offset=0, exchange=None, pair_mode="auto", resort_every=64,
-                 count_pairs=False, graph=False, global_classes=None):
+                 count_pairs=False, graph=False, global_classes=None, reuse=None):
         """``q_scale`` / ``extent`` / ``origin``: the Q-format frame of the f32 payload -- positions are
         stored as int32 multiples of ``q_scale`` (default: the finest power of two that fits ``extent``
         into 2^30 units) relative to ``origin`` (default with ``extent``/``q_scale``: (0, 0); with neither:
@@ -407,12 +407,21 @@ class Engine:
         first group unless ``global_classes`` = [(first, count, params), ...] names the parameter set of
         every contiguous range of the GLOBAL numbering (the same list on every rank: a source's field
         parameters are not part of the exchanged payload, so every rank has to know them up front).
+        ``reuse``: an engine that is being replaced (road-user churn): its device buffers -- payload, force
+        arrays, sorted copy, tiles, permutations, workspace -- are taken over wherever they are large enough
+        (buffers are allocated with 25 % head room), so that adding or removing road users does not go through
+        the allocator.
         ``graph=True``: ``step()`` replays a CUDA graph of the step's kernel sequence (captured at the
         first call; the periodic re-sort of the spatial order and the exchange stay outside it)."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.CsfError("no CUDA device: the csf_b200 engine has no CPU fallback")
         self.device = torch.device(device)
+        self._pool = {}
+        if reuse is not None and reuse.device == self.device and reuse.dtype == dtype:
+            self._pool = reuse._pool
+            reuse._pool = {}
+            reuse._graph = None
         self.dtype = dtype
         self.f32 = dtype == torch.float32
         self.sfx = "f32" if self.f32 else "f64"
@@ -462,11 +471,10 @@ class Engine:
             self.payload = exchange.payload_tensor()      # lives in the peer-shared buffer (PeerExchange)
             assert self.payload.shape[0] == n and self.payload.dtype == (torch.int32 if self.f32 else torch.float64)
         else:
-            self.payload = torch.zeros((n, 4), dtype=torch.int32 if self.f32 else torch.float64,
-                                       device=self.device)
-        self.frep = torch.zeros((max(self.n_agents, 1), 2), dtype=dtype, device=self.device)
-        self.force = torch.zeros_like(self.frep)
-        self.fdest = torch.zeros_like(self.frep)
+            self.payload = self._buf("payload", (n, 4), torch.int32 if self.f32 else torch.float64)
+        self.frep = self._buf("frep", (max(self.n_agents, 1), 2), dtype)
+        self.force = self._buf("force", (max(self.n_agents, 1), 2), dtype)
+        self.fdest = self._buf("fdest", (max(self.n_agents, 1), 2), dtype)
         self.froad = None
         self.set_road_edges(road_edges)
         # source classes: contiguous payload ranges with identical field parameters
@@ -519,19 +527,19 @@ class Engine:
         if self.tiled:
             eb = 4 if self.f32 else 8
             tile_elems = self.lib.csf_tiled_tile_bytes(eb) // eb
-            for s, c, _, _ in self.classes:
+            for ci, (s, c, _, _) in enumerate(self.classes):
                 n_pad = int(self.lib.csf_tiled_padded_sources(c))
                 n_tiles = int(self.lib.csf_tiled_num_tiles(c))
                 self._tiles.append(dict(
-                    sorted=torch.zeros((n_pad, 4), dtype=self.payload.dtype, device=self.device),
-                    tiles=torch.zeros((n_tiles, tile_elems), dtype=self.payload.dtype, device=self.device),
-                    perm=torch.zeros(c, dtype=torch.int64, device=self.device)))
+                    sorted=self._buf(f"sorted{ci}", (n_pad, 4), self.payload.dtype),
+                    tiles=self._buf(f"tiles{ci}", (n_tiles, tile_elems), self.payload.dtype),
+                    perm=self._buf(f"perm{ci}", c, torch.int64)))
                 # scheduling of the pair kernel's work items: cost per item (written by every launch) and
                 # the order to hand them out in (heaviest first; refreshed with the spatial order)
                 n_items = int(self.lib.csf_tiled_num_items(c, self.n_agents, eb))
                 tl = self._tiles[-1]
                 tl["n_items"] = n_items
-                tl["item_cost"] = torch.zeros(max(n_items, 1), dtype=torch.int32, device=self.device)
+                tl["item_cost"] = self._buf(f"item_cost{ci}", max(n_items, 1), torch.int32)
                 tl["item_order"] = (torch.arange(n_items, dtype=torch.int32, device=self.device)
                                     if 0 < n_items <= 4096 else None)
                 wsb = max(wsb, int(self.lib.csf_pair_tiled_workspace_bytes(c, self.n_agents, eb)))
@@ -543,7 +551,7 @@ class Engine:
                                   and self.classes[0][1] == self.n_agents)
             self._morton = (-float(extent if extent is not None else 2.0 ** 30 * self.q_scale),
                             2.0 * float(extent if extent is not None else 2.0 ** 30 * self.q_scale) / 65536.0)
-        self.ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=self.device)
+        self.ws = self._buf("ws", max(wsb, 16), torch.uint8, zero=False)
         # Fused step (three launches: tile build + block bounds [+ wait for the peers' pushes] -> pair kernel
         # -> per-agent kernel that also reduces the pair kernel's partial sums [and signals / pushes to the
         # peers]): one tiled source class, no Bicycle-field sources
@@ -556,6 +564,22 @@ class Engine:
             self.pack()
 
     # ---- helpers ----------------------------------------------------------------------------
+    def _buf(self, name, shape, dtype, zero=True):
+        """Device array ``shape`` of ``dtype``, carved from the pooled buffer ``name`` if that is large enough
+        (see ``reuse``); otherwise a new buffer with 25 % head room replaces it."""
+        shape = tuple(int(d) for d in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        numel = 1
+        for d in shape:
+            numel *= d
+        flat = self._pool.get(name)
+        if flat is None or flat.dtype != dtype or flat.numel() < numel:
+            flat = torch.empty(max(numel + numel // 4, 16), dtype=dtype, device=self.device)
+            self._pool[name] = flat
+        out = flat[:numel].view(shape)
+        if zero:
+            out.zero_()
+        return out
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -570,7 +594,7 @@ class Engine:
         self.road = [(torch.as_tensor(np.ascontiguousarray(np.concatenate(v)), dtype=torch.float64,
                                       device=self.device).contiguous(), k[0], k[1])
                      for k, v in merged.items()]
-        self.froad = torch.zeros_like(self.frep) if self.road else None
+        self.froad = self._buf("froad", tuple(self.frep.shape), self.frep.dtype) if self.road else None
         self._road_version = getattr(self, "_road_version", 0) + 1
 
     def _version(self):
@@ -600,10 +624,10 @@ class Engine:
         written into buffers whose addresses never change (a captured CUDA graph keeps pointing at them)."""
         st = self._stream()
         if self._key_box is None:
-            self._key_box = torch.zeros(4, dtype=torch.float64, device=self.device)
+            self._key_box = self._buf("key_box", 4, torch.float64)
             nmax = max([c for _, c, _, _ in self.classes] + [self.n_agents])
-            self._order_ws = torch.empty(int(self.lib.csf_spatial_order_workspace_bytes(nmax)), dtype=torch.uint8,
-                                         device=self.device)
+            self._order_ws = self._buf("order_ws", int(self.lib.csf_spatial_order_workspace_bytes(nmax)), torch.uint8,
+                                       zero=False)
         _lib.check(self._fn("csf_spatial_bbox")(_ptr(self.payload), self.n_total, _ptr(self._key_box), st),
                    "csf_spatial_bbox")
         self.gpu_launches += 1
@@ -620,7 +644,7 @@ class Engine:
         else:
             tgt = C.c_void_p(self.payload.data_ptr() + self.global_offset * self.elem_bytes)
             if self._tgt_perm is None:
-                self._tgt_perm = torch.zeros(self.n_agents, dtype=torch.int64, device=self.device)
+                self._tgt_perm = self._buf("tgt_perm", self.n_agents, torch.int64)
             _lib.check(self._fn("csf_spatial_order")(tgt, self.n_agents, _ptr(self._key_box), _ptr(self._tgt_perm),
                                                      _ptr(self._order_ws), self._order_ws.numel(), st),
                        "csf_spatial_order")

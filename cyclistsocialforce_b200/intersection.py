@@ -250,8 +250,9 @@ class SocialForceIntersection:
         self._obstacles_dirty = False
         edges = [e for el in self.road_elements for e in el.edges_flat()]
         if self.n_bikes > 0:
+            # (the engine being replaced hands its device buffers over: churn does not go through the allocator)
             self._engine = Engine(self._groups, obstacles=self._obstacle_groups, priority_rule=self.priority_rule,
-                                  road_edges=edges, dtype=self.dtype, device=self.device)
+                                  road_edges=edges, dtype=self.dtype, device=self.device, reuse=self._engine)
         else:
             self._engine = None
         self._invalidate()

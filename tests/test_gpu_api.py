@@ -159,8 +159,11 @@ def test_churn_against_the_oracle(cls_name, model):
 
     run(12)
     check("before churn")
+    pool = {k: v.data_ptr() for k, v in ins._engine._pool.items()}
     ins.remove_road_user(3)                                  # reference :576-616 pops index 3
     W.groups.pop(3)
+    # the replaced engine handed its device buffers over: no allocation for a crowd that did not grow
+    assert pool and all(ins._engine._pool[k].data_ptr() == ptr for k, ptr in pool.items())
     run(9)
     check("after remove_road_user")
     ins.add_road_user(mk(n))                                 # a fresh road user in the middle of the crowd
