@@ -234,3 +234,45 @@ def test_road_geometry_matches_reference_live(direction):
         for em, er in zip(m.edges, r.edges):
             assert em.vertices.shape == np.asarray(er.vertices).shape
             assert np.abs(em.vertices - np.asarray(er.vertices)).max() < 1e-12
+
+
+def test_empty_intersection_steps_without_a_device():
+    """An intersection without road users (reference :866-896 with n_bikes == 0: nothing to do but the
+    ``hist_n_vecs`` bookkeeping) needs no device and returns empty force arrays."""
+    from cyclistsocialforce_b200.intersection import SocialForceIntersection
+    ins = SocialForceIntersection([])
+    ins.step()
+    ins.step()
+    fx, fy = ins.calc_forces()
+    assert fx.shape == (0,) and fy.shape == (0,)
+    assert ins.n_bikes == 0 and ins.hist_n_vecs == [0, 0] and ins.get_road_user_ids() == []
+    assert ins.check_status() == []
+
+
+def test_sumo_cosimulation_needs_a_client():
+    """activate_sumo_cosimulation=True without traci and without a client object: a clear ImportError (the
+    reference imports traci at module level, scenario.py:33-50)."""
+    import sys
+    from cyclistsocialforce_b200.intersection import SocialForceIntersection
+    try:
+        import traci  # noqa: F401  (absent from this image; other tests of the session may have stubbed it)
+        have = True
+    except ImportError:
+        have = False
+    if not have and "traci" not in sys.modules:
+        with pytest.raises(ImportError):
+            SocialForceIntersection([], activate_sumo_cosimulation=True)
+    ins = SocialForceIntersection([], activate_sumo_cosimulation=True, sumo_client=object())
+    assert ins.activate_sumo_cosimulation
+    ins.step()                                   # no road users: nothing is handed over
+
+
+def test_copy_segment_struct_matches_header():
+    """CsfCopySegments (trajectory stream) as ctypes == the header's layout: 16 segments of {src, dst, bytes}."""
+    import ctypes as C
+    from cyclistsocialforce_b200 import _lib
+    assert C.sizeof(_lib.CsfCopySegment) == 24
+    assert C.sizeof(_lib.CsfCopySegments) == 8 + 16 * 24
+    assert _lib.MAX_COPY_SEGMENTS == 16
+    hdr = open(os.path.join(ROOT, "include", "csf_b200.h")).read()
+    assert "#define CSF_MAX_COPY_SEGMENTS 16" in hdr
