@@ -27,7 +27,7 @@ class CsfFieldParams(C.Structure):
 
 
 CSF_MAX_PEERS = 16
-CSF_TILED_PREPARED, CSF_TILED_NO_REDUCE = 1, 2
+CSF_TILED_PREPARED, CSF_TILED_NO_REDUCE, CSF_TILED_PDL = 1, 2, 4
 
 
 class CsfPeerComm(C.Structure):
@@ -43,7 +43,7 @@ class CsfPeerComm(C.Structure):
 class CsfStepFusion(C.Structure):
     _fields_ = [
         ("partial", C.c_void_p), ("partial_stride", C.c_int64), ("partial_offset", C.c_int64),
-        ("n_groups", C.c_int32), ("f0", C.c_double), ("comm", CsfPeerComm),
+        ("n_groups", C.c_int32), ("pdl", C.c_int32), ("f0", C.c_double), ("comm", CsfPeerComm),
     ]
 
 

@@ -803,12 +803,16 @@ template <typename T> __device__ __forceinline__ T ldT(const void* p, int64_t k)
 template <typename T> __device__ __forceinline__ void stT(void* p, int64_t k, T v) { reinterpret_cast<T*>(p)[k] = v; }
 
 // Everything one agent does in a step; returns true if a new payload element was produced (*out).
-template <typename T, int MODEL, int MODE>
+// `pair_done()` is called exactly once, after everything that does not depend on the pair kernel of this
+// step (state and queue loads, navigation machine, destination force) and before the repulsive force is
+// read: the fused step launches this kernel as a programmatic dependent of the pair kernel, so that part
+// runs in the pair kernel's tail, on the SMs that have already run out of items.
+template <typename T, int MODEL, int MODE, typename PairDone>
 __device__ __forceinline__ bool agent_body(const CsfAgentState& st, const CsfAgentParams& p, int64_t n_total,
                                            const T* __restrict__ frep, const T* __restrict__ froad,
                                            T* __restrict__ force, T* __restrict__ fdest_out,
                                            void* __restrict__ next_xycs, const CsfStepFusion& fu, int64_t k,
-                                           Xycs<T>* out) {
+                                           Xycs<T>* out, PairDone pair_done) {
     Agent<T> a;
     a.x = st.x[k];
     a.y = st.y[k];
@@ -861,20 +865,6 @@ __device__ __forceinline__ bool agent_body(const CsfAgentState& st, const CsfAge
     T frx0 = (T)0, fry0 = (T)0, fox = (T)0, foy = (T)0;
     const bool fused_rep = MODE == MODE_STEP && fu.partial != nullptr;
     const bool have_rep = MODE != MODE_ADVANCE && n_total > 1 && (frep != nullptr || fused_rep);
-    if (have_rep && fused_rep) {
-        // partial sums of the tiled pair kernel, one slab per chunk group, reduced here in fixed order
-        // (what reduce_groups_kernel does as a launch of its own)
-        const T* part = reinterpret_cast<const T*>(fu.partial) + (size_t)(fu.partial_offset + k) * 2;
-        for (int g = 0; g < fu.n_groups; ++g) {
-            frx0 += part[(size_t)g * fu.partial_stride * 2];
-            fry0 += part[(size_t)g * fu.partial_stride * 2 + 1];
-        }
-        frx0 *= (T)fu.f0;
-        fry0 *= (T)fu.f0;
-    } else if (have_rep) {
-        frx0 = frep[k * 2];
-        fry0 = frep[k * 2 + 1];
-    }
     if (MODE != MODE_ADVANCE && froad != nullptr) {
         fox = froad[k * 2];
         foy = froad[k * 2 + 1];
@@ -886,6 +876,21 @@ __device__ __forceinline__ bool agent_body(const CsfAgentState& st, const CsfAge
         // ---- K2: destination force + assembly (intersection.py:797-799, :841-862) ----
         T fdx, fdy;
         destination_force<T, MODEL>(a, p, st, k, pv_x, pv_y, fdx, fdy);
+        pair_done();
+        if (have_rep && fused_rep) {
+            // partial sums of the tiled pair kernel, one slab per chunk group, reduced here in fixed order
+            // (what reduce_groups_kernel does as a launch of its own)
+            const T* part = reinterpret_cast<const T*>(fu.partial) + (size_t)(fu.partial_offset + k) * 2;
+            for (int g = 0; g < fu.n_groups; ++g) {
+                frx0 += part[(size_t)g * fu.partial_stride * 2];
+                fry0 += part[(size_t)g * fu.partial_stride * 2 + 1];
+            }
+            frx0 *= (T)fu.f0;
+            fry0 *= (T)fu.f0;
+        } else if (have_rep) {
+            frx0 = frep[k * 2];
+            fry0 = frep[k * 2 + 1];
+        }
         T frx = (T)0, fry = (T)0;
         if (have_rep) {
             frx = frx0;
@@ -909,6 +914,7 @@ __device__ __forceinline__ bool agent_body(const CsfAgentState& st, const CsfAge
         stT<T>(st.znav_d1, k, a.z_d1);
         if (!(isfinite((double)Fx) && isfinite((double)Fy))) a.flags |= 1;
     } else {
+        pair_done();
         Fx = force[k * 2];
         Fy = force[k * 2 + 1];
     }
@@ -1087,12 +1093,19 @@ __global__ void __launch_bounds__(128) agent_kernel(CsfAgentState st, CsfAgentPa
     if (peers) {
         if (threadIdx.x == 0) s_epoch = ld_sys(fu.comm.seq + SEQ_PUSH) + 1u;
         __syncthreads();
-        if (blockIdx.x == 0 && threadIdx.x < fu.comm.world && (int)threadIdx.x != fu.comm.rank)
-            st_sys(fu.comm.read_flags[threadIdx.x] + fu.comm.rank, s_epoch);
     }
+    // The pair kernel of this step has completed (all of its memory operations are visible): a no-op unless
+    // the kernel was launched as a programmatic dependent.  Only then may the peers be told that this rank
+    // has finished reading their payload entries.
+    auto pair_done = [&]() {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (peers && blockIdx.x == 0 && threadIdx.x < fu.comm.world && (int)threadIdx.x != fu.comm.rank)
+            st_sys(fu.comm.read_flags[threadIdx.x] + fu.comm.rank, s_epoch);
+    };
     Xycs<T> mine;
     bool produced = false;
-    if (active) produced = agent_body<T, MODEL, MODE>(st, p, n_total, frep, froad, force, fdest_out, next_xycs, fu, k, &mine);
+    if (active) produced = agent_body<T, MODEL, MODE>(st, p, n_total, frep, froad, force, fdest_out, next_xycs, fu, k, &mine, pair_done);
+    else pair_done();
     if (peers) {
         const CsfPeerComm& c = fu.comm;
         if (threadIdx.x < c.world && (int)threadIdx.x != c.rank && peer_ok(c)) {
@@ -1152,8 +1165,21 @@ int launch_agent(int model, const CsfAgentState* st, const CsfAgentParams* p, in
     if (fusion) fu = *fusion;
     if (st->count <= 0 && fu.comm.world <= 1) return 0;
     const unsigned grid = (unsigned)((st->count + 127) / 128) > 0 ? (unsigned)((st->count + 127) / 128) : 1u;
+    // fu.pdl: programmatic dependent launch -- the kernel may start while the preceding kernel in the stream (the
+    // pair kernel, which releases its dependents when its CTAs run out of items) is still draining; everything
+    // that depends on it sits behind griddepcontrol.wait (pair_done above)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(128);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = fu.pdl ? 1 : 0;
 #define CSF_LAUNCH(MODEL)                                                                                      \
-    agent_kernel<T, MODEL, MODE><<<grid, 128, 0, stream>>>(*st, *p, n_total, frep, froad, force, fdest, next_xycs, fu)
+    cudaLaunchKernelEx(&cfg, agent_kernel<T, MODEL, MODE>, *st, *p, n_total, frep, froad, force, fdest, next_xycs, fu)
     switch (model) {
         case CSF_MODEL_TWOD: CSF_LAUNCH(CSF_MODEL_TWOD); break;
         case CSF_MODEL_INVPENDULUM: CSF_LAUNCH(CSF_MODEL_INVPENDULUM); break;

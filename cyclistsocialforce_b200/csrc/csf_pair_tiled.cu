@@ -278,6 +278,9 @@ tiled_prepare_kernel(const Xycs<T>* __restrict__ xycs, int64_t n, const int64_t*
                      const Xycs<T>* __restrict__ tgt, const int64_t* __restrict__ tgt_perm, int64_t n_tgt,
                      Tile<T>* __restrict__ blocks, int64_t n_blocks, unsigned int* __restrict__ item_counter,
                      CsfPeerComm comm) {
+    // a pair kernel launched as a programmatic dependent may bring its CTAs up while this kernel runs (it reads
+    // nothing of ours before its griddepcontrol.wait)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (comm.world > 1) {
         csf_peer_wait_all(comm);
         __syncthreads();
@@ -577,6 +580,9 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
     for (int i = threadIdx.x; i < 2 * 2 * kBT * 2; i += blockDim.x) bacc[i] = (T)0;
     if (threadIdx.x == 0) *last_seen = 0;
     __syncthreads();
+    // everything above touches shared memory and kernel parameters only; from here on the kernel reads what the
+    // preceding kernel (tile build, block bounds, item counter) wrote.  A no-op unless launched with CSF_TILED_PDL.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const unsigned int n_items = (unsigned int)n_tblocks * (unsigned int)n_groups;
     const int64_t n_chunks = (n_tiles + kCT - 1) / kCT;
@@ -617,7 +623,13 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
             unsigned int item = 0;
             if (lane == 0) item = atomicAdd(counter, 1u);
             item = __shfl_sync(0xffffffffu, item, 0);
-            if (item >= n_items) break;
+            if (item >= n_items) {
+                // this CTA takes no further items: once every CTA has said so (or exited), a kernel launched
+                // as a programmatic dependent of this one (the step's per-agent kernel) may start on the SMs
+                // that are running dry; whatever it needs from this launch it reads behind griddepcontrol.wait
+                asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+                break;
+            }
             ++fetched;
             if (item_order) item = item_order[item];        // heaviest items first (previous step's costs)
 #ifdef CSF_TILED_PROF
@@ -1314,16 +1326,30 @@ int pair_tiled(const void* sorted, const void* tiles, int64_t n_src, const void*
             (const Xycs<T>*)tgt, tgt_perm, n_tgt, kBT, tblocks, pl.n_tblocks, counter);
         CSF_CHECK_LAUNCH("block_bounds_kernel");
     }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)pl.grid);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (flags & CSF_TILED_PDL) ? 1 : 0;
+    const unsigned char* sorted_c = (const unsigned char*)sorted;
+    const Tile<T>* tiles_c = (const Tile<T>*)tiles;
+    const Xycs<T>* tgt_c = (const Xycs<T>*)tgt;
+    const Tile<T>* tblocks_c = tblocks;
 #define CSF_TILED_LAUNCH(P2R_, FW_, EW_)                                                                             \
-    pair_tiled_kernel<T, P2R_, FW_, EW_><<<pl.grid, (1 + FW_ + EW_) * 32, smem, st>>>(                               \
-        (const unsigned char*)sorted, (const Tile<T>*)tiles, pl.n_tiles, (const Xycs<T>*)tgt, tgt_perm, n_tgt, tblocks, \
-        k, cc, partial, pl.n_groups, pl.n_tblocks, counter, item_order, item_cost, stats)
+    cfg.blockDim = dim3((1 + FW_ + EW_) * 32);                                                                       \
+    cudaLaunchKernelEx(&cfg, pair_tiled_kernel<T, P2R_, FW_, EW_>, sorted_c, tiles_c, pl.n_tiles, tgt_c, tgt_perm, n_tgt, \
+                       tblocks_c, k, cc, partial, pl.n_groups, pl.n_tblocks, counter, item_order, item_cost, stats)
     if (pl.wide) {
-        if (fp->p2r) CSF_TILED_LAUNCH(true, kWideFW, kWideEW);
-        else CSF_TILED_LAUNCH(false, kWideFW, kWideEW);
+        if (fp->p2r) { CSF_TILED_LAUNCH(true, kWideFW, kWideEW); }
+        else { CSF_TILED_LAUNCH(false, kWideFW, kWideEW); }
     } else {
-        if (fp->p2r) CSF_TILED_LAUNCH(true, kNarrowFW, kNarrowEW);
-        else CSF_TILED_LAUNCH(false, kNarrowFW, kNarrowEW);
+        if (fp->p2r) { CSF_TILED_LAUNCH(true, kNarrowFW, kNarrowEW); }
+        else { CSF_TILED_LAUNCH(false, kNarrowFW, kNarrowEW); }
     }
 #undef CSF_TILED_LAUNCH
     CSF_CHECK_LAUNCH("pair_tiled_kernel");

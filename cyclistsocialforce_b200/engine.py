@@ -14,6 +14,7 @@ does with Python loops.  PyTorch is used for device memory and streams only.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 
 import numpy as np
@@ -749,6 +750,9 @@ class Engine:
             fu.partial_offset = g.payload_offset - self.global_offset
             fu.n_groups = int(self.lib.csf_tiled_num_groups(c, self.n_agents, eb))
             fu.f0 = fp.f_0
+            # the per-agent kernel follows the pair kernel directly in the stream: launched as its programmatic
+            # dependent, its destination-force part runs in the pair kernel's tail (CSF_PDL=0: plain launch)
+            fu.pdl = 0 if os.environ.get("CSF_PDL", "1") == "0" else 1
             if self._peer_fused():
                 fu.comm = self.exchange.comm
             self._fusion[key] = fu
@@ -780,7 +784,8 @@ class Engine:
         _lib.check(self._fn("csf_pair_forces_tiled")(
             _ptr(tl["sorted"]), _ptr(tl["tiles"]), c, tgt, _ptr(self._tgt_perm), self.n_agents, C.byref(fp),
             _ptr(self.frep), 0, _ptr(self.ws), self.ws.numel(), _ptr(tl["item_order"]), _ptr(tl["item_cost"]),
-            _ptr(self.pair_stats), _lib.CSF_TILED_PREPARED | _lib.CSF_TILED_NO_REDUCE, st), "csf_pair_forces_tiled")
+            _ptr(self.pair_stats), _lib.CSF_TILED_PREPARED | _lib.CSF_TILED_NO_REDUCE |
+            (0 if os.environ.get("CSF_PDL", "1") == "0" else _lib.CSF_TILED_PDL), st), "csf_pair_forces_tiled")
         self.gpu_launches += 2
         mark(2)
         if self.exchange is not None and not self._peer_fused() and hasattr(self.exchange, "after_pair"):

@@ -221,6 +221,8 @@ int csf_bicycle_eccentricity_f64(const double* v, int64_t n, double v_max, doubl
  *                         tail.  Scheduling only: the forces do not depend on it. */
 #define CSF_TILED_PREPARED 1   /* csf_tiled_prepare_* has run: block bounds and item counter are in the workspace */
 #define CSF_TILED_NO_REDUCE 2  /* leave the partial sums in the workspace (csf_agent_step_fused_* reduces them) */
+#define CSF_TILED_PDL 4        /* launch the pair kernel as a programmatic dependent of the preceding kernel in the stream
+                                * (csf_tiled_prepare_*): its CTAs set up shared memory while that kernel drains */
 int64_t csf_tiled_padded_sources(int64_t n_src);
 int64_t csf_tiled_num_tiles(int64_t n_src);
 int csf_tiled_tile_bytes(int elem_bytes);
@@ -347,6 +349,8 @@ typedef struct CsfStepFusion {
     int64_t partial_stride;  /* n_tgt of the pair call */
     int64_t partial_offset;  /* index of the group's agent 0 among the pair call's targets */
     int32_t n_groups;        /* csf_tiled_num_groups() */
+    int32_t pdl;             /* 1: launch as a programmatic dependent of the preceding kernel in the stream (the pair
+                              * kernel): the part of the step that does not need the pair forces overlaps its tail */
     double f0;               /* field strength f_0 (the partial sums are per unit f_0) */
     CsfPeerComm comm;        /* comm.world <= 1: no exchange */
 } CsfStepFusion;
