@@ -64,8 +64,16 @@ namespace {
 constexpr int kNarrowFW = CSF_NARROW_FW, kNarrowEW = CSF_NARROW_EW, kWideFW = 4, kWideEW = 22;
 constexpr int kBT = 64;                  // targets per block
 constexpr int kTileS = 64;               // sources per tile (2 per lane)
-constexpr int kCT = 16;                  // tiles per chunk of the sorted copy = dynamic tiles per survivor buffer
-constexpr int kCS = kCT * kTileS;        // sources per chunk / survivor buffer
+constexpr int kCT = 16;                  // tiles per chunk of the sorted copy
+constexpr int kCS = kCT * kTileS;        // sources per chunk
+// Dynamic tiles per survivor buffer: 16 (two targets' view cones per cull ballot) or 32 (one target per
+// ballot, half as many (target, buffer) units for a large item -- their fixed cost, cull + reductions, is a
+// fifth of the evaluate warps' instructions).  f64 buffers are twice the size: 16 there.
+#ifndef CSF_TILED_DT
+#define CSF_TILED_DT 32
+#endif
+template <typename T> struct DynTiles { static constexpr int n = sizeof(T) == 4 ? CSF_TILED_DT : 16; };
+static_assert(CSF_TILED_DT == 16 || CSF_TILED_DT == 32, "dynamic tiles per survivor buffer: 16 or 32");
 constexpr int kST = 8;                   // tiles per shared-memory stage
 constexpr int kTMaxGroups = 64;
 #ifndef CSF_TILED_ITEMS_IN_FLIGHT
@@ -87,9 +95,9 @@ static_assert(kST % kNarrowFW == 0 && kST % kWideFW == 0, "filter warps split st
 #ifndef CSF_TILED_CAP1
 #define CSF_TILED_CAP1 8
 #endif
-__device__ __forceinline__ int buffer_cap(int k) {
-    if (!CSF_TILED_SLOW_START) return kCS;
-    return k == 0 ? CSF_TILED_CAP0 * kTileS : (k == 1 ? CSF_TILED_CAP1 * kTileS : kCS);
+template <int DT> __device__ __forceinline__ int buffer_cap(int k) {
+    if (!CSF_TILED_SLOW_START) return DT * kTileS;
+    return k == 0 ? CSF_TILED_CAP0 * kTileS : (k == 1 ? CSF_TILED_CAP1 * kTileS : DT * kTileS);
 }
 
 template <typename T> struct Tile;
@@ -547,10 +555,12 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
     constexpr int kStages = Stages<T>::n;
     constexpr size_t kTileB = TileBytes<T>::v;
     unsigned char* stage_src = smem_raw;                                            // [kStages][kST] tiles
-    unsigned char* sbuf = stage_src + (size_t)kStages * kST * kTileB;               // [2][kCT] survivor tiles
-    Tile<T>* srec = reinterpret_cast<Tile<T>*>(sbuf + (size_t)2 * kCT * kTileB);    // [kStages][kST] circles of the staged tiles
-    Tile<T>* dtile = srec + kStages * kST;                                          // [2][kCT] circles of the survivor tiles
-    Xycs<T>* btgt = reinterpret_cast<Xycs<T>*>(dtile + 2 * kCT);                    // [2][kBT] targets, by heading rank
+    constexpr int kDT = DynTiles<T>::n;                                             // dynamic tiles per survivor buffer
+    constexpr int kDS = kDT * kTileS;                                               // survivors per buffer
+    unsigned char* sbuf = stage_src + (size_t)kStages * kST * kTileB;               // [2][kDT] survivor tiles
+    Tile<T>* srec = reinterpret_cast<Tile<T>*>(sbuf + (size_t)2 * kDT * kTileB);    // [kStages][kST] circles of the staged tiles
+    Tile<T>* dtile = srec + kStages * kST;                                          // [2][kDT] circles of the survivor tiles
+    Xycs<T>* btgt = reinterpret_cast<Xycs<T>*>(dtile + 2 * kDT);                    // [2][kBT] targets, by heading rank
     long long* bj = reinterpret_cast<long long*>(btgt + 2 * kBT);                   // [2][kBT] their indices
     uint64_t* full = reinterpret_cast<uint64_t*>(bj + 2 * kBT);                     // [kStages]
     uint64_t* empty = full + kStages;                                               // [kStages]
@@ -775,7 +785,7 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
         // every append is followed by a filter_barrier before publish() is entered
         auto publish = [&](int flags) {
             const int slot = bk & 1;
-            unsigned char* sb = sbuf + (size_t)slot * kCT * kTileB;
+            unsigned char* sb = sbuf + (size_t)slot * kDT * kTileB;
             const int n_dt = (count + kTileS - 1) / kTileS;
             {   // pad the last dynamic tile with far-away sentinels (they contribute exactly 0)
                 Xycs<T> pad;
@@ -790,7 +800,7 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                 if (lane < valid) bb.add(A.x0, A.y0);
                 if (lane + 32 < valid) bb.add(A.x1, A.y1);
                 bb.warp_reduce();
-                if (lane == 0) dtile[slot * kCT + t] = bb.circle(valid);
+                if (lane == 0) dtile[slot * kDT + t] = bb.circle(valid);
             }
             filter_barrier<FW>();
             if (ftid == 0) {
@@ -890,9 +900,9 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                     if (lane >= o) incl += v;
                 }
                 const int tot = __shfl_sync(0xffffffffu, incl, kST - 1);
-                if (have_slot && count + tot > kCS) publish(0);     // (warp-uniform, the same in every filter warp)
+                if (have_slot && count + tot > kDS) publish(0);     // (warp-uniform, the same in every filter warp)
                 if (!have_slot) acquire();
-                unsigned char* sb = sbuf + (size_t)(bk & 1) * kCT * kTileB;
+                unsigned char* sb = sbuf + (size_t)(bk & 1) * kDT * kTileB;
                 const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
                 for (int u = 0; u < kTPW; ++u) {
@@ -910,7 +920,7 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                 count += tot;
                 surv += tot;
                 filter_barrier<FW>();                             // the appends have landed, the stage has been read
-                if (count >= buffer_cap(kbuf)) publish(0);
+                if (count >= buffer_cap<kDT>(kbuf)) publish(0);
             }
             if (lane == 0) mbar_arrive(&empty[stage]);
             ++it;
@@ -955,15 +965,16 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
         const int64_t left = n_tgt - (int64_t)tb * kBT;
         const int nvalid = (int)(left < kBT ? left : kBT);
         if (n_dt > 0) {
-            const unsigned char* base = sbuf + (size_t)slot * kCT * kTileB;
+            const unsigned char* base = sbuf + (size_t)slot * kDT * kTileB;
             const Xycs<T>* mytgt = btgt + par * kBT;
             T* acc = bacc + (size_t)(par * 2 + kpar) * kBT * 2;
-            const int tl = lane & (kCT - 1), half = lane >> 4;
+            constexpr int kTPB = 32 / kDT;                   // targets per cull ballot
+            const int tl = lane & (kDT - 1), half = lane / kDT;
             Tile<T> mytile;
-            if (tl < n_dt) mytile = dtile[slot * kCT + tl];
+            if (tl < n_dt) mytile = dtile[slot * kDT + tl];
             for (;;) {
                 int q0 = 0;
-                if (lane == 0) q0 = atomicAdd(&nextq[slot], 2);
+                if (lane == 0) q0 = atomicAdd(&nextq[slot], kTPB);
                 q0 = __shfl_sync(0xffffffffu, q0, 0);
                 if (q0 >= nvalid) break;
                 uint32_t m2;
@@ -975,8 +986,8 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                     m2 = __ballot_sync(0xffffffffu, v);
                 }
 #pragma unroll 1
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t mask = h ? (m2 >> 16) : (m2 & 0xffffu);
+                for (int h = 0; h < kTPB; ++h) {
+                    uint32_t mask = kTPB == 1 ? m2 : (h ? (m2 >> 16) : (m2 & 0xffffu));
                     if (mask == 0) continue;
                     PROF_INC(ev_units);
                     const int q = q0 + h;
@@ -1079,8 +1090,9 @@ __global__ void reduce_groups_kernel(const T* __restrict__ partial, int n_groups
 
 template <typename T> size_t tiled_smem_bytes() {
     constexpr int kStages = Stages<T>::n;
-    return (size_t)kStages * kST * TileBytes<T>::v + (size_t)2 * kCT * TileBytes<T>::v +
-           (size_t)(kStages * kST + 2 * kCT) * sizeof(Tile<T>) + (size_t)2 * kBT * sizeof(Xycs<T>) +
+    constexpr int kDT = DynTiles<T>::n;
+    return (size_t)kStages * kST * TileBytes<T>::v + (size_t)2 * kDT * TileBytes<T>::v +
+           (size_t)(kStages * kST + 2 * kDT) * sizeof(Tile<T>) + (size_t)2 * kBT * sizeof(Xycs<T>) +
            (size_t)2 * kBT * sizeof(long long) + (size_t)(2 * kStages + 4) * sizeof(uint64_t) +
            (size_t)(kStages + 2) * sizeof(int4) + (size_t)kStages * kST * sizeof(uint2) +
            (size_t)kLobeBins * sizeof(T) + (size_t)2 * 2 * kBT * 2 * sizeof(T) + 8 * sizeof(int);
