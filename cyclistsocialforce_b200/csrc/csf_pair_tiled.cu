@@ -17,11 +17,10 @@
 //                      into a ring of shared-memory stages (8 tiles each) with 1-D TMA bulk copies;
 //   filter   (2 warps; 4 in the wide shape) take the stages, drop every source whose field cannot reach the block circle
 //                      (lobe test, packed FP32x2) and append the survivors, in stream order, to one
-//                      of two survivor buffers (16 dynamic tiles of 64, with bounding circles); they
-//                      also load the block's targets, ordered by heading so that every evaluate warp
-//                      owns targets looking in all directions (its work per buffer is then even);
-//   evaluate (11 warps; 22 in the wide shape) take the block's targets two at a time from a shared
-//                      counter: per survivor buffer a warp tests the two targets' view cones against the 16
+//                      of two survivor buffers (32 dynamic tiles of 64, with bounding circles); they
+//                      also load the block's targets;
+//   evaluate (11 warps; 22 in the wide shape) take the block's targets one at a time from a shared
+//                      counter: per survivor buffer a warp tests the target's view cone against the 32
 //                      circles (one ballot), evaluates the surviving tiles two sources per lane
 //                      (pair_eval2, which still applies the exact per-pair mask), reduces both force
 //                      components with one butterfly and adds them to the target's accumulator.  The
@@ -29,7 +28,7 @@
 // While the evaluate warps work on one buffer the filter warps fill the other, and the producer is
 // stages ahead of both.  Culled pairs contribute exactly 0 (mask) or < 2^-cutoff_log2 f_0 (f32), so
 // the result equals the dense kernel's up to the order of summation and that bound.  Every sum has
-// a fixed order (stream order of the survivors, static ownership of targets): deterministic, no
+// a fixed order (stream order of the survivors, one warp per (target, buffer)): deterministic, no
 // float atomics; partial sums per chunk group are reduced in fixed order.
 #include "csf_common.cuh"
 #include "csf_pair_common.cuh"
@@ -89,15 +88,26 @@ static_assert(kST % kNarrowFW == 0 && kST % kWideFW == 0, "filter warps split st
 #ifndef CSF_TILED_SLOW_START
 #define CSF_TILED_SLOW_START 1
 #endif
+// (tiles; narrow shape / wide shape.  Measured with 32-tile buffers, step in us at N = 65,536 / 1 M / a 1/8
+// shard (wide): 4, 8: 298 / 4602 / 73;  8, 16: 285 / 4281 / 75;  4, 16: 287 / 4399 / 76;  none: 289 / 4333 / 82;
+// 16-tile buffers with 4, 8: 299 / 4535 / 78.)
 #ifndef CSF_TILED_CAP0
-#define CSF_TILED_CAP0 4
+#define CSF_TILED_CAP0 8
 #endif
 #ifndef CSF_TILED_CAP1
-#define CSF_TILED_CAP1 8
+#define CSF_TILED_CAP1 16
 #endif
-template <int DT> __device__ __forceinline__ int buffer_cap(int k) {
+#ifndef CSF_TILED_WIDE_CAP0
+#define CSF_TILED_WIDE_CAP0 4
+#endif
+#ifndef CSF_TILED_WIDE_CAP1
+#define CSF_TILED_WIDE_CAP1 8
+#endif
+template <int DT, bool WIDE> __device__ __forceinline__ int buffer_cap(int k) {
     if (!CSF_TILED_SLOW_START) return DT * kTileS;
-    return k == 0 ? CSF_TILED_CAP0 * kTileS : (k == 1 ? CSF_TILED_CAP1 * kTileS : DT * kTileS);
+    const int c0 = (WIDE ? CSF_TILED_WIDE_CAP0 : CSF_TILED_CAP0) < DT ? (WIDE ? CSF_TILED_WIDE_CAP0 : CSF_TILED_CAP0) : DT;
+    const int c1 = (WIDE ? CSF_TILED_WIDE_CAP1 : CSF_TILED_CAP1) < DT ? (WIDE ? CSF_TILED_WIDE_CAP1 : CSF_TILED_CAP1) : DT;
+    return k == 0 ? c0 * kTileS : (k == 1 ? c1 * kTileS : DT * kTileS);
 }
 
 template <typename T> struct Tile;
@@ -920,7 +930,7 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                 count += tot;
                 surv += tot;
                 filter_barrier<FW>();                             // the appends have landed, the stage has been read
-                if (count >= buffer_cap<kDT>(kbuf)) publish(0);
+                if (count >= buffer_cap<kDT, (EW == kWideEW)>(kbuf)) publish(0);
             }
             if (lane == 0) mbar_arrive(&empty[stage]);
             ++it;
@@ -941,9 +951,9 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
     }
 
     // ===== evaluate warps =====
-    // Per survivor buffer the warps take the block's targets two at a time from a shared counter (the
-    // targets' headings make the work per target very uneven): cull -- the view cones of the two
-    // targets against the 16 circles (lanes 0-15 / 16-31, one ballot); evaluate -- the surviving tiles
+    // Per survivor buffer the warps take the block's targets from a shared counter (the targets' headings
+    // make the work per target very uneven): cull -- the target's view cone against the buffer's 32 circles,
+    // one ballot (f64 build: 16-tile buffers, two targets per ballot in lanes 0-15 / 16-31); evaluate -- the surviving tiles
     // two at a time (four independent pair evaluations per lane in flight), one butterfly reduces both
     // force components (lanes 0-15: x, 16-31: y), one lane each adds them to the target's accumulator.
     // A (buffer, target) sum is formed by one warp in a fixed order whoever takes it, and buffers that
