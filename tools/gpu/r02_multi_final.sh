@@ -19,12 +19,16 @@ done
 timeout 300 python bench.py --gpus 1 --steps 50 --warmup 5 --no-cpu-baseline --no-extra > gpurun_out/mf_bench_1.json 2> gpurun_out/mf_bench_1.err; show gpurun_out/mf_bench_1.json
 CSF_BENCH_N=1048576 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 8 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/mf_bench_1M_8.json 2> gpurun_out/mf_bench_1M_8.err
 echo "bench 1M x8 rc=$?"; tail -2 gpurun_out/mf_bench_1M_8.err | cut -c1-300; show gpurun_out/mf_bench_1M_8.json
+if [ "$1" = "long" ]; then
 CSF_BENCH_N=1048576 timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/mf_bench_1M_1.json 2> gpurun_out/mf_bench_1M_1.err; show gpurun_out/mf_bench_1M_1.json
+fi
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29612 tools/bench_scenarios.py --scenarios 524288 --steps 50 > gpurun_out/mf_scen_8.json 2> gpurun_out/mf_scen_8.err
 echo "scenarios x8 (weak: 65,536 per GPU) rc=$?"; cut -c1-330 gpurun_out/mf_scen_8.json
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29615 tools/bench_scenarios.py --scenarios 65536 --steps 50 > gpurun_out/mf_scen_8_c4.json 2> gpurun_out/mf_scen_8_c4.err
 echo "config 4 as named (65,536 scenarios over 8 GPUs) rc=$?"; cut -c1-330 gpurun_out/mf_scen_8_c4.json
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29613 tools/check_sharded.py --peer --big > gpurun_out/mf_check_8.log 2>&1
 echo "check_sharded --peer --big rc=$?"; grep -E "sharded_vs_single" gpurun_out/mf_check_8.log | cut -c1-420 | tail -5
+if [ "$1" = "long" ]; then
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29614 tools/check_sharded.py > gpurun_out/mf_check_2_nccl.log 2>&1
 echo "check_sharded nccl x2 rc=$?"; grep -E "sharded_vs_single" gpurun_out/mf_check_2_nccl.log | cut -c1-300 | tail -3
+fi
