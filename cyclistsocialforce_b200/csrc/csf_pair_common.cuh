@@ -7,6 +7,7 @@ namespace {
 
 template <typename T> struct PairConst {
     T sg0, sg1, sg2, sg3;  // sigma_0..3 / (q_scale * log2 e)
+    T sg2s, sg3s;          // sg2 / sqrt 2, sg3 / sqrt 2 (pair_eval2 works with sqrt 2 x the half-angle functions)
     T e0, e1;
     T qa, qb, qc;          // 1 - e^2 = qa + qb s2 + qc s2^2  (qa = 1-e0^2, qb = 2 e0 e1, qc = -e1^2)
     T ncosH;               // -cos(hfov/2); +2 if hfov/2 >= pi (always visible)
@@ -127,15 +128,18 @@ __device__ __forceinline__ void pair_eval2(int32_t x0, int32_t x1, int32_t y0, i
     const F2 SR = fma2(SS, TC, neg2(mul2(SC, TS)));
     const F2 S2 = mul2(SR, SR);
     const F2 A = fma2(splat(k.sg1), S2, splat(k.sg0));
-    const F2 B = fma2(splat(k.sg3), S2, splat(k.sg2));
+    // half-angle functions of phi scaled by sqrt 2: with hm2 = 1 + |c| = 2 hm,  sqrt(2 hm) = hm2 rsqrt(hm2)  and
+    // |s| / sqrt(2 hm) = |s| rsqrt(hm2) -- one packed instruction less than via hm = (1 + |c|) / 2; the factor
+    // 1 / sqrt 2 sits in the constants of B (B only ever multiplies one of the two)
+    const F2 B = fma2(splat(k.sg3s), S2, splat(k.sg2s));
     const F2 E = fma2(splat(-k.e1), S2, splat(k.e0));
     const F2 AS = abs2(S);
-    const F2 HM = fma2(splat(0.5f), abs2(C), splat(0.5f));
+    const F2 HM = add2(abs2(C), splat(1.f));
     float hma, hmb;
     up(HM, hma, hmb);
     const F2 RM = pk(M<float>::rsqrt(hma), M<float>::rsqrt(hmb));
     const F2 HBIG = mul2(HM, RM);
-    const F2 HSMALL = mul2(AS, mul2(splat(0.5f), RM));
+    const F2 HSMALL = mul2(AS, RM);
     float ca, cb, sa, sb, hba, hbb, hsa, hsb;
     up(C, ca, cb);
     up(S, sa, sb);
@@ -234,6 +238,8 @@ template <typename T> inline PairConst<T> make_const(const CsfFieldParams* fp, b
     k.sg1 = (T)(fp->sigma_1 / kappa);
     k.sg2 = (T)(fp->sigma_2 / kappa);
     k.sg3 = (T)(fp->sigma_3 / kappa);
+    k.sg2s = (T)(fp->sigma_2 / kappa / 1.4142135623730951);
+    k.sg3s = (T)(fp->sigma_3 / kappa / 1.4142135623730951);
     k.e0 = (T)fp->e_0;
     k.e1 = (T)fp->e_1;
     k.qa = (T)(1.0 - fp->e_0 * fp->e_0);

@@ -34,6 +34,7 @@
 #include "csf_pair_common.cuh"
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include "csf_peer.cuh"
 
 namespace {
@@ -1263,6 +1264,8 @@ template <typename T> CullConst<T> make_cull(const CsfFieldParams* fp, bool is_f
         struct Entry { CsfFieldParams fp; double rate; double rate_c[NC]; bool ok; bool used; };
         static Entry cache[kCache];
         static int next_slot = 0;
+        static std::mutex cache_mutex;                   // engines on several host threads share the cache
+        std::lock_guard<std::mutex> lock(cache_mutex);
         Entry* hit = nullptr;
         for (int i = 0; i < kCache && !hit; ++i) {
             const Entry& e = cache[i];
