@@ -105,6 +105,19 @@ class CsfCopySegments(C.Structure):
     _fields_ = [("n", C.c_int32), ("pad_", C.c_int32), ("seg", CsfCopySegment * MAX_COPY_SEGMENTS)]
 
 
+MAX_GATHER_SEGMENTS = 48
+
+
+class CsfGatherSegment(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("idx", C.c_void_p), ("outer", C.c_int64), ("n_src", C.c_int64),
+                ("n_dst", C.c_int64), ("dst_off", C.c_int64), ("count", C.c_int64), ("inner_bytes", C.c_int64),
+                ("dst_inner_bytes", C.c_int64)]
+
+
+class CsfGatherSegments(C.Structure):
+    _fields_ = [("n", C.c_int32), ("pad_", C.c_int32), ("seg", CsfGatherSegment * MAX_GATHER_SEGMENTS)]
+
+
 _AP = C.POINTER(CsfAgentParams)
 _AS = C.POINTER(CsfAgentState)
 
@@ -163,6 +176,7 @@ SIGNATURES = {
     "csf_pack_xypsi_f32": (C.c_int, [_vp, _vp, _vp, _i64, _dbl, _dbl, _dbl, _vp, _vp]),
     "csf_pack_xypsi_f64": (C.c_int, [_vp, _vp, _vp, _i64, _dbl, _dbl, _dbl, _vp, _vp]),
     "csf_copy_segments": (C.c_int, [C.POINTER(CsfCopySegments), _vp]),
+    "csf_gather_segments": (C.c_int, [C.POINTER(CsfGatherSegments), _vp]),
     "csf_sumo_pose_f32": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "csf_sumo_pose_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "csf_ffma_peak": (C.c_int, [_i64, _vp, C.POINTER(C.c_double), _vp]),

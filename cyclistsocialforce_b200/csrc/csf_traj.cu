@@ -27,6 +27,25 @@ __global__ void __launch_bounds__(256) copy_segments_kernel(CsfCopySegments segs
     }
 }
 
+// Road-user churn (intersection.py:458-539, :576-634): every per-agent array of a model group is re-laid in ONE
+// launch.  A segment describes an array as (outer, n, inner): dst[o][dst_off + j][:] = src[o][idx ? idx[j] : j][:]
+// for j < count -- rows of agents (outer = 1), column-wise arrays such as the history rings (outer = rows), with
+// an index list (select / compact) or without (append the agents of another group behind dst_off).
+// blockIdx.y = segment, grid-stride over 4-byte words.
+__global__ void __launch_bounds__(256) gather_segments_kernel(CsfGatherSegments segs) {
+    const CsfGatherSegment sg = segs.seg[blockIdx.y];
+    const int64_t wpr = sg.inner_bytes >> 2;                       // words per (outer, agent) element of the source
+    const int64_t wpd = (sg.dst_inner_bytes > 0 ? sg.dst_inner_bytes : sg.inner_bytes) >> 2;   // ... of the destination
+    const int64_t total = sg.outer * sg.count * wpr;
+    const uint32_t* __restrict__ src = static_cast<const uint32_t*>(sg.src);
+    uint32_t* __restrict__ dst = static_cast<uint32_t*>(sg.dst);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t w = i % wpr, j = (i / wpr) % sg.count, o = i / (wpr * sg.count);
+        const int64_t from = sg.idx ? sg.idx[j] : j;
+        dst[(o * sg.n_dst + sg.dst_off + j) * wpd + w] = src[(o * sg.n_src + from) * wpr + w];
+    }
+}
+
 // SFM heading (rad, counter-clockwise from +x) -> SUMO angle (deg, clockwise from north), utils.py:89-111
 // angleSFMtoSUMO; and the positions, as one [n][3] double array for a batched traci.vehicle.moveToXY.
 template <typename T>
@@ -58,6 +77,31 @@ int csf_copy_segments(const CsfCopySegments* segs, csf_stream_t s) {
     const unsigned gx = (unsigned)(want < 1 ? 1 : (want > 592 ? 592 : want));      // <= 4 CTAs per SM and segment
     copy_segments_kernel<<<dim3(gx, (unsigned)segs->n), 256, 0, (cudaStream_t)s>>>(*segs);
     CSF_CHECK_LAUNCH("copy_segments_kernel");
+    return 0;
+}
+
+int csf_gather_segments(const CsfGatherSegments* segs, csf_stream_t s) {
+    if (segs->n <= 0) return 0;
+    if (segs->n > CSF_MAX_GATHER_SEGMENTS) {
+        csf_set_error("csf_gather_segments: too many segments", cudaErrorInvalidValue);
+        return -(int)cudaErrorInvalidValue;
+    }
+    int64_t most = 0;
+    for (int i = 0; i < segs->n; ++i) {
+        const CsfGatherSegment& g = segs->seg[i];
+        if ((g.inner_bytes & 3) || g.inner_bytes <= 0 || (g.dst_inner_bytes & 3) ||
+            (g.dst_inner_bytes > 0 && g.dst_inner_bytes < g.inner_bytes)) {
+            csf_set_error("csf_gather_segments: element sizes must be positive multiples of 4 bytes", cudaErrorInvalidValue);
+            return -(int)cudaErrorInvalidValue;
+        }
+        const int64_t w = g.outer * g.count * (g.inner_bytes >> 2);
+        most = w > most ? w : most;
+    }
+    if (most == 0) return 0;
+    const int64_t want = (most + 255) / 256;
+    const unsigned gx = (unsigned)(want < 1 ? 1 : (want > 592 ? 592 : want));
+    gather_segments_kernel<<<dim3(gx, (unsigned)segs->n), 256, 0, (cudaStream_t)s>>>(*segs);
+    CSF_CHECK_LAUNCH("gather_segments_kernel");
     return 0;
 }
 

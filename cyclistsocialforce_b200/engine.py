@@ -213,42 +213,88 @@ class AgentGroup:
         g._cstate = g._cparams = None
         return g
 
+    @staticmethod
+    def _regroup(parts, n_new, q_cap):
+        """New group made of ``parts`` = [(group, device index tensor or None, count, first row in the new
+        group)]: every per-agent array -- state columns, navigation machine, history rings, dynamic state,
+        destination queues, stochastic-rider state -- is re-laid by the library's gather kernel
+        (``csf_gather_segments``: one launch per part), not by tensor indexing."""
+        like = parts[0][0]
+        dev = like.device
+        cols = {name: torch.zeros(n_new, dtype=getattr(like, name).dtype, device=dev) for name in _STATE_COLS
+                if getattr(like, name) is not None}
+        fields = {}
+        for name, ax in _FIELD_AXIS.items():
+            t = getattr(like, name)
+            if t is None:
+                continue
+            shape = list(t.shape)
+            shape[ax] = n_new
+            if name == "destq":
+                shape[1] = q_cap
+            fields[name] = torch.zeros(shape, dtype=t.dtype, device=dev)
+        new = AgentGroup._from_fields(like, n_new, cols, fields,
+                                      np.zeros((n_new, q_cap, 3)), np.zeros(n_new, dtype=np.int32), q_cap)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            for g, idx, count, off in parts:
+                if count == 0:
+                    continue
+                segs = _lib.CsfGatherSegments()
+                k = 0
+
+                def add(src, dst, outer, inner, dst_inner=0):
+                    nonlocal k
+                    sg = segs.seg[k]
+                    sg.src, sg.dst = src.data_ptr(), dst.data_ptr()
+                    sg.idx = idx.data_ptr() if idx is not None else None
+                    sg.outer, sg.n_src, sg.n_dst, sg.dst_off, sg.count = outer, g.n, n_new, off, count
+                    sg.inner_bytes, sg.dst_inner_bytes = inner, dst_inner
+                    k += 1
+
+                for name in _STATE_COLS:
+                    if getattr(g, name) is not None:
+                        add(getattr(g, name), getattr(new, name), 1, getattr(g, name).element_size())
+                for name, ax in _FIELD_AXIS.items():
+                    t = getattr(g, name)
+                    if t is None:
+                        continue
+                    d = getattr(new, name)
+                    if ax == 0:
+                        inner = t.element_size() * (t.numel() // max(t.shape[0], 1)) if t.dim() > 1 else t.element_size()
+                        dinner = d.element_size() * (d.numel() // max(d.shape[0], 1)) if d.dim() > 1 else d.element_size()
+                        add(t, d, 1, inner, 0 if dinner == inner else dinner)
+                    else:
+                        add(t, d, t.shape[0], t.element_size())
+                segs.n = k
+                _lib.check(lib.csf_gather_segments(C.byref(segs), st), "csf_gather_segments")
+        return new
+
     def select(self, keep):
         """New group with the agents ``keep`` (indices, any order) -- every per-agent field, including
         the navigation machine, the history rings and the dynamic state, gathered on the device."""
         keep_h = np.asarray(keep, dtype=np.int64).reshape(-1)
         idx = torch.as_tensor(keep_h, device=self.device)
-        cols = {name: getattr(self, name).index_select(0, idx) for name in _STATE_COLS if getattr(self, name) is not None}
-        fields = {name: getattr(self, name).index_select(ax, idx).contiguous()
-                  for name, ax in _FIELD_AXIS.items() if getattr(self, name) is not None}
-        return AgentGroup._from_fields(self, len(keep_h), cols, fields, self.destq_host[keep_h].copy(),
-                                       self.dest_len_host[keep_h].copy(), self.q_cap)
+        new = AgentGroup._regroup([(self, idx, len(keep_h), 0)], len(keep_h), self.q_cap)
+        new.destq_host, new.dest_len_host = self.destq_host[keep_h].copy(), self.dest_len_host[keep_h].copy()
+        return new
 
     @staticmethod
     def concat(a, b):
         """Agents of ``a`` followed by those of ``b`` (same model and parameter set), joined on the device."""
         assert a.model == b.model and a.dtype == b.dtype
         q_cap = max(a.q_cap, b.q_cap)
+        new = AgentGroup._regroup([(a, None, a.n, 0), (b, None, b.n, a.n)], a.n + b.n, q_cap)
 
         def padq(g):
-            if g.q_cap == q_cap:
-                return g.destq, g.destq_host
-            dq = torch.zeros((g.n, q_cap, 3), dtype=torch.float64, device=g.device)
-            dq[:, :g.q_cap] = g.destq
             hq = np.zeros((g.n, q_cap, 3))
             hq[:, :g.q_cap] = g.destq_host
-            return dq, hq
+            return hq
 
-        (da, ha), (db, hb) = padq(a), padq(b)
-        cols = {name: torch.cat([getattr(a, name), getattr(b, name)]) for name in _STATE_COLS
-                if getattr(a, name) is not None}
-        fields = {}
-        for name, ax in _FIELD_AXIS.items():
-            ta, tb = (da, db) if name == "destq" else (getattr(a, name), getattr(b, name))
-            if ta is not None:
-                fields[name] = torch.cat([ta, tb], dim=ax).contiguous()
-        return AgentGroup._from_fields(a, a.n + b.n, cols, fields, np.concatenate([ha, hb]),
-                                       np.concatenate([a.dest_len_host, b.dest_len_host]), q_cap)
+        new.destq_host = np.concatenate([padq(a), padq(b)])
+        new.dest_len_host = np.concatenate([a.dest_len_host, b.dest_len_host])
+        return new
 
     # ---- C structs ------------------------------------------------------------------------
     def cstate(self):

@@ -403,6 +403,25 @@ typedef struct CsfCopySegments {
     CsfCopySegment seg[CSF_MAX_COPY_SEGMENTS];
 } CsfCopySegments;
 int csf_copy_segments(const CsfCopySegments* segs, csf_stream_t stream);
+/* Road-user churn (intersection.py:458-539 add_road_user, :576-634 remove_road_user[s_by_id]): every per-agent
+ * array of a model group re-laid in one launch.  A segment views an array as (outer, n, inner_bytes):
+ *   dst[o][dst_off + j][:] = src[o][idx ? idx[j] : j][:]   for o < outer, j < count
+ * (idx: device array of source agents -- select / compact; NULL -- append behind dst_off). */
+#define CSF_MAX_GATHER_SEGMENTS 48
+typedef struct CsfGatherSegment {
+    const void* src;
+    void* dst;
+    const int64_t* idx;   /* [count] or NULL */
+    int64_t outer, n_src, n_dst, dst_off, count, inner_bytes;
+    int64_t dst_inner_bytes; /* 0: as inner_bytes; larger: the element is copied into the head of a wider destination
+                              * element (destination queues of different capacity), the rest is left untouched */
+} CsfGatherSegment;
+typedef struct CsfGatherSegments {
+    int32_t n;
+    int32_t pad_;
+    CsfGatherSegment seg[CSF_MAX_GATHER_SEGMENTS];
+} CsfGatherSegments;
+int csf_gather_segments(const CsfGatherSegments* segs, csf_stream_t stream);
 int csf_sumo_pose_f32(const double* x, const double* y, const void* psi, int64_t n, double* out, csf_stream_t stream);
 int csf_sumo_pose_f64(const double* x, const double* y, const void* psi, int64_t n, double* out, csf_stream_t stream);
 
