@@ -276,3 +276,8 @@ def test_copy_segment_struct_matches_header():
     assert _lib.MAX_COPY_SEGMENTS == 16
     hdr = open(os.path.join(ROOT, "include", "csf_b200.h")).read()
     assert "#define CSF_MAX_COPY_SEGMENTS 16" in hdr
+    # churn: CsfGatherSegments (three pointers + seven 64-bit integers per segment), passed by value to the
+    # kernel: must stay below the 4 KB that every CUDA 12 driver accepts for kernel parameters
+    assert C.sizeof(_lib.CsfGatherSegment) == 80
+    assert C.sizeof(_lib.CsfGatherSegments) == 8 + _lib.MAX_GATHER_SEGMENTS * 80 <= 4096
+    assert f"#define CSF_MAX_GATHER_SEGMENTS {_lib.MAX_GATHER_SEGMENTS}" in hdr
