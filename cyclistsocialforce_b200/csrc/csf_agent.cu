@@ -865,10 +865,6 @@ __device__ __forceinline__ bool agent_body(const CsfAgentState& st, const CsfAge
     T frx0 = (T)0, fry0 = (T)0, fox = (T)0, foy = (T)0;
     const bool fused_rep = MODE == MODE_STEP && fu.partial != nullptr;
     const bool have_rep = MODE != MODE_ADVANCE && n_total > 1 && (frep != nullptr || fused_rep);
-    if (MODE != MODE_ADVANCE && froad != nullptr) {
-        fox = froad[k * 2];
-        foy = froad[k * 2 + 1];
-    }
     load_window(a);
 
     T Fx, Fy;
@@ -877,6 +873,10 @@ __device__ __forceinline__ bool agent_body(const CsfAgentState& st, const CsfAge
         T fdx, fdy;
         destination_force<T, MODEL>(a, p, st, k, pv_x, pv_y, fdx, fdy);
         pair_done();
+        if (froad != nullptr) {       // (written by the road kernels of this step: read behind the dependency wait too)
+            fox = froad[k * 2];
+            foy = froad[k * 2 + 1];
+        }
         if (have_rep && fused_rep) {
             // partial sums of the tiled pair kernel, one slab per chunk group, reduced here in fixed order
             // (what reduce_groups_kernel does as a launch of its own)
