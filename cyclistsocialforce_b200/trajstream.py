@@ -106,18 +106,10 @@ class TrajectoryStream:
             h, steps = self._pending.pop(0)
             self._copied[h].synchronize()
             buf = self._host[h][:steps * self.slot_bytes].numpy().reshape(steps, self.slot_bytes)
-            rec = {"steps": steps, "groups": [], "force": None}
-            for g, off, nb in self._layout:
-                cols = {}
-                for name, (o, n, dt) in g.state_layout.items():
-                    npdt = np.float64 if dt == torch.float64 else np.float32
-                    w = n * np.dtype(npdt).itemsize
-                    cols[name] = buf[:, off + o: off + o + w].copy().view(npdt).reshape(steps, n)
-                rec["groups"].append(cols)
+            layouts = [(off, {name: (o, n, np.float64 if dt == torch.float64 else np.float32)
+                              for name, (o, n, dt) in g.state_layout.items()}) for g, off, nb in self._layout]
             ft = np.float64 if self.engine.force.dtype == torch.float64 else np.float32
-            rec["force"] = buf[:, self._force_off: self._force_off + self._force_bytes].copy().view(ft).reshape(
-                steps, -1, 2)
-            self._out.append(rec)
+            self._out.append(decode_chunk(buf, layouts, self._force_off, self._force_bytes, ft))
 
     def drain(self):
         """Everything recorded so far and not yet drained: list of chunks
@@ -131,6 +123,22 @@ class TrajectoryStream:
     @property
     def steps_recorded(self):
         return self._steps_total
+
+
+def decode_chunk(buf, group_layouts, force_off, force_bytes, force_dtype):
+    """One drained chunk of the ring -> arrays.  ``buf``: (steps, slot_bytes) uint8; ``group_layouts``: per model
+    group (offset of its state slab in the slot, {column: (offset in the slab, n, numpy dtype)});
+    returns {"steps": k, "groups": [{column: (k, n) array}], "force": (k, n_agents, 2) array}."""
+    steps = buf.shape[0]
+    rec = {"steps": steps, "groups": [], "force": None}
+    for off, cols_layout in group_layouts:
+        cols = {}
+        for name, (o, n, npdt) in cols_layout.items():
+            w = n * np.dtype(npdt).itemsize
+            cols[name] = buf[:, off + o: off + o + w].copy().view(npdt).reshape(steps, n)
+        rec["groups"].append(cols)
+    rec["force"] = buf[:, force_off: force_off + force_bytes].copy().view(force_dtype).reshape(steps, -1, 2)
+    return rec
 
 
 def sumo_poses(group, out_dev=None, out_host=None):

@@ -281,3 +281,29 @@ def test_copy_segment_struct_matches_header():
     assert C.sizeof(_lib.CsfGatherSegment) == 80
     assert C.sizeof(_lib.CsfGatherSegments) == 8 + _lib.MAX_GATHER_SEGMENTS * 80 <= 4096
     assert f"#define CSF_MAX_GATHER_SEGMENTS {_lib.MAX_GATHER_SEGMENTS}" in hdr
+
+
+def test_trajectory_chunk_decoding():
+    """Host side of the trajectory stream: a drained chunk (bytes of [state slabs | forces] per step) decodes
+    into per-column arrays -- mixed double / float columns at 256-byte aligned offsets, two groups."""
+    from cyclistsocialforce_b200.trajstream import decode_chunk
+    rng = np.random.default_rng(0)
+    steps, na, nb = 5, 7, 3
+    lay_a = {"x": (0, na, np.float64), "y": (256, na, np.float64), "psi": (512, na, np.float32), "v": (768, na, np.float32)}
+    lay_b = {"x": (0, nb, np.float64), "y": (256, nb, np.float64), "psi": (512, nb, np.float32)}
+    off_a, off_b, force_off = 0, 1024, 2048
+    force_bytes = (na + nb) * 2 * 4
+    slot = force_off + 256
+    buf = np.zeros((steps, slot), dtype=np.uint8)
+    truth = {}
+    for gi, (off, lay) in enumerate(((off_a, lay_a), (off_b, lay_b))):
+        for name, (o, n, dt) in lay.items():
+            val = rng.normal(size=(steps, n)).astype(dt)
+            truth[(gi, name)] = val
+            buf[:, off + o: off + o + n * np.dtype(dt).itemsize] = val.view(np.uint8).reshape(steps, -1)
+    f = rng.normal(size=(steps, na + nb, 2)).astype(np.float32)
+    buf[:, force_off: force_off + force_bytes] = f.reshape(steps, -1).view(np.uint8)
+    rec = decode_chunk(buf, [(off_a, lay_a), (off_b, lay_b)], force_off, force_bytes, np.float32)
+    assert rec["steps"] == steps and np.array_equal(rec["force"], f)
+    for (gi, name), val in truth.items():
+        assert np.array_equal(rec["groups"][gi][name], val)
