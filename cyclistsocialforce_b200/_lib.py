@@ -150,6 +150,8 @@ SIGNATURES = {
     "csf_spatial_order_f64": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "csf_tile_sources_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "csf_tile_sources_f64": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "csf_tile_sources_bicycle_f32": (C.c_int, [_vp, _vp, _dbl, _i64, _vp, _vp, _vp, _vp]),
+    "csf_tile_sources_bicycle_f64": (C.c_int, [_vp, _vp, _dbl, _i64, _vp, _vp, _vp, _vp]),
     "csf_pair_forces_tiled_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp, _vp, C.c_int, _vp]),
     "csf_pair_forces_tiled_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _FP, _vp, C.c_int, _vp, _sz, _vp, _vp, _vp, C.c_int, _vp]),
     "csf_tiled_prepare_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp, _vp]),

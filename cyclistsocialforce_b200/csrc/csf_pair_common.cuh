@@ -183,6 +183,38 @@ __device__ __forceinline__ void pair_eval2(int32_t x0, int32_t x1, int32_t y0, i
     ay = fma2(FB, UX, ay);
 }
 
+// ---- Bicycle v0.1 elliptic field (reference vehicle.py:1054-1147) for the tiled kernel ---------------
+// e = min((v / v_max)^0.1, 0.7) (updateExcentricity :1054-1064);  b = rho (1 - e cos phi0) / (sqrt(1-e^2) p_decay);
+// P = p_0 exp(-b) / p_decay;  F_rho = P (1 - e cos phi0) / sqrt(1-e^2);  F_phi = P e sin phi0 / sqrt(1-e^2).
+// The sorted copy of such sources carries the heading scaled by the eccentricity, (e cos psi, e sin psi): the
+// field needs nothing else of the source -- e cos phi0 and e sin phi0 are the two products with the unit vector
+// towards the target, e^2 is the squared length -- so a source stays one 16-byte (f64: 32-byte) element and the
+// tile layout, the stages and the survivor buffers are those of the TwoD field.  k.sg0 = log2(e) / p_decay in
+// payload units; the sum is scaled by p_0 / p_decay where the partial sums are reduced.
+template <typename T, bool P2R>
+__device__ __forceinline__ void pair_eval_bike(const Xycs<T>& sr, const Tgt<T>& tg, const PairConst<T>& k, T& ax, T& ay) {
+    T dx, dy;
+    delta(sr, tg, dx, dy);
+    const T r2 = fma(dy, dy, fma(dx, dx, k.tiny));
+    const T rinv = M<T>::rsqrt(r2);
+    const T ux = dx * rinv, uy = dy * rinv;
+    const T ec = fma(uy, sr.s, ux * sr.c);             // e cos phi0
+    const T es = fma(-ux, sr.s, uy * sr.c);            // e sin phi0
+    const T t = fma(uy, tg.s, ux * tg.c);
+    bool vis = t <= k.ncosH;
+    if (P2R) vis = vis && (fma(tg.s, ux, -(tg.c * uy)) <= (T)0);
+    const T ke = M<T>::rsqrt(fma(-sr.s, sr.s, fma(-sr.c, sr.c, (T)1)));   // 1 / sqrt(1 - e^2)
+    const T g = ((T)1 - ec) * ke;
+    const T rho = r2 * rinv;
+    const T P = M<T>::ex2(-(rho * g * k.sg0));
+    const T fr = vis ? P * g : (T)0;
+    const T fp = vis ? P * (es * ke) : (T)0;
+    ax = fma(fr, ux, ax);
+    ax = fma(-fp, uy, ax);
+    ay = fma(fr, uy, ay);
+    ay = fma(fp, ux, ay);
+}
+
 // ---- mbarrier / TMA bulk-copy primitives (sm_90+/sm_100a) --------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -247,8 +279,11 @@ template <typename T> inline PairConst<T> make_const(const CsfFieldParams* fp, b
     k.qc = (T)(-fp->e_1 * fp->e_1);
     k.ncosH = (fp->hfov * 0.5 >= CSF_PI) ? (T)2 : (T)(-cos(fp->hfov * 0.5));
     k.tiny = (T)(is_f32 ? 1e-6 : 1e-200);
+    if (fp->field_kind == 1) k.sg0 = (T)(kappa / fp->p_decay);   // v0.1 Bicycle field: exponent per payload unit
     return k;
 }
+// amplitude the reduced sums are scaled with
+inline double field_amplitude(const CsfFieldParams* fp) { return fp->field_kind == 1 ? fp->p_0 / fp->p_decay : fp->f_0; }
 
 
 }  // namespace

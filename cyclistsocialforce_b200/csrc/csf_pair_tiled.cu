@@ -173,9 +173,20 @@ template <bool P2R> struct TileAcc64 {
     __device__ __forceinline__ void merge(const TileAcc64& o) { x0 += o.x0; y0 += o.y0; x1 += o.x1; y1 += o.y1; }
     __device__ __forceinline__ void total(double& sx, double& sy) const { sx = x0 + x1; sy = y0 + y1; }
 };
-template <typename T, bool P2R> struct TileAccSel;
-template <bool P2R> struct TileAccSel<float, P2R> { typedef TileAcc32<P2R> type; };
-template <bool P2R> struct TileAccSel<double, P2R> { typedef TileAcc64<P2R> type; };
+// v0.1 Bicycle field (FIELD 1; the sources' headings arrive scaled by their eccentricity): either precision,
+// one scalar evaluation per source -- a legacy field, not on the benchmarked path
+template <typename T, bool P2R> struct TileAccBike {
+    T x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    __device__ __forceinline__ void eval(const SrcA<T>& A, const SrcB<T>& B, const Tgt<T>& tg, const PairConst<T>& k) {
+        pair_eval_bike<T, P2R>(src0(A, B), tg, k, x0, y0);
+        pair_eval_bike<T, P2R>(src1(A, B), tg, k, x1, y1);
+    }
+    __device__ __forceinline__ void merge(const TileAccBike& o) { x0 += o.x0; y0 += o.y0; x1 += o.x1; y1 += o.y1; }
+    __device__ __forceinline__ void total(T& sx, T& sy) const { sx = x0 + x1; sy = y0 + y1; }
+};
+template <typename T, bool P2R, int FIELD> struct TileAccSel { typedef TileAccBike<T, P2R> type; };
+template <bool P2R> struct TileAccSel<float, P2R, 0> { typedef TileAcc32<P2R> type; };
+template <bool P2R> struct TileAccSel<double, P2R, 0> { typedef TileAcc64<P2R> type; };
 
 // ---- bounding circles ---------------------------------------------------------------------------
 __device__ __forceinline__ void pad_entry(Xycs<float>& e) { e.xq = 1 << 30; e.yq = 1 << 30; e.c = 1.f; e.s = 0.f; }
@@ -233,10 +244,18 @@ template <> struct BBox<double> {
 // identity), write them in the SrcA/SrcB layout with the tile's bounding circle, then combine the 16
 // tile boxes into the chunk's bounding circle.  Entries past n are padded with a far-away sentinel
 // that contributes exactly 0 and is not part of any bounding circle.
+// speed: sources with the v0.1 Bicycle field (nullptr: TwoD field) -- their entries of the sorted copy carry the
+// heading scaled by the eccentricity e = min((v / v_max)^0.1, 0.7) (vehicle.py:1054-1064), padding e = 0.
+template <typename T> __device__ __forceinline__ void scale_heading(Xycs<T>& a, bool valid, const T* speed, int64_t i, T v_max) {
+    const T e = valid ? (T)fmin(pow((double)speed[i] / (double)v_max, 0.1), 0.7) : (T)0;
+    a.c *= e;
+    a.s *= e;
+}
 template <typename T>
 __global__ void __launch_bounds__(kCT * 32)
 tile_sources_kernel(const Xycs<T>* __restrict__ xycs, int64_t n, const int64_t* __restrict__ perm,
-                    unsigned char* __restrict__ sorted, Tile<T>* __restrict__ tiles, int64_t n_tiles) {
+                    unsigned char* __restrict__ sorted, Tile<T>* __restrict__ tiles, int64_t n_tiles,
+                    const T* __restrict__ speed, T v_max) {
     __shared__ __align__(16) unsigned char boxes_raw[kCT * sizeof(BBox<T>)];
     BBox<T>* boxes = reinterpret_cast<BBox<T>*>(boxes_raw);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -246,8 +265,13 @@ tile_sources_kernel(const Xycs<T>* __restrict__ xycs, int64_t n, const int64_t* 
         const int64_t i0 = t * kTileS + lane, i1 = i0 + 32;
         Xycs<T> a, b;
         const bool va = i0 < n, vb = i1 < n;
-        if (va) a = xycs[perm ? perm[i0] : i0]; else pad_entry(a);
-        if (vb) b = xycs[perm ? perm[i1] : i1]; else pad_entry(b);
+        const int64_t j0 = va ? (perm ? perm[i0] : i0) : 0, j1 = vb ? (perm ? perm[i1] : i1) : 0;
+        if (va) a = xycs[j0]; else pad_entry(a);
+        if (vb) b = xycs[j1]; else pad_entry(b);
+        if (speed) {
+            scale_heading(a, va, speed, j0, v_max);
+            scale_heading(b, vb, speed, j1, v_max);
+        }
         SrcA<T> A;
         SrcB<T> B;
         split(a, b, A, B);
@@ -513,6 +537,31 @@ __device__ __forceinline__ void lobe_reaches2(const Tile<double>& blk, const Src
     r1 = lobe_reaches<double, double>(blk, A.x1, A.y1, B.c1, B.s1, lobe, tiny);
 }
 
+// v0.1 Bicycle field: the level set b = const of a source is an ellipse with the source in one focus, eccentricity
+// e and the long axis along the heading -- reach(phi0) = K sqrt(1 - e^2) / (1 - e cos phi0), K = lobe[0] (payload
+// units; b = K / p_decay is where |F| has fallen to 2^-cutoff_log2 p_0 / p_decay).  (c, s) = heading scaled by e.
+// w = max of e cos(phi) over the directions under which the source sees the block circle, d - R_b = lower bound
+// of the distance: the source cannot matter if (d - R_b) (1 - w) > K sqrt(1 - e^2).
+template <typename T, typename P>
+__device__ __forceinline__ bool bike_reaches(const Tile<T>& blk, P x, P y, T c, T s, T K, T tiny) {
+    T dx, dy;
+    block_delta(blk, x, y, dx, dy);
+    const T d2 = fma(dy, dy, fma(dx, dx, tiny));
+    const T rinv = M<T>::rsqrt(d2);
+    const T d = d2 * rinv;
+    const T Rb = (T)blk.R;
+    const T e2 = fmin(fma(s, s, c * c), (T)0.5);          // e <= 0.7
+    const T e = M<T>::sqrt(e2);
+    const T cphi = fma(dy, s, dx * c) * rinv;             // e cos(phi0)
+    const T sphi = fabs(fma(dy, c, -(dx * s))) * rinv;    // e |sin(phi0)|
+    const T sdel = fmin(Rb * rinv, (T)1);
+    const T cdel = M<T>::sqrt(fmax(fma(-sdel, sdel, (T)1), (T)0));
+    T w = fma(cphi, cdel, sphi * sdel);                   // e cos(|phi0| - delta)
+    w = (cphi >= e * cdel) ? e : w;                       // the circle straddles the heading direction
+    w = fmin(w, e);
+    return (d - Rb) * ((T)1 - w) <= K * M<T>::sqrt((T)1 - e2) * (T)1.0001;
+}
+
 // named barrier 1 among the filter warps only
 template <int FW> __device__ __forceinline__ void filter_barrier() {
     if (FW > 1) asm volatile("bar.sync 1, %0;" ::"n"(FW * 32) : "memory");
@@ -554,7 +603,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // with their circle records; n == -1 closes the item, n == -2 ends the kernel.
 // Buffer protocol (filter -> evaluate warps): bdesc[slot] = {item, dynamic tiles, flags, target set}:
 // BUF_LAST = last buffer of the item (the evaluate warps write their sums), BUF_EXIT = leave.
-template <typename T, bool P2R, int FW, int EW>
+// FIELD 0: TwoD field (vehicle.py:1560-1648); FIELD 1: v0.1 Bicycle field (vehicle.py:1054-1147; bike_reaches, pair_eval_bike).
+template <typename T, bool P2R, int FW, int EW, int FIELD = 0>
 __global__ void __launch_bounds__((1 + FW + EW) * 32, (sizeof(T) == 4 && EW == kNarrowEW) ? CSF_TILED_MINB : 1)
 pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __restrict__ tiles, int64_t n_tiles,
                   const Xycs<T>* __restrict__ tgt, const int64_t* __restrict__ tgt_perm, int64_t n_tgt,
@@ -801,6 +851,7 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
             {   // pad the last dynamic tile with far-away sentinels (they contribute exactly 0)
                 Xycs<T> pad;
                 pad_entry(pad);
+                if (FIELD == 1) { pad.c = (T)0; pad.s = (T)0; }       // eccentricity 0
                 for (int kidx = count + ftid; kidx < n_dt * kTileS; kidx += FW * 32)
                     write_entry(sb, kidx, pos_x(pad), pos_y(pad), pad.c, pad.s);
             }
@@ -887,7 +938,12 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                         const SrcA<T> A = reinterpret_cast<const SrcA<T>*>(base + (size_t)t * kTileB)[lane];
                         const SrcB<T> B = reinterpret_cast<const SrcB<T>*>(base + (size_t)t * kTileB + 32 * sizeof(SrcA<T>))[lane];
                         bool p0, p1;
-                        lobe_reaches2(blk, A, B, lobe, k.tiny, p0, p1);
+                        if (FIELD == 1) {
+                            p0 = bike_reaches<T, P>(blk, A.x0, A.y0, B.c0, B.s0, lobe[0], k.tiny);
+                            p1 = bike_reaches<T, P>(blk, A.x1, A.y1, B.c1, B.s1, lobe[0], k.tiny);
+                        } else {
+                            lobe_reaches2(blk, A, B, lobe, k.tiny, p0, p1);
+                        }
                         mb0[u] = __ballot_sync(0xffffffffu, p0 && (lane < valid));
                         mb1[u] = __ballot_sync(0xffffffffu, p1 && (lane + 32 < valid));
                         if (FW > 1 && lane == 0) fm[t] = make_uint2(mb0[u], mb1[u]);
@@ -1005,7 +1061,7 @@ pair_tiled_kernel(const unsigned char* __restrict__ sorted, const Tile<T>* __res
                     if (stats) n_eval += (unsigned long long)__popc(mask) * kTileS;
                     const Xycs<T> te = mytgt[q];
                     const Tgt<T> tg = *reinterpret_cast<const Tgt<T>*>(&te);
-                    typename TileAccSel<T, P2R>::type acc0, acc1;
+                    typename TileAccSel<T, P2R, FIELD>::type acc0, acc1;
                     // two surviving tiles per iteration: four independent pair evaluations in flight
                     while (mask & (mask - 1)) {
                         const int t0 = __ffs(mask) - 1;
@@ -1131,6 +1187,10 @@ template <typename T, int FW, int EW> int tiled_shape_ctas() {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, (1 + FW + EW) * 32, smem);
         best = nb < best ? nb : best;
     }
+    // the v0.1 Bicycle-field instances share the plan (grid sized for the TwoD instances: CTAs that are not
+    // resident at once simply start later -- items come from a counter, no CTA waits for another)
+    cudaFuncSetAttribute(pair_tiled_kernel<T, false, FW, EW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(pair_tiled_kernel<T, true, FW, EW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     return best < 1 ? 1 : best;
 }
 // resident CTAs per SM of the narrow (wide = false) or wide CTA shape on the current device
@@ -1248,6 +1308,17 @@ bool field_decay_rate_by_angle(const CsfFieldParams* fp, int NC, double* rate_c)
     return true;
 }
 
+// v0.1 Bicycle field (vehicle.py:1054-1147): |F| = (p_0 / p_decay) exp(-b) sqrt(g^2 + (e sin(phi0))^2 / (1 - e^2)),
+// g = (1 - e cos(phi0)) / sqrt(1 - e^2), b = rho g / p_decay, and e <= 0.7 (:1062-1064): the square root is at
+// most 2.58 < 2^1.5, so |F| < 2^-cutoff_log2 p_0 / p_decay wherever b > (cutoff_log2 + 1.5) ln 2, i.e. beyond
+// rho = K sqrt(1 - e^2) / (1 - e cos(phi0)) with K [m] below; straight ahead at e = 0.7 that is K sqrt(1.7 / 0.3).
+constexpr double kBikeEmax = 0.7;
+const double kBikeAhead = sqrt((1.0 + kBikeEmax) / (1.0 - kBikeEmax));
+double bike_reach_K(const CsfFieldParams* fp) {
+    const double bits = fp->cutoff_log2 > 0.0 ? fp->cutoff_log2 : 40.0;
+    return (bits + 1.5) * 0.6931471805599453 * fp->p_decay;
+}
+
 template <typename T> CullConst<T> make_cull(const CsfFieldParams* fp, bool is_f32) {
     CullConst<T> c;
     const double a = fmin(fp->hfov * 0.5, CSF_PI);
@@ -1257,6 +1328,17 @@ template <typename T> CullConst<T> make_cull(const CsfFieldParams* fp, bool is_f
     const T never = (T)(is_f32 ? 3.0e9 : 1e150);          // (payload positions span < 2^31 units)
     c.dmax = never;
     for (int b = 0; b < kLobeBins; ++b) c.lobe[b] = never;
+    if (fp->field_kind == 1) {
+        // v0.1 Bicycle field: lobe[0] = K of bike_reaches, dmax = the reach straight ahead at the largest eccentricity
+        if (is_f32) {
+            const double K = bike_reach_K(fp) * 1.0001 / fp->q_scale;
+            if (K * kBikeAhead < 3.0e9) {
+                c.lobe[0] = (T)K;
+                c.dmax = (T)(K * kBikeAhead);
+            }
+        }
+        return c;
+    }
     if (is_f32) {
         // exp(-d * rate) = 2^-cutoff_log2  ->  reach d.  The bounds cost ~1 ms of host time per parameter
         // set: a small cache (several source classes alternate within a step)
@@ -1305,11 +1387,12 @@ template <typename T> CullConst<T> make_cull(const CsfFieldParams* fp, bool is_f
 }
 
 template <typename T>
-int tile_sources(const void* xycs, int64_t n, const int64_t* perm, void* sorted, void* tiles, cudaStream_t st) {
+int tile_sources(const void* xycs, int64_t n, const int64_t* perm, void* sorted, void* tiles, cudaStream_t st,
+                 const void* speed = nullptr, double v_max = 1.0) {
     if (n <= 0) return 0;
     const int64_t n_tiles = (n + kTileS - 1) / kTileS, n_chunks = (n_tiles + kCT - 1) / kCT;
     tile_sources_kernel<T><<<(unsigned)n_chunks, kCT * 32, 0, st>>>(
-        (const Xycs<T>*)xycs, n, perm, (unsigned char*)sorted, (Tile<T>*)tiles, n_tiles);
+        (const Xycs<T>*)xycs, n, perm, (unsigned char*)sorted, (Tile<T>*)tiles, n_tiles, (const T*)speed, (T)v_max);
     CSF_CHECK_LAUNCH("tile_sources_kernel");
     return 0;
 }
@@ -1325,7 +1408,8 @@ int pair_tiled(const void* sorted, const void* tiles, int64_t n_src, const void*
                const unsigned int* item_order, unsigned int* item_cost, unsigned long long* stats, int flags,
                cudaStream_t st) {
     if (n_tgt <= 0) return 0;
-    if (n_src <= 0 || fp->f_0 == 0.0) {
+    const double amplitude = field_amplitude(fp);
+    if (n_src <= 0 || amplitude == 0.0) {
         if (flags & CSF_TILED_NO_REDUCE) {
             csf_set_error("csf_pair_forces_tiled: CSF_TILED_NO_REDUCE needs sources and f_0 != 0", cudaErrorInvalidValue);
             return -(int)cudaErrorInvalidValue;
@@ -1365,22 +1449,24 @@ int pair_tiled(const void* sorted, const void* tiles, int64_t n_src, const void*
     const Tile<T>* tiles_c = (const Tile<T>*)tiles;
     const Xycs<T>* tgt_c = (const Xycs<T>*)tgt;
     const Tile<T>* tblocks_c = tblocks;
-#define CSF_TILED_LAUNCH(P2R_, FW_, EW_)                                                                             \
+#define CSF_TILED_LAUNCH(P2R_, FW_, EW_, FIELD_)                                                                     \
     cfg.blockDim = dim3((1 + FW_ + EW_) * 32);                                                                       \
-    cudaLaunchKernelEx(&cfg, pair_tiled_kernel<T, P2R_, FW_, EW_>, sorted_c, tiles_c, pl.n_tiles, tgt_c, tgt_perm, n_tgt, \
-                       tblocks_c, k, cc, partial, pl.n_groups, pl.n_tblocks, counter, item_order, item_cost, stats)
-    if (pl.wide) {
-        if (fp->p2r) { CSF_TILED_LAUNCH(true, kWideFW, kWideEW); }
-        else { CSF_TILED_LAUNCH(false, kWideFW, kWideEW); }
+    cudaLaunchKernelEx(&cfg, pair_tiled_kernel<T, P2R_, FW_, EW_, FIELD_>, sorted_c, tiles_c, pl.n_tiles, tgt_c, tgt_perm, \
+                       n_tgt, tblocks_c, k, cc, partial, pl.n_groups, pl.n_tblocks, counter, item_order, item_cost, stats)
+#define CSF_TILED_LAUNCH_SHAPE(P2R_, FIELD_)                                                                         \
+    if (pl.wide) { CSF_TILED_LAUNCH(P2R_, kWideFW, kWideEW, FIELD_); }                                               \
+    else { CSF_TILED_LAUNCH(P2R_, kNarrowFW, kNarrowEW, FIELD_); }
+    if (fp->field_kind == 1) {
+        if (fp->p2r) { CSF_TILED_LAUNCH_SHAPE(true, 1) } else { CSF_TILED_LAUNCH_SHAPE(false, 1) }
     } else {
-        if (fp->p2r) { CSF_TILED_LAUNCH(true, kNarrowFW, kNarrowEW); }
-        else { CSF_TILED_LAUNCH(false, kNarrowFW, kNarrowEW); }
+        if (fp->p2r) { CSF_TILED_LAUNCH_SHAPE(true, 0) } else { CSF_TILED_LAUNCH_SHAPE(false, 0) }
     }
+#undef CSF_TILED_LAUNCH_SHAPE
 #undef CSF_TILED_LAUNCH
     CSF_CHECK_LAUNCH("pair_tiled_kernel");
     if (flags & CSF_TILED_NO_REDUCE) return 0;          // the caller sums partial[group][target][2] * f_0 itself
     const int64_t n2 = n_tgt * 2;
-    reduce_groups_kernel<T><<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(partial, pl.n_groups, n_tgt, (T)fp->f_0, frep,
+    reduce_groups_kernel<T><<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(partial, pl.n_groups, n_tgt, (T)amplitude, frep,
                                                                            accumulate);
     CSF_CHECK_LAUNCH("reduce_groups_kernel");
     return 0;
@@ -1427,6 +1513,7 @@ size_t csf_pair_tiled_workspace_bytes(int64_t n_src, int64_t n_tgt, int elem_byt
     return kWsHeader + tiled_ws_blocks_bytes<double>(pl) + (size_t)pl.n_groups * (size_t)n_tgt * 2 * 8;
 }
 double csf_field_cutoff_distance(const CsfFieldParams* fp) {
+    if (fp->field_kind == 1) return bike_reach_K(fp) * kBikeAhead;
     const double rate = field_min_decay_rate(fp);
     const double bits = fp->cutoff_log2 > 0.0 ? fp->cutoff_log2 : 40.0;
     return rate > 0.0 ? bits * 0.6931471805599453 / rate : INFINITY;
@@ -1435,6 +1522,12 @@ int csf_field_reach_table(const CsfFieldParams* fp, int n_bins, double* reach_m)
     // host-only: the reach table of the lobe filter in metres (bin b covers cos(phi) in
     // [-1 + 2b/n_bins, -1 + 2(b+1)/n_bins]); n_bins must be kLobeBins
     if (n_bins != kLobeBins) return -1;
+    if (fp->field_kind == 1) {      // the ellipse of bike_reaches at the largest eccentricity, at each bin's upper edge
+        const double K = bike_reach_K(fp);
+        for (int b = 0; b < kLobeBins; ++b)
+            reach_m[b] = K * sqrt(1.0 - kBikeEmax * kBikeEmax) / (1.0 - kBikeEmax * (-1.0 + 2.0 * (b + 1) / kLobeBins));
+        return 0;
+    }
     CsfFieldParams q = *fp;
     if (!(q.q_scale > 0.0)) q.q_scale = 1.0;
     const CullConst<float> c = make_cull<float>(&q, true);
@@ -1474,6 +1567,14 @@ int csf_tile_sources_f32(const void* xycs, int64_t n, const int64_t* perm, void*
 }
 int csf_tile_sources_f64(const void* xycs, int64_t n, const int64_t* perm, void* sorted, void* tiles, csf_stream_t st) {
     return tile_sources<double>(xycs, n, perm, sorted, tiles, (cudaStream_t)st);
+}
+int csf_tile_sources_bicycle_f32(const void* xycs, const float* speed, double v_max, int64_t n, const int64_t* perm,
+                                 void* sorted, void* tiles, csf_stream_t st) {
+    return tile_sources<float>(xycs, n, perm, sorted, tiles, (cudaStream_t)st, speed, v_max);
+}
+int csf_tile_sources_bicycle_f64(const void* xycs, const double* speed, double v_max, int64_t n, const int64_t* perm,
+                                 void* sorted, void* tiles, csf_stream_t st) {
+    return tile_sources<double>(xycs, n, perm, sorted, tiles, (cudaStream_t)st, speed, v_max);
 }
 int csf_pair_forces_tiled_f32(const void* sorted, const void* tiles, int64_t n_src, const void* tgt,
                               const int64_t* tgt_perm, int64_t n_tgt, const CsfFieldParams* fp, float* frep,

@@ -563,10 +563,9 @@ class Engine:
         if self.n_total > 1 and scenario_size is None:
             for s, c, _, _ in self.classes:
                 wsb = max(wsb, int(self.lib.csf_pair_workspace_bytes(c, self.n_agents, 4 if self.f32 else 8)))
-        # tiled + culled kernel for every class with the TwoD field; Bicycle-field (v0.1) classes of a mixed
-        # crowd go through their dense kernel and add to the same sums
+        # tiled + culled kernel for every source class, TwoD field or v0.1 Bicycle field (the latter's sorted
+        # copy carries the headings scaled by the eccentricities: csf_tile_sources_bicycle)
         self.tiled = (scenario_size is None and self.n_total > 1 and
-                      any(fp.field_kind == 0 for _, _, _, fp in self.classes) and
                       (pair_mode == "tiled" or (pair_mode == "auto" and self.n_total >= 2048)))
         self.pair_stats = torch.zeros(16 + 4 * 16384, dtype=torch.int64, device=self.device) if count_pairs else None
         self._tiles = []
@@ -679,8 +678,6 @@ class Engine:
                    "csf_spatial_bbox")
         self.gpu_launches += 1
         for ci, (s, c, _, fp) in enumerate(self.classes):
-            if fp.field_kind == 1:
-                continue
             tl = self._tiles[ci]
             src = C.c_void_p(self.payload.data_ptr() + s * self.elem_bytes)
             _lib.check(self._fn("csf_spatial_order")(src, c, _ptr(self._key_box), _ptr(tl["perm"]), _ptr(self._order_ws),
@@ -746,6 +743,19 @@ class Engine:
                 tgt = C.c_void_p(self.payload.data_ptr() + self.global_offset * self.elem_bytes)
                 for ci, (s, c, _, fp) in enumerate(self.classes):
                     src = C.c_void_p(self.payload.data_ptr() + s * self.elem_bytes)
+                    if fp.field_kind == 1 and self.tiled:
+                        g, _ = self._ecc[s]
+                        tl = self._tiles[ci]
+                        _lib.check(self._fn("csf_tile_sources_bicycle")(src, _ptr(g.v), fp.v_max, c, _ptr(tl["perm"]),
+                                                                        _ptr(tl["sorted"]), _ptr(tl["tiles"]), st),
+                                   "csf_tile_sources_bicycle")
+                        _lib.check(self._fn("csf_pair_forces_tiled")(
+                            _ptr(tl["sorted"]), _ptr(tl["tiles"]), c, tgt, _ptr(self._tgt_perm), self.n_agents,
+                            C.byref(fp), _ptr(self.frep), 1 if ci > 0 else 0, _ptr(self.ws), self.ws.numel(),
+                            _ptr(tl["item_order"]), _ptr(tl["item_cost"]), _ptr(self.pair_stats), 0, st),
+                            "csf_pair_forces_tiled")
+                        self.gpu_launches += 4   # tile build, block bounds, pair, reduce
+                        continue
                     if fp.field_kind == 1:
                         g, ecc = self._ecc[s]
                         _lib.check(self._fn("csf_bicycle_eccentricity")(_ptr(g.v), g.n, fp.v_max, _ptr(ecc), st),

@@ -256,6 +256,15 @@ int csf_tile_sources_f32(const void* xycs, int64_t n, const int64_t* perm, void*
                          csf_stream_t stream);
 int csf_tile_sources_f64(const void* xycs, int64_t n, const int64_t* perm, void* sorted, void* tiles,
                          csf_stream_t stream);
+/* Sources with the v0.1 `Bicycle` elliptic field (fp->field_kind 1; Bicycle.calcRepulsiveForce / calcPotential /
+ * updateExcentricity, vehicle.py:1054-1147) through the tiled kernel: the sorted copy carries every source's
+ * heading scaled by its eccentricity e = min((speed / v_max)^0.1, 0.7) (`speed`: the sources' v column, same
+ * indexing as xycs; v_max = v_max_riding[1]); csf_pair_forces_tiled_* with the same fp then evaluates that field,
+ * culling with the elliptic level sets of the potential (f32: beyond 2^-cutoff_log2 p_0 / p_decay). */
+int csf_tile_sources_bicycle_f32(const void* xycs, const float* speed, double v_max, int64_t n, const int64_t* perm,
+                                 void* sorted, void* tiles, csf_stream_t stream);
+int csf_tile_sources_bicycle_f64(const void* xycs, const double* speed, double v_max, int64_t n, const int64_t* perm,
+                                 void* sorted, void* tiles, csf_stream_t stream);
 int csf_pair_forces_tiled_f32(const void* sorted, const void* tiles, int64_t n_src, const void* tgt_xycs,
                               const int64_t* tgt_perm, int64_t n_tgt, const CsfFieldParams* fp,
                               float* frep_xy, int accumulate, void* workspace, size_t workspace_bytes,

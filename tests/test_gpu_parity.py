@@ -376,10 +376,64 @@ def test_tiled_clusters_with_gaps(dtype):
     assert np.abs(res["tiled"][1] - res["dense"][1]).max() < (1e-9 if dtype == torch.float64 else 2e-3)
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("p2r", [False, True])
+def test_bicycle_field_tiled(dtype, p2r):
+    """v0.1 ``Bicycle`` elliptic field (vehicle.py:1054-1147) through the tiled + culled kernel: a crowd two
+    cut-off distances wide (the f32 far-field cut-off along the potential's level-set ellipses is active) with
+    speeds from standstill (eccentricity 0) to beyond the 0.7 cap, a size that is not a multiple of the tile --
+    against the oracle and against the dense Bicycle kernel, both priority rules."""
+    n = 3011
+    s0, q = co.synthetic_crowd(n, seed=17, spacing=12.0)
+    rng = np.random.default_rng(4)
+    s0[:, 3] = np.where(rng.uniform(size=n) < 0.25, rng.uniform(0.0, 1e-3, n), rng.uniform(0.0, 9.0, n))
+    s0[:7, 3] = 0.0
+    res = {}
+    for mode in ("tiled", "dense"):
+        eng, g = make_engine("bicycle", s0, 5.0, q, dtype=dtype, pair_mode=mode, count_pairs=True,
+                             priority_rule="p2r" if p2r else "unregulated")
+        assert eng.tiled == (mode == "tiled")
+        eng._pair_and_road()
+        res[mode] = eng.frep.cpu().numpy().astype(float)
+        if mode == "tiled":
+            frac = float(eng.pair_stats[0].item()) / (n * n)
+    p = co.default_params("bicycle")
+    ref, margin = co.pair_forces(s0[:, 0], s0[:, 1], s0[:, 2], co.field_params_array([p])[0], p2r=p2r,
+                                 src_kind=np.ones(n, int), src_v=s0[:, 3], bicycle_params=p, return_margin=True)
+    ok = margin > (1e-9 if dtype == torch.float64 else 1e-5)
+    assert ok.mean() > 0.9
+    err = _vec_rel(res["tiled"][ok], ref[ok], 1e-6 if dtype == torch.float64 else 1e-3)
+    report(test="bicycle_field_tiled", dtype=str(dtype), p2r=p2r, n=n, max_rel=float(err.max()),
+           evaluated_pair_fraction=frac)
+    assert err.max() < (F64_TOL if dtype == torch.float64 else F32_TOL)
+    assert _vec_rel(res["tiled"], res["dense"], 1e-3).max() < (1e-10 if dtype == torch.float64 else 2e-5)
+    assert frac < (0.4 if dtype == torch.float32 else 0.75)      # view cones (+ f32: the level-set cut-off) cull
+
+
+def test_bicycle_crowd_steps_tiled_equals_dense():
+    """A pure v0.1 Bicycle crowd stepped through the tiled kernel (re-sorts included) equals the dense engine and
+    the oracle."""
+    n = 2100
+    s0, q = co.synthetic_crowd(n, seed=23, spacing=3.0)
+    res = {}
+    for mode in ("dense", "tiled"):
+        eng, g = make_engine("bicycle", s0, 5.0, q, dtype=torch.float64, pair_mode=mode, resort_every=2)
+        for _ in range(5):
+            eng.step()
+        eng.check_status()
+        res[mode] = (g.states_numpy(), eng.force.cpu().numpy())
+    assert np.abs(res["dense"][0] - res["tiled"][0]).max() < 1e-10
+    assert np.abs(res["dense"][1] - res["tiled"][1]).max() < 1e-10
+    W = oracle_world("bicycle", s0, np.full(n, 5.0), q)
+    for _ in range(5):
+        W.step()
+    assert np.abs(res["tiled"][0] - W.groups[0].s).max() < 1e-9
+
+
 def test_mixed_crowd_with_v01_bicycles_keeps_the_tiled_kernel():
     """A crowd that contains ``Bicycle`` (v0.1 elliptic field, vehicle.py:1054-1147) road users next to
-    TwoD-field ones: the TwoD-field classes still go through the tiled + culled kernel, the Bicycle class
-    through its dense kernel, both into the same sums -- equal to the all-dense engine and to the oracle."""
+    TwoD-field ones: every class goes through the tiled + culled kernel (the Bicycle class with its own field
+    and cull bound), into the same sums -- equal to the all-dense engine and to the oracle."""
     from cyclistsocialforce_b200 import parameters as P
     from cyclistsocialforce_b200.engine import AgentGroup, Engine
     from cyclistsocialforce_b200.synthetic import queues_with_start
