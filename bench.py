@@ -326,6 +326,34 @@ def run(args, out):
     agent_ms = [e[2].elapsed_time(e[3]) for e in ev2]
     ungraphed_ms = statistics.mean(e[0].elapsed_time(e[3]) for e in ev2)
     eng.check_status()
+    if os.environ.get("CSF_BENCH_DEBUG"):
+        print("second pass, pair kernel ms per step (first pair call of the pass: %d):" % (eng._pair_calls - args.steps),
+              " ".join(f"{t:.3f}" for t in pair_ms), file=sys.stderr, flush=True)
+        if eng.tiled and fused:
+            eng.pair_stats = eng.pair_stats_ptr_backup
+            eng.pair_stats.zero_()
+            eng._pair_alone()
+            sync()
+            print("executed pairs per launch now: %.4g (before the timed steps: %.4g)" % (
+                float(eng.pair_stats[0].item()), executed_pairs), file=sys.stderr, flush=True)
+            eng.pair_stats = None
+    # On a sharded crowd the intervals of that pass also hold the ranks' skew (waits for the peers, launches that
+    # a host issues late): the pair kernel's own duration is taken from launches of [tile build, pair kernel]
+    # alone on this rank's shard while every rank is quiescent (the pair kernel never talks to a peer)
+    pair_timing = "second pass of the same K steps, launched kernel by kernel"
+    if world > 1 and fused:
+        barrier()
+        sync()
+        ev3 = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(min(args.steps, 30))]
+        for k, e in enumerate(ev3):
+            flush.fill_(k & 0xFF)
+            eng._pair_alone(mark=lambda i, e=e: e[i].record())
+        sync()
+        barrier()
+        pair_ms = [e[1].elapsed_time(e[2]) for e in ev3]
+        pair_timing = ("%d launches of [tile build, pair kernel] alone on rank 0's shard after the timed steps, L2 flushed "
+                       "before each; prepare / per-agent kernel (with their waits for the peers) from a second pass of "
+                       "the same K steps launched kernel by kernel" % len(ev3))
     value = N_AGENTS * args.steps / (total_ms * 1e-3)
     ms_per_step = total_ms / args.steps
 
@@ -397,9 +425,9 @@ def run(args, out):
                          "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops,
                          "traffic": traffic, "peak_source": "csf_ffma_peak micro-benchmark in this run",
                          "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs_per_launch,
-                         "kernel_ms": pair_s * 1e3, "share_of_step": pair_s * 1e3 / ungraphed_ms,
+                         "kernel_ms": pair_s * 1e3, "share_of_step": pair_s * 1e3 / (ungraphed_ms if world == 1 else ms_per_step),
                          "prepare_kernel_ms": statistics.mean(prep_ms),
-                         "timing": "second pass of the same K steps, launched kernel by kernel (ms_per_step of that pass: %.4f)" % ungraphed_ms},
+                         "timing": pair_timing + " (ms_per_step of that pass: %.4f)" % ungraphed_ms},
             "roofline_agent_kernel": {"bound": "hbm", "kernel": "agent_kernel<float,TWOD,STEP>" + (" (+ reduction of the pair kernel's partial sums" + (", payload exchange" if world > 1 else "") + ")" if fused else ""),
                                       "achieved": n_local * BYTES_PER_AGENT_STEP / agent_s / 1e9, "peak": hbm_peak,
                                       "unit": "GB/s", "frac": n_local * BYTES_PER_AGENT_STEP / agent_s / 1e9 / hbm_peak,

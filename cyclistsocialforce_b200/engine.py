@@ -50,6 +50,15 @@ def _wrap_angle(a):
     return np.where(a < -np.pi, a + 2 * np.pi, a)
 
 
+#: tuning aid: "refresh" (default) re-sorts the pair kernel's items by cost after the first launch that follows a
+#: spatial re-sort, "stale" keeps the order computed from the costs of the previous spatial order until the next
+#: re-sort (only call 1 refreshes), "none" hands the items out in index order
+_ITEM_ORDER_MODE = os.environ.get("CSF_ITEM_ORDER", "refresh")
+#: tuning aid: visiting order of a shard's targets -- "partition" (default: the order of the agent numbering) or
+#: "curve" (re-sorted along the Hilbert curve of the current bounding box with the sources)
+_SHARD_TARGET_ORDER = os.environ.get("CSF_SHARD_TARGET_ORDER", "partition")
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -493,6 +502,7 @@ class Engine:
             off += g.n
         self.n_agents = sum(g.n for g in self.groups)
         self.n_total = off if n_global is None else int(n_global)
+        self._sharded = n_global is not None
         # Q-format scale of the f32 payload
         if q_scale is None and extent is None and n_global is not None:
             # every rank must quantise the exchanged payload with the same scale: it cannot be derived
@@ -685,6 +695,17 @@ class Engine:
             self.gpu_launches += 2
         if self._single_class:      # one class covering exactly the targets: same order
             self._tgt_perm = self._tiles[0]["perm"]
+        elif self._sharded and _SHARD_TARGET_ORDER == "partition":
+            # A rank's targets are a contiguous range of a numbering along a space-filling curve (the partition,
+            # fixed for the run): they are visited in that order.  Sorting them along the curve of the CURRENT
+            # bounding box instead looks equivalent but is not -- the range is a segment of the numbering's curve,
+            # and along any other curve (the box has moved by a few metres since) it is left and re-entered many
+            # times, so that a few blocks of 64 consecutive targets straddle a jump across the whole region: one
+            # such block streams every source through its filter, and that one item then IS the launch (measured
+            # on a half crowd: pair kernel 0.17 -> 0.27 ms from the first re-sort on).
+            if self._tgt_perm is None:
+                self._tgt_perm = self._buf("tgt_perm", self.n_agents, torch.int64)
+                self._tgt_perm.copy_(torch.arange(self.n_agents, dtype=torch.int64, device=self.device))
         else:
             tgt = C.c_void_p(self.payload.data_ptr() + self.global_offset * self.elem_bytes)
             if self._tgt_perm is None:
@@ -700,7 +721,7 @@ class Engine:
         """Hand the pair kernel's work items out heaviest first (costs measured by the previous launch)."""
         st = self._stream()
         for tl in self._tiles:
-            if tl.get("item_order") is not None:
+            if tl.get("item_order") is not None and _ITEM_ORDER_MODE != "none":
                 _lib.check(self.lib.csf_tiled_item_order(_ptr(tl["item_cost"]), tl["n_items"],
                                                          _ptr(tl["item_order"]), st), "csf_tiled_item_order")
                 self.gpu_launches += 1
@@ -714,7 +735,9 @@ class Engine:
             if self.exchange is not None and hasattr(self.exchange, "begin_step"):
                 self.exchange.begin_step()  # the keys are computed from the peers' payload: wait for their pushes
             self._refresh_order()
-        elif self._pair_calls == 1:
+            self._item_order_at = self._pair_calls
+        elif self._pair_calls == (1 if _ITEM_ORDER_MODE == "stale" else getattr(self, "_item_order_at", 0) + 1):
+            # the launch that followed the re-sort has measured the items' costs in the new order
             self._refresh_item_order()
 
     def _pair_and_road(self):
@@ -856,6 +879,29 @@ class Engine:
         mark(3)
         if exchange and self.exchange is not None and not self._peer_fused():
             self.exchange(self.payload)
+
+    def _pair_alone(self, mark=None):
+        """Measurement aid (bench.py on a sharded crowd): the tile build WITHOUT the wait for the peers, then the
+        pair kernel, on whatever the payload buffer holds -- no reduction, no per-agent kernel, no exchange; the
+        partial sums it leaves are overwritten by the next step.  Call it only while every rank is quiescent."""
+        assert self._fused and self._order_valid
+        mark = mark or (lambda i: None)
+        st = self._stream()
+        s, c, _, fp = self.classes[0]
+        tl = self._tiles[0]
+        src = C.c_void_p(self.payload.data_ptr() + s * self.elem_bytes)
+        tgt = C.c_void_p(self.payload.data_ptr() + self.global_offset * self.elem_bytes)
+        mark(0)
+        _lib.check(self._fn("csf_tiled_prepare")(src, c, _ptr(tl["perm"]), _ptr(tl["sorted"]), _ptr(tl["tiles"]), tgt,
+                                                 _ptr(self._tgt_perm), self.n_agents, _ptr(self.ws), self.ws.numel(),
+                                                 None, st), "csf_tiled_prepare")
+        mark(1)
+        _lib.check(self._fn("csf_pair_forces_tiled")(
+            _ptr(tl["sorted"]), _ptr(tl["tiles"]), c, tgt, _ptr(self._tgt_perm), self.n_agents, C.byref(fp),
+            _ptr(self.frep), 0, _ptr(self.ws), self.ws.numel(), _ptr(tl["item_order"]), _ptr(tl["item_cost"]),
+            _ptr(self.pair_stats), _lib.CSF_TILED_PREPARED | _lib.CSF_TILED_NO_REDUCE, st), "csf_pair_forces_tiled")
+        mark(2)
+        self.gpu_launches += 2
 
     def _step_kernels(self, exchange=True):
         if self._fused and self.n_total > 1:
