@@ -466,6 +466,54 @@ def test_mixed_crowd_with_v01_bicycles_keeps_the_tiled_kernel():
     assert np.abs(res["tiled"][0] - ref).max() < 1e-9
 
 
+def test_shard_target_blocks_stay_compact_across_a_resort():
+    """A rank's targets are visited in the order of the partition's numbering, not re-sorted along the curve of
+    the current bounding box: after a re-sort over a box that has changed (a remote road user walked out of it) no
+    work item of the pair kernel may grow -- with targets re-sorted along the new curve a few blocks of 64 span
+    the whole shard region and one item streams every source through its filter.  Timing-free:
+    the items' costs (sources that survive the block filter, written by every launch) are compared."""
+    from cyclistsocialforce_b200 import engine as E, parameters as P
+    from cyclistsocialforce_b200.engine import AgentGroup, Engine
+    from cyclistsocialforce_b200.synthetic import queues_with_start, spatial_order
+    n, lo, hi = 16384, 4096, 8192
+    s0, q = co.synthetic_crowd(n, seed=5, spacing=4.0)
+    order = spatial_order(s0[:, 0], s0[:, 1])
+    s0, q = s0[order], q[order]
+    queues = list(queues_with_start(s0, q))
+    origin, extent = P.payload_frame([s0[:, :2], q[..., :2]])
+    extent = float(extent) + 200.0                      # room for the road user that walks away
+    full = Engine([AgentGroup("twod", s0, P.InvPendulumBicycleParameters(), destqueues=queues, dtype=torch.float32)],
+                  dtype=torch.float32, extent=extent, origin=origin, pair_mode="dense")
+    payload = full.payload.clone()
+    far = int(np.argmax(s0[:, 0] + 1e6 * ((np.arange(n) >= lo) & (np.arange(n) < hi)) * -1.0))   # not one of ours
+
+    def max_costs(mode):
+        old = E._SHARD_TARGET_ORDER
+        E._SHARD_TARGET_ORDER = mode
+        try:
+            g = AgentGroup("twod", s0[lo:hi], P.InvPendulumBicycleParameters(), destqueues=queues[lo:hi], dtype=torch.float32)
+            eng = Engine([g], dtype=torch.float32, extent=extent, origin=origin, n_global=n, global_offset=lo,
+                         pair_mode="tiled", resort_every=2)
+            own = eng.payload[lo:hi].clone()
+            eng.payload.copy_(payload)
+            eng.payload[lo:hi].copy_(own)
+            eng.step(); eng.step()                      # spatial order of the initial box; items sorted by cost
+            tl = eng._tiles[0]
+            before = int(tl["item_cost"][:tl["n_items"]].max().item())
+            eng.payload[far, 0] += int(150.0 / eng.q_scale)   # the box of the next re-sort is 150 m wider
+            eng.step(); eng.step()                      # re-sort at pair call 2
+            after = int(tl["item_cost"][:tl["n_items"]].max().item())
+            eng.check_status()
+            return before, after
+        finally:
+            E._SHARD_TARGET_ORDER = old
+
+    before, after = max_costs("partition")
+    cb, ca = max_costs("curve")
+    report(test="shard_target_blocks_across_resort", max_item_cost_partition=[before, after], max_item_cost_curve=[cb, ca])
+    assert after <= 1.25 * before, (before, after)
+
+
 def _lockstep(engines, bounds, steps):
     """Step several shard engines that live in ONE process (one GPU) in lock step: after every step each
     engine's own payload rows are copied into the others' payload buffers -- what the exchange does across
