@@ -83,3 +83,37 @@ def test_balanced_spatial_partition():
     share = np.array([w[lo:hi].sum() for lo, hi in b]) / w.sum()
     assert np.abs(share - 0.125).max() < 0.01
     assert balanced_bounds(np.ones(10), 3) == shard_bounds(10, 3) or sum(hi - lo for lo, hi in balanced_bounds(np.ones(10), 3)) == 10
+
+
+def test_partition_order_keeps_a_shards_target_blocks_compact():
+    """Why a sharded engine visits its targets in the order of the agent numbering: a rank's
+    agents are a segment of the Hilbert curve they were numbered along, so 64 consecutive ones are always
+    neighbours; re-sorted along the curve of a bounding box that has moved by a few metres the same agents are
+    no longer a segment, and a few blocks of 64 consecutive ones span hundreds of metres -- the pair kernel
+    cannot cull anything for such a block."""
+    from cyclistsocialforce_b200.synthetic import spatial_order, synthetic_crowd
+
+    def block_radii(x, y):
+        nb = len(x) // 64
+        xs, ys = x[:nb * 64].reshape(nb, 64), y[:nb * 64].reshape(nb, 64)
+        return 0.5 * np.hypot(xs.max(axis=1) - xs.min(axis=1), ys.max(axis=1) - ys.min(axis=1))
+
+    n = 65536
+    s0, _ = synthetic_crowd(n, seed=1)
+    o = spatial_order(s0[:, 0], s0[:, 1])
+    x, y = s0[o, 0], s0[o, 1]
+    worst_resorted = 0.0
+    for lo, hi in ((0, 32768), (8192, 16384), (20000, 28192)):       # a half, an eighth, an unaligned eighth
+        xs, ys = x[lo:hi], y[lo:hi]
+        r0 = block_radii(xs, ys)
+        assert r0.max() < 1.5 * np.median(r0) and np.median(r0) < 30.0      # partition order: every block compact
+        for shift in (3.0, 10.0):           # the crowd's bounding box has grown by `shift` metres on one side
+            xa, ya = np.r_[x, x.min() - shift], np.r_[y, y.min() - 0.3 * shift]
+            oa = spatial_order(xa, ya)
+            rank = np.empty(len(xa), np.int64)
+            rank[oa] = np.arange(len(xa))
+            loc = np.argsort(rank[lo:hi], kind="stable")             # the shard's agents along the new curve
+            r1 = block_radii(xs[loc], ys[loc])
+            assert abs(np.median(r1) - np.median(r0)) < 2.0          # typical blocks are as compact as before ...
+            worst_resorted = max(worst_resorted, float(r1.max()))
+    assert worst_resorted > 200.0                                    # ... but some span the whole region
